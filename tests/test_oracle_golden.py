@@ -1,0 +1,196 @@
+"""Oracle vs fixtures minted from the reference's own code (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox, solver, spline, vector_field, wrapper
+
+TOL = dict(atol=1e-6, rtol=1e-6)        # the reference test's own tolerance (tests/...alignment.py:127-128)
+
+
+@pytest.fixture(scope="module")
+def fg_cases(golden_dir):
+    return torch.load(golden_dir / "fg_golden.pt")
+
+
+def _build(case):
+    B, K, C, H, HH, L = case["dims"]
+    m = vector_field.DiffusionModel(C, H, HH, L, input_option=case["input_option"],
+                                    noise_option=case["noise_option"])
+    ref_keys = {k: tuple(v.shape) for k, v in case["state_dict"].items()}
+    own_keys = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ref_keys == own_keys                      # same pin as the reference test :102-104
+    m.load_state_dict(case["state_dict"])
+    return m
+
+
+def test_fg_all_options_match_reference(fg_cases):
+    assert len(fg_cases) == 143
+    seen = set()
+    with torch.no_grad():
+        for case in fg_cases:
+            m = _build(case)
+            m.set_X(case["coeffs"], case["times"])
+            for i, t in enumerate(case["t"]):
+                f, g = m.f(t, case["y"]), m.g(t, case["y"])
+                assert torch.allclose(f, case["f"][i], **TOL), (case["input_option"], case["noise_option"])
+                assert torch.allclose(g, case["g"][i], **TOL, equal_nan=True), (case["input_option"], case["noise_option"])
+            seen.add((case["input_option"], case["noise_option"]))
+    assert len(seen) == 140
+
+
+def test_reference_test_fixture_recipe(fg_cases):
+    named = [c for c in fg_cases if "name" in c]
+    assert sorted(c["name"] for c in named) == ["gsde", "lnsde", "lsde"]
+    for c in named:
+        assert torch.isfinite(c["f"]).all() and torch.isfinite(c["g"]).all()
+        assert c["f"].shape == (1, 2, 4)
+
+
+def test_natural_spline_matches_in_tree_controldiffeq(golden_dir):
+    for c in torch.load(golden_dir / "spline_golden.pt"):
+        a, b, c2, d3 = spline.natural_cubic_spline_coeffs(c["times"], c["x"])
+        for own, ref in ((a, c["a"]), (b, c["b"]), (c2, c["two_c"]), (d3, c["three_d"])):
+            assert torch.allclose(own, ref, atol=1e-5, rtol=1e-5)
+        sp = spline.CubicSpline(torch.cat([c["a"], c["b"], c["two_c"], c["three_d"]], -1), c["times"])
+        ev = torch.stack([sp.evaluate(t) for t in c["tq"]])
+        assert torch.allclose(ev, c["evaluate"], **TOL)
+
+
+def test_interval_choice_equals_in_tree_rule():
+    # bucketize(t)-1 (torchcde) == (t > times).sum()-1 (controldiffeq/interpolate.py:263), both clamped
+    times = torch.tensor([0.0, 0.5, 1.25, 2.0, 3.5])
+    sp = spline.CubicSpline(torch.zeros(1, 4, 4), times)
+    for t in [-1.0, 0.0, 0.25, 0.5, 0.5001, 1.25, 3.4, 3.5, 9.0]:
+        _, idx = sp.interpret_t(torch.tensor(t))
+        want = int(((torch.tensor(t) > times).sum() - 1).clamp(0, 3))
+        assert int(idx) == want
+
+
+def test_hermite_interpolates_knots_and_is_c1_inside():
+    torch.manual_seed(0)
+    times = torch.tensor([0.0, 0.3, 1.0, 1.5, 2.7])
+    x = torch.randn(2, 5, 3, dtype=torch.float64)
+    co = spline.hermite_cubic_coefficients_with_backward_differences(x, times.double())
+    sp = spline.CubicSpline(co, times.double())
+    for k in range(5):
+        assert torch.allclose(sp.evaluate(times[k].double()), x[:, k], atol=1e-12)
+    # right end of interval k reproduces x[k+1] (left interval evaluated at full width)
+    C = 3
+    h = (times[1:] - times[:-1]).double()[None, :, None]
+    a, b, c2, d3 = co[..., :C], co[..., C:2 * C], co[..., 2 * C:3 * C], co[..., 3 * C:]
+    end = a + (b + (c2 / 2 + d3 * h / 3) * h) * h
+    assert torch.allclose(end, x[:, 1:], atol=1e-12)
+    # slope at the right end equals this interval's secant slope (backward difference), so the
+    # next interval starts with the same derivative
+    slope_end = b + (c2 + d3 * h) * h
+    sec = (x[:, 1:] - x[:, :-1]) / h
+    assert torch.allclose(slope_end, sec, atol=1e-10)
+    assert torch.allclose(b[:, 1:], sec[:, :-1], atol=1e-12)
+
+
+def test_hermite_nan_fill():
+    times = torch.arange(5.0)
+    x = torch.tensor([[float("nan"), 1.0, float("nan"), 3.0, float("nan")]]).T.unsqueeze(0)
+    co = spline.hermite_cubic_coefficients_with_backward_differences(x, times)
+    assert torch.allclose(co[0, :, 0], torch.tensor([1.0, 1.0, 2.0, 3.0]))
+
+
+def test_forward_wrappers_match_reference(golden_dir):
+    for c in torch.load(golden_dir / "forward_golden.pt"):
+        m = _build(c)
+        bm = solver.BrownianTable(c["dW"])
+        if c["kind"] == "classification":
+            z = wrapper.classification_latent(m, c["times"], c["coeffs"], c["final_index"], c["z0"], bm)
+        else:
+            m.set_X(c["coeffs"], c["times"])
+            init = torch.nn.Linear(c["dims"][2], c["dims"][3])
+            init.load_state_dict(c["initial_network"])
+            with torch.no_grad():
+                z0 = init(m.X.evaluate(c["times"][0]))
+            z = wrapper.streamed_latent(m, c["times"], c["coeffs"], z0, bm)[:, -c["output_time"]:, :]
+        assert z.shape == c["z"].shape
+        assert torch.allclose(z, c["z"], **TOL)
+
+
+# ---- solver restatement: closed-form / structural checks (torchsde parity is unpinned) ----
+
+class _OU(torch.nn.Module):
+    sde_type, noise_type = "ito", "diagonal"
+
+    def __init__(self, th, mu, sg):
+        super().__init__()
+        self.th, self.mu, self.sg = th, mu, sg
+
+    def f(self, t, y):
+        return self.th * (self.mu - y)
+
+    def g(self, t, y):
+        return torch.full_like(y, self.sg)
+
+
+def test_euler_on_ou_matches_hand_recursion_and_lerp():
+    ou = _OU(0.7, 0.2, 0.3)
+    ts = torch.tensor([0.0, 0.13, 0.25, 0.5])
+    dt = 0.1
+    steps = solver.step_times(ts, dt)
+    assert [round(b - a, 6) for a, b in steps] == [0.1] * 5
+    dW = torch.randn(len(steps), 4, 2, dtype=torch.float64) * dt ** 0.5
+    y0 = torch.ones(4, 2, dtype=torch.float64)
+    out = solver.sdeint(ou, y0, ts.double(), dt, solver.BrownianTable(dW))
+    ys, y = [y0], y0
+    for k in range(5):
+        y = y + 0.7 * (0.2 - y) * dt + 0.3 * dW[k]
+        ys.append(y)
+    assert torch.allclose(out[0], y0)
+    assert torch.allclose(out[1], ys[1] + (ys[2] - ys[1]) * 0.3, atol=1e-12)     # t=0.13 in (0.1,0.2)
+    assert torch.allclose(out[2], ys[2] + (ys[3] - ys[2]) * 0.5, atol=1e-12)     # t=0.25
+    assert torch.allclose(out[3], ys[5], atol=1e-12)                             # lands on the grid
+
+
+def test_step_plan_float32_sliver():
+    # linspace(0,1,64) with dt=min diff -> 64 steps, the last one clamped to ts[-1]
+    ts = torch.linspace(0, 1, 64)
+    dt = solver.solver_dt(ts)
+    st = solver.step_times(ts, dt)
+    assert len(st) == 64 and st[-1][1] == 1.0 and (st[-1][1] - st[-1][0]) < 0.5 * dt
+    ts = torch.linspace(0, 1, 20)
+    assert len(solver.step_times(ts, 0.05)) == 20
+
+
+class _GBM(torch.nn.Module):
+    sde_type, noise_type = "ito", "diagonal"
+
+    def f(self, t, y):
+        return 0.1 * y
+
+    def g(self, t, y):
+        return 0.4 * y
+
+
+def test_milstein_matches_closed_form_for_gbm():
+    ts = torch.tensor([0.0, 0.5], dtype=torch.float64)
+    dW = torch.randn(5, 3, 2, dtype=torch.float64) * 0.1 ** 0.5
+    y0 = torch.rand(3, 2, dtype=torch.float64) + 0.5
+    out = solver.sdeint(_GBM(), y0, ts, 0.1, solver.BrownianTable(dW), method="milstein")
+    y = y0
+    for k in range(5):
+        y = y + 0.1 * y * 0.1 + 0.4 * y * dW[k] + 0.5 * 0.4 * 0.4 * y * (dW[k] ** 2 - 0.1)
+    assert torch.allclose(out[-1], y, atol=1e-12)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [([0, 0, 0, 0], [0, 0], "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+           ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+           ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+            "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for c, k, want in kat:
+        r = philox.philox4x32_10(np.array([c], dtype=np.uint32), np.array([k], dtype=np.uint32))[0]
+        assert " ".join("%08x" % x for x in r) == want
+
+
+def test_philox_normal_reference_moments():
+    n = np.concatenate([philox.normals_reference(7, s, np.arange(64), 32).ravel() for s in range(40)])
+    assert abs(n.mean()) < 0.02 and abs(n.std() - 1) < 0.02
+    assert abs((n ** 3).mean()) < 0.08 and abs((n ** 4).mean() - 3) < 0.15
