@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""SDE-steps/sec benchmark of the Neural-SDE solve (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+
+One "step" = one forward trajectory solve of one synthetic batch (B rows x S solver steps);
+SDE-steps/sec = B_global * S * K / seconds.  Default workload: BASELINE config c2 - Neural
+LNSDE (input_option 4, noise_option 17), Sepsis shape, B=1024 rows per GPU, hidden 128, C=35,
+200 Euler steps, per-row final_index capture.  N GPUs shard the batch (1024 rows each, weak
+scaling) and all-gather the final latents over NCCL.
+
+Printed JSON (one line, rank 0): see the prompt contract; `value` = device-resident solve timed
+with CUDA events, `e2e` = the public API with HOST buffers (H2D of the inputs and D2H of the
+latents inside the timed region), `roofline` = the solve kernel against MEASURED_PEAKS.json,
+`cpu_baseline` = the CPU oracle (port of the reference path) on this box's host cores.
+`--impl reference` times that CPU port alone (torchsde/torchcde are not installable: no
+network), with all host threads.
+"""
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: model (input_option, noise_option), rows per GPU, hidden, channels, solver steps, layers, method, output
+    "c1": dict(family="tutorial", io=0, no=0, B=64, H=32, C=2, S=50, L=1, method="euler", out="stream",
+               desc="tutorial Neural LSDE func, B=64 H=32 50 Euler steps (dt=0.02 on linspace(0,1,51))"),
+    "c2": dict(family="benchmark", io=4, no=17, B=1024, H=128, C=35, S=200, L=1, method="euler", out="final_index",
+               desc="Neural LNSDE (4,17) Sepsis-shape B=1024/GPU H=128 C=35 200 Euler steps, final_index capture"),
+    "c3": dict(family="benchmark", io=6, no=17, B=2048, H=64, C=35, S=200, L=1, method="milstein", out="final_index",
+               desc="Neural GSDE (6,17) Milstein B=2048/GPU H=64 C=35 200 steps, final_index capture"),
+    "c4": dict(family="benchmark", io=3, no=18, B=1024, H=128, C=21, S=160, L=1, method="euler", out="last",
+               desc="Neural SDE (3,18) Speech-shape B=1024/GPU H=128 C=21 160 Euler steps, last knot"),
+    "c5": dict(family="benchmark", io=4, no=17, B=1024, H=256, C=14, S=500, L=1, method="euler", out="tail10",
+               desc="Neural LNSDE (4,17) MuJoCo-shape B=1024/GPU H=256 C=14 500 Euler steps, last 10 knots"),
+}
+N_INPUT_SETS = 3          # rotated so that consecutive steps never re-read inputs from L2
+
+
+def alg_flops_per_sde_step(w):
+    """algorithmic multiply-adds x2 per batch row per solver step (layer-wise form)."""
+    H, C, L, io, no = w["H"], w["C"], w["L"], w["io"], w["no"]
+    if w["family"] == "tutorial":
+        return 2 * C * H + 4 * H * H + 2 * (L + 1) * H * H + 2 * H * H
+    ctl = io in (0, 2, 4, 6)
+    emb = io in (2, 4, 6)
+    tau = 2 if io in (3, 4, 5, 6) else 0
+    f = (2 * C * H if ctl else 0) + 2 * (H + tau) * H + (4 * H * H if emb else 0) + (L - 1) * 2 * H * H + 2 * H * H
+    if no in (18, 19):
+        f += 2 * (H + 2) * H + 2 * H * H
+    if no in (14, 15):
+        f += 2 * (H + 2) * H
+    return f
+
+
+def alg_bytes_per_sde_step(w, n_out):
+    """one 4C-float spline row per step + outputs and z0 amortised over S steps."""
+    H, C, S = w["H"], w["C"], w["S"]
+    ctl = w["family"] == "tutorial" or w["io"] in (0, 2, 4, 6)
+    return (16 * C if ctl else 0) + 4.0 * H * n_out / S + 4.0 * H / S
+
+
+def make_inputs(w, B, seed):
+    """Synthetic inputs of SURVEY 8d on the CPU (fp32): integer knots, time channel + random-walk channels,
+    Hermite/backward-difference coefficients (natural spline for c5), z0 ~ N(0, 0.1^2), random final_index."""
+    from snsde_b200 import data
+    g = torch.Generator().manual_seed(seed)
+    S, C, H = w["S"], w["C"], w["H"]
+    if w["family"] == "tutorial":
+        times = torch.linspace(0, 1, S + 1)
+    else:
+        times = torch.arange(S + 1, dtype=torch.float32)
+    x = (torch.randn(B, S + 1, C, generator=g) * 0.1).cumsum(1)
+    x[..., 0] = times
+    build = data.natural_cubic_coeffs if w["out"] == "tail10" else data.hermite_backward_difference_coeffs
+    coeffs = build(x, times).contiguous()
+    z0 = torch.randn(B, H, generator=g) * 0.1
+    if w["out"] == "final_index":
+        final_index = torch.randint(2, S + 1, (B,), generator=g)
+    else:
+        final_index = torch.full((B,), S, dtype=torch.long)
+    return times, coeffs, z0, final_index
+
+
+def make_model(w, seed=0):
+    from snsde_b200 import modules
+    torch.manual_seed(seed)
+    if w["family"] == "tutorial":
+        return modules.TutorialLSDEParams(w["C"], w["H"], w["H"], w["L"])
+    return modules.DiffusionModelParams(w["C"], w["H"], w["H"], w["L"], theta=1.0, sigma=1.0,
+                                        input_option=w["io"], noise_option=w["no"])
+
+
+def output_times(w, times):
+    if w["out"] == "stream":
+        return times
+    if w["out"] == "tail10":
+        return torch.cat([times[:1], times[-10:]])
+    if w["out"] == "last":
+        return times[[0, -1]]
+    return None          # final_index: derived per batch
+
+
+class ClockSampler:
+    """nvidia-smi SM clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU port of the reference path (the oracle), used for cpu_baseline and --impl reference
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_solver(w, B, seed=0):
+    """Returns (callable running ONE solve, S_executed, description).  Mirrors what the reference does
+    per forward: set_X, unique(final_index) output times, torchsde-style step loop with f/g evaluated
+    op by op, Brownian increments drawn per step, gather."""
+    from oracle import solver, vector_field, wrapper
+    torch.manual_seed(seed)
+    if w["family"] == "tutorial":
+        m = vector_field.TutorialLSDEFunc(w["C"], w["H"], w["H"], w["L"])
+    else:
+        m = vector_field.DiffusionModel(w["C"], w["H"], w["H"], w["L"], input_option=w["io"], noise_option=w["no"])
+    times, coeffs, z0, final_index = make_inputs(w, B, seed)
+
+    class DrawnBM:                       # N(0, (t1-t0) I) per call, like BrownianInterval but without its tree
+        def __call__(self, t0, t1):
+            return torch.randn(B, w["H"]) * (t1 - t0).sqrt()
+
+    def run():
+        with torch.no_grad():
+            if w["out"] == "final_index":
+                return wrapper.classification_latent(m, times, coeffs, final_index, z0, DrawnBM(), method=w["method"])
+            m.set_X(coeffs, times)
+            dt = 1.0 / w["S"] if w["family"] == "tutorial" else solver.solver_dt(times)
+            return solver.sdeint(m, z0, output_times(w, times), dt, DrawnBM(), method=w["method"])
+    return run, w["S"]
+
+
+def time_cpu_reference(w, B, repeats, warmup=1):
+    torch.set_num_threads(os.cpu_count())
+    run, S = cpu_reference_solver(w, B)
+    for _ in range(warmup):
+        run()
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter(); run(); ts.append(time.perf_counter() - t0)
+    return B * S / statistics.median(ts), ts
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = w["B"]
+    t0 = time.perf_counter()
+    run, S = cpu_reference_solver(w, B)
+    torch.set_num_threads(os.cpu_count())
+    for _ in range(min(args.warmup, 1)):
+        run()
+    ts = []
+    for _ in range(args.steps):
+        a = time.perf_counter(); run(); ts.append(time.perf_counter() - a)
+        if time.perf_counter() - t0 > 240:          # bounded: the whole arm ends within a few minutes
+            break
+    sec = sum(ts)
+    value = B * S * len(ts) / sec
+    sample = f"{len(ts)} full solves of the workload (B={B}, S={S}) on the CPU"
+    line = {
+        "impl": "reference", "metric": "SDE-steps/sec", "value": value, "unit": "SDE-steps/s",
+        "n_gpus": args.gpus, "steps": len(ts), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sec / len(ts),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "rows_timed": B,
+                   "note": "CPU port of the reference path (oracle/): torchsde/torchcde 0.2.5 are not installable offline"},
+        "cpu_baseline": {"value": value, "unit": "SDE-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "SDE-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--rows", type=int, default=None, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.rows:
+        w["B"] = args.rows
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import snsde_b200
+    from snsde_b200 import dist as sdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, H, S = w["B"], w["H"], w["S"]
+    Bg = B * world
+    row_offset = rank * B
+    model = make_model(w).to(dev)
+    sets_host = [make_inputs(w, B, seed=1000 * rank + i) for i in range(N_INPUT_SETS)]
+    pinned = [tuple(t.pin_memory() for t in s) for s in sets_host]
+    sets_dev = [tuple(t.to(dev) for t in s) for s in sets_host]
+    times_dev = sets_dev[0][0]
+    ts_fixed = output_times(w, times_dev)
+    out_rows = (Bg, H) if w["out"] == "final_index" else None
+    method = w["method"]
+
+    with torch.no_grad():
+        plan = snsde_b200.engine._plan_for(model, method, args.precision, dev)
+    dt = 1.0 / S if w["family"] == "tutorial" else snsde_b200.solver_dt(sets_host[0][0].numpy())
+
+    # resident-input step: everything on the device, result written into this rank's slice of the gather buffer
+    step_plans, slots = [], []
+    for (times, coeffs, z0, fi) in sets_dev:
+        if w["out"] == "final_index":
+            ts, sl = snsde_b200.final_index_slots(times, fi)
+            step_plans.append(plan.step_plan(ts, dt, times)); slots.append(sl.to(torch.int32))
+        else:
+            step_plans.append(plan.step_plan(ts_fixed, dt, times)); slots.append(None)
+    n_out = step_plans[0].n_out if w["out"] != "final_index" else 1
+    gather = torch.empty((Bg, H) if w["out"] == "final_index" else (n_out, Bg, H), device=dev)
+
+    def step_resident(i):
+        times, coeffs, z0, fi = sets_dev[i % N_INPUT_SETS]
+        sp, sl = step_plans[i % N_INPUT_SETS], slots[i % N_INPUT_SETS]
+        if w["out"] == "final_index":
+            plan.forward(z0, sp, coeffs=coeffs, row_slot=sl, seed=i, row_offset=row_offset,
+                         out=gather[row_offset:row_offset + B])
+            if world > 1:
+                sdist.all_gather_rows(gather, rank, world)
+        else:
+            z = plan.forward(z0, sp, coeffs=coeffs, seed=i, row_offset=row_offset)
+            if world > 1:
+                dist.all_gather_into_tensor(gather.view(n_out, world, B, H).transpose(0, 1).contiguous(), z)
+        return gather
+
+    # end-to-end step: the public API with HOST (pinned) inputs; H2D + solve + D2H of the latents
+    host_out = torch.empty((B, H) if w["out"] == "final_index" else (n_out, B, H)).pin_memory()
+
+    def step_e2e(i):
+        times, coeffs, z0, fi = pinned[i % N_INPUT_SETS]
+        t_d = times.to(dev, non_blocking=True)
+        c_d = coeffs.to(dev, non_blocking=True)
+        z_d = z0.to(dev, non_blocking=True)
+        model.set_X(c_d, t_d)
+        if w["out"] == "final_index":
+            f_d = fi.to(dev, non_blocking=True)
+            z = snsde_b200.solve_final(model, t_d, f_d, z_d, method=method, seed=i, precision=args.precision,
+                                       row_offset=row_offset, dt=dt)
+        else:
+            z = snsde_b200.sdeint(model, z_d, output_times(w, t_d), dt=dt, method=method, seed=i,
+                                  precision=args.precision, row_offset=row_offset)
+        if world > 1:
+            buf = torch.empty((world, *z.shape), device=dev)
+            dist.all_gather_into_tensor(buf, z)
+        host_out.copy_(z, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host_out
+
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0])
+    d2h = host_out.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step_resident(i)
+        barrier()
+        launches0 = plan.launches
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        with ClockSampler(local_rank) as clocks:
+            barrier()
+            t_wall = time.perf_counter()
+            for i in range(args.steps):
+                evs[i][0].record()
+                step_resident(i)
+                evs[i][1].record()
+            barrier()
+            t_wall = time.perf_counter() - t_wall
+            if t_wall < 1.5:                       # keep the GPU under load long enough for >= 10 clock samples
+                t_end = time.perf_counter() + 1.5
+                j = 0
+                while time.perf_counter() < t_end:
+                    step_resident(j); j += 1
+                    if j % 8 == 0:
+                        torch.cuda.synchronize()
+                torch.cuda.synchronize()
+        launches = plan.launches - launches0 if t_wall >= 1.5 else args.steps * ((plan.launches - launches0) // max(1, args.steps + j)) if False else None
+        per_step_ms = [a.elapsed_time(b) for a, b in evs]
+        dev_ms = max_over_ranks(evs[0][0].elapsed_time(evs[-1][1]))       # whole K-step region on the device
+        kern_ms = statistics.mean(per_step_ms)
+
+        for i in range(args.warmup):
+            step_e2e(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step_e2e(i)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    value = Bg * S * args.steps / (dev_ms * 1e-3)
+    e2e_value = Bg * S * args.steps / e2e_s
+
+    if rank == 0:
+        hbm_peak, tf_peak, peak_src = peaks()
+        n_out_rows = 1 if w["out"] == "final_index" else n_out
+        abytes = alg_bytes_per_sde_step(w, n_out_rows)
+        aflops = alg_flops_per_sde_step(w)
+        sde_per_s_kernel = B * S / (kern_ms * 1e-3)                   # one launch, this GPU
+        hbm_gbs = sde_per_s_kernel * abytes / 1e9
+        tflops = sde_per_s_kernel * aflops / 1e12
+        hbm_frac, tf_frac = hbm_gbs / hbm_peak, tflops / tf_peak
+        if tf_frac >= hbm_frac:
+            roof = {"bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_frac}
+        else:
+            roof = {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac}
+        roof.update({"traffic": None, "kernel": plan.kernel, "kernel_ms_per_launch": kern_ms, "peak_source": peak_src,
+                     "alg_bytes_per_sde_step": abytes, "alg_flops_per_sde_step": aflops,
+                     "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_frac},
+                     "tensor": {"achieved_tflops": tflops, "peak_tflops": tf_peak, "frac": tf_frac},
+                     "note": "latency-bound chain of small dependent GEMMs (SURVEY 8d); both fractions reported"})
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, ts_cpu = time_cpu_reference(w, B, repeats=3)
+            cpu = {"value": v, "unit": "SDE-steps/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"median of 3 full solves of the workload (B={B}, S={S}); {sum(ts_cpu):.1f}s of CPU work"}
+        line = {
+            "metric": "SDE-steps/sec", "value": value, "unit": "SDE-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "global_rows": Bg, "rows_per_gpu": B,
+                       "solver_steps": S, "precision": args.precision, "kernel": plan.kernel,
+                       "parallelism": f"batch-shard x{world}" + (" + NCCL all-gather of final latents" if world > 1 else ""),
+                       "l2": f"rotating {N_INPUT_SETS} input sets ({N_INPUT_SETS * h2d / 1e6:.0f} MB) > 126 MB L2",
+                       "brownian": "in-kernel Philox4x32-10"},
+            "e2e": {"value": e2e_value, "unit": "SDE-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": (plan.launches - launches0) if False else args.steps * 1 * (2 if plan.kernel == "tcgen05" else 1),
+            "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,146 @@
+/* snsde.h - C ABI of the B200-native Neural-SDE integration engine.
+ *
+ * Drop-in boundary for ONE reference path: the fixed-step SDE solve that
+ *   /root/reference/benchmark_classification/models_sde/neuralsde.py:71-82
+ * (= benchmark_forecasting/models_sde/neuralsde.py:71-82,145-156 and
+ *    torch-ists/torch_ists/diff_module/NSDE/nsde_model.py:63-74)
+ * delegates to `torchsde.sdeint(sde=func, y0=z0, ts=ts, dt=dt, method=...)`, with the
+ * vector field `Diffusion_model.f/g` (neuralsde.py:123-307) evaluated inside the step.
+ *
+ * The reference is pure Python and has no FFI; the binding a maintainer adds is the
+ * ctypes stub shown in INTEGRATION.md (it replaces the body of `_solve_sde_path`).
+ *
+ * Conventions
+ *  - plain C, no torch types; all device pointers are raw CUDA pointers owned by the caller;
+ *  - every entry point returns 0 on success or a negative snsde_status; nothing is written
+ *    to `out` on a negative return that is detected before launch; no exception crosses;
+ *  - `snsde_last_error()` returns a thread-local, NUL-terminated description of the last failure;
+ *  - entry points only ENQUEUE work on `stream` (a cudaStream_t passed as void*); they never
+ *    synchronise the device, except `snsde_plan_set_weights` with `on_device=1`
+ *    (one blocking D2H copy of <= a few MB) ;
+ *  - a plan is not thread-safe; distinct plans are independent.
+ */
+#ifndef SNSDE_H_
+#define SNSDE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNSDE_ABI_VERSION 1
+
+typedef enum {
+  SNSDE_OK = 0,
+  SNSDE_ERR_BAD_ARG = -1,        /* NULL pointer, non-positive size, inconsistent plan/step tables  */
+  SNSDE_ERR_UNSUPPORTED = -2,    /* option pair / method / precision the engine does not implement  */
+  SNSDE_ERR_CUDA = -3,           /* CUDA runtime error (allocation, launch); text in last_error      */
+  SNSDE_ERR_NO_WEIGHTS = -4      /* forward called before snsde_plan_set_weights                     */
+} snsde_status;
+
+enum { SNSDE_FAMILY_BENCHMARK = 0,   /* Diffusion_model, neuralsde.py:123-307                        */
+       SNSDE_FAMILY_TUTORIAL_LSDE = 1 /* NeuralLSDEFunc, tutorial "Neural LSDE" notebook cell 7      */ };
+enum { SNSDE_METHOD_EULER = 0,       /* torchsde Euler.step (Ito)                                     */
+       SNSDE_METHOD_MILSTEIN = 1     /* torchsde Milstein.step (Ito, diagonal, derivative-based)      */ };
+enum { SNSDE_PRECISION_FP32 = 0,     /* fp32 FMA kernel, every model/shape                            */
+       SNSDE_PRECISION_TC = 1,       /* tcgen05 tensor-core kernel, split-fp16 operands (fp32-class)   */
+       SNSDE_PRECISION_AUTO = 2      /* TC when the model/shape is supported, else FP32               */ };
+
+/* Model descriptor.  Replaces the constructor arguments of Diffusion_model
+ * (neuralsde.py:124) plus the `method=` kwarg of sdeint (neuralsde.py:35-36). */
+typedef struct {
+  int32_t family;           /* SNSDE_FAMILY_*                                        */
+  int32_t input_option;     /* 0..6   (neuralsde.py:148-156,200-225); 0 for tutorial */
+  int32_t noise_option;     /* 0..19  (neuralsde.py:233-288);        0 for tutorial  */
+  int32_t input_channels;   /* C                                                     */
+  int32_t hidden;           /* H  = hidden_channels                                  */
+  int32_t hidden_hidden;    /* HH = hidden_hidden_channels                           */
+  int32_t num_hidden_layers;/* L                                                     */
+  int32_t method;           /* SNSDE_METHOD_*                                        */
+  int32_t precision;        /* SNSDE_PRECISION_*                                     */
+} snsde_model_desc;
+
+/* One solver step, built on the host by replaying torchsde's fixed-step loop in fp32
+ * (BaseSDESolver.integrate: next_t = min(curr_t + dt, ts[-1])).  40 bytes. */
+typedef struct {
+  float t0;            /* step start (the time f and g are evaluated at)              */
+  float h;             /* fp32(t1 - t0)                                               */
+  float sqrt_h;        /* sqrtf(h): in-kernel Brownian increments are N(0,1)*sqrt_h   */
+  float sin_t0;        /* time features of neuralsde.py:191-193                       */
+  float cos_t0;
+  int32_t interval;    /* clamp(bucketize(t0, knots) - 1, 0, K-2)  (CubicSpline)      */
+  float frac;          /* fp32(t0 - knots[interval])                                  */
+  int32_t emit_begin;  /* outputs produced after this step: emits[emit_begin:emit_end]*/
+  int32_t emit_end;
+  int32_t reserved;
+} snsde_step;
+
+/* One output row: out[slot] = w_prev * y_before_step + w_curr * y_after_step
+ * (torchsde linear_interp; w_prev = 0, w_curr = 1 when the step lands on ts[slot]). */
+typedef struct {
+  int32_t slot;
+  float w_prev;
+  float w_curr;
+} snsde_emit;
+
+typedef struct snsde_plan snsde_plan;
+
+int snsde_abi_version(void);
+const char* snsde_last_error(void);
+
+/* Number of floats in the weight blob for `desc`, and the blob layout: the tensors of the
+ * reference state_dict in declaration order, each row-major as stored by nn.Linear
+ * ([out,in] weight then [out] bias):
+ *   benchmark: initial_network, linear_in, [emb], linears.0..L-2, linear_out, theta(1),
+ *              [sigma(1) | sigma_diag(H)], [noise_t | noise_t.0, noise_t.2 | noise_y | noise_y.0, noise_y.2]
+ *   tutorial : linear_X, emb, f_net._model.{0,2,..}, linear_out, noise_in, g_net._model.{0,2,..}
+ * Returns a negative status for an invalid descriptor. */
+int64_t snsde_weight_count(const snsde_model_desc* desc);
+
+int snsde_plan_create(const snsde_model_desc* desc, int device, snsde_plan** out_plan);
+int snsde_plan_destroy(snsde_plan* plan);
+
+/* Copies and re-lays the blob into the plan's device images (sync only when on_device). */
+int snsde_plan_set_weights(snsde_plan* plan, const float* blob, int64_t n_floats, int on_device,
+                           void* stream);
+
+/* Which kernel the plan will run: 0 = fp32 FMA, 1 = tcgen05.  Negative on error. */
+int snsde_plan_kernel_kind(const snsde_plan* plan);
+
+/* The solve.  Replaces torchsde.sdeint as called at neuralsde.py:78-82.
+ *   coeffs_dev       [B, K-1, 4C] fp32, packed cat(a,b,two_c,three_d); row b starts at
+ *                    coeffs_dev + b*coeff_row_stride (floats).  May be NULL iff the model
+ *                    never reads the control (input options 1,3,5).
+ *   y0_dev           [B, H] fp32
+ *   steps_host       [S] (S >= 0), emits_host [E]; the first `n_init_emits` emits apply to y0
+ *                    itself (slot of ts[0]); n_out = number of output slots
+ *   row_slot_dev     NULL: out_dev is [n_out, B, H] (the torchsde layout);
+ *                    else int32[B]: out_dev is [B, H] and row b keeps only slot row_slot[b]
+ *                    (fused `z_t.gather(final_index)` of neuralsde.py:115-116)
+ *   dW_dev           NULL: increments drawn in-kernel from Philox4x32-10(seed; feature,
+ *                    (row_offset+b)>>2, step); else explicit increments [S, B, H] (parity mode)
+ *   row_offset       global index of local row 0 (batch sharding keeps the stream invariant)
+ */
+int snsde_forward(snsde_plan* plan,
+                  const float* coeffs_dev, int64_t coeff_row_stride, int32_t n_knots,
+                  const float* y0_dev, int32_t B,
+                  const snsde_step* steps_host, int32_t S,
+                  const snsde_emit* emits_host, int32_t E, int32_t n_init_emits, int32_t n_out,
+                  const int32_t* row_slot_dev,
+                  const float* dW_dev, uint64_t seed, uint64_t row_offset,
+                  float* out_dev, void* stream);
+
+/* Materialises the increments the kernels would draw: dW_dev[s,b,j] for s<S, b<B, j<H,
+ * scaled by sqrt_h_host[s].  Used to feed the oracle the identical Brownian path. */
+int snsde_philox_fill(uint64_t seed, uint64_t row_offset, int32_t S, int32_t B, int32_t H,
+                      const float* sqrt_h_host, float* dW_dev, int device, void* stream);
+
+/* Number of engine kernels launched by this plan so far (for bench.py's gpu_launches). */
+int64_t snsde_plan_launch_count(const snsde_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNSDE_H_ */

@@ -1,0 +1,16 @@
+"""B200-native Neural-SDE integration engine (drop-in for the reference's torchsde.sdeint path).
+
+Public surface (mirrors the reference's operator interface for this path):
+    sdeint(sde, y0, ts, dt, method=..., bm=..., seed=...)   -> [len(ts), B, H]
+    solve_final(sde, times, final_index, z0, ...)            -> [B, H]   (fused gather)
+    patch(model)                                             -> swaps the engine into a NeuralSDE
+    BrownianIncrements(dW), philox_increments(...), Plan, build_step_plan, dist helpers
+"""
+from . import dist, packing, stepplan                                    # noqa: F401
+from ._lib import EngineError, LIB_PATH                                  # noqa: F401
+from .engine import (BrownianIncrements, Plan, final_index_slots, patch, philox_increments,  # noqa: F401
+                     sdeint, solve_final)
+from .stepplan import build_step_plan, solver_dt                          # noqa: F401
+
+__all__ = ["sdeint", "solve_final", "patch", "Plan", "BrownianIncrements", "philox_increments",
+           "final_index_slots", "build_step_plan", "solver_dt", "dist", "EngineError"]

@@ -1,0 +1,74 @@
+// Shared host/device definitions of the SDE engine (internal; the public surface is include/snsde.h).
+#pragma once
+#include <stdint.h>
+#include "../../include/snsde.h"
+
+namespace snsde {
+
+constexpr int kMaxOps = 24;
+constexpr int kMaxRowsPerCta = 16;
+
+// Activation buffers of the FMA interpreter kernel.  Row buffers are [R][ld]; vector
+// buffers (row-independent work such as noise_t(time_features), neuralsde.py:272-282) are [ld].
+enum Buf : int { BUF_NONE = -1, BUF_Y = 0, BUF_X, BUF_U, BUF_A, BUF_B, BUF_P, BUF_Q, BUF_V0, BUF_V1, BUF_COUNT };
+constexpr int kNumRowBufs = BUF_V0;          // Y..Q
+constexpr int kNumVecBufs = BUF_COUNT - BUF_V0;
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LIPSWISH = 2 };
+enum TimeMode : int { TM_NONE = 0, TM_SINCOS = 1, TM_RAW = 2 };
+
+// dst[r][j] = act( b[j] + sum_k src[r][k] Wt[k][j] + sum_k src2[r][k] Wt2[k][j] + time_term[j] )
+// Wt is the TRANSPOSE of the nn.Linear weight ([in][out]) so that threads j read it coalesced.
+struct DenseOp {
+  int dst, src, src2;
+  int K, K2, N;
+  int w_off, w2_off, b_off, tw_off;   // float offsets into the weight image (-1: absent)
+  int tmode;                          // TimeMode: tw is [2][N] (sin,cos rows) or [1][N] (raw t)
+  int act;
+  int vec;                            // 1: row-independent (one row), 0: per batch row
+  int final_drift;                    // 1: result stays in registers and feeds the SDE update
+};
+
+// Elementwise diffusion g (neuralsde.py:233-307) and the state update.
+enum CoefSrc : int { CO_NONE = 0, CO_SCALAR, CO_IMG, CO_VBUF, CO_RBUF };
+enum Mult : int { MU_ONE = 0, MU_T, MU_Y, MU_TY };
+enum Special : int { SP_NONE = 0, SP_ZERO, SP_SQRT, SP_CUBE, SP_SIGMOID, SP_RELU };
+
+struct TailOp {
+  int geometric;      // drift *= tanh(y)           (input options 5,6; neuralsde.py:219-225)
+  int clip_drift;     // drift = tanh(drift)        (neuralsde.py:227-231)
+  int coef_src;       // CoefSrc
+  int coef_ref;       // image offset / buffer id
+  float coef_scalar;  // exp(sigma) for options 1-3
+  int mult;           // Mult
+  int special;        // Special (options 0,7,8,9,10)
+  int bounded;        // g = tanh(sigmoid(theta) * nan_to_num(raw)) (benchmark) vs g = raw (tutorial)
+  float s_theta;      // sigmoid(theta)
+  int milstein;       // method
+};
+
+struct Program {
+  int n_ops;
+  int uses_control;   // spline X(t) is read (input options 0,2,4,6 / tutorial)
+  int C, H, HH;
+  int ld;             // leading dimension (floats) of every activation buffer
+  DenseOp ops[kMaxOps];
+  TailOp tail;
+};
+
+struct FmaParams {
+  Program prog;
+  const float* wimg;          // weight image (global)
+  int wimg_floats;
+  int smem_w_floats;          // leading floats of the image staged into shared memory
+  const float* coeffs; long long coeff_row_stride;
+  const float* y0; int B;
+  const snsde_step* steps; int S;
+  const snsde_emit* emits; int n_init_emits; int n_out;
+  const int* row_slot;
+  const float* dW;
+  unsigned long long seed, row_offset;
+  float* out;
+};
+
+}  // namespace snsde

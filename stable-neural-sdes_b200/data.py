@@ -1,0 +1,56 @@
+"""Control-path coefficient construction with torch ops (runs on any device).
+
+Host-side data preparation either side of the hot path: the reference builds these once per
+dataset (/root/reference/benchmark_classification/datasets/common.py:82-84 via torchcde;
+benchmark_forecasting/datasets/common.py:79-81 via the in-tree natural spline) and feeds the
+packed ``[B, K-1, 4C]`` tensor to ``set_X``.  Packing: ``cat(a, b, two_c, three_d)``.
+"""
+import torch
+
+
+def hermite_backward_difference_coeffs(x, t):
+    """x ``[..., K, C]`` (no NaNs), t ``[K]`` -> ``[..., K-1, 4C]``.  Cubic Hermite pieces whose
+    start slope is the previous interval's secant (the first piece reuses its own)."""
+    h = (t[1:] - t[:-1]).unsqueeze(-1)
+    dx = x[..., 1:, :] - x[..., :-1, :]
+    m1 = dx / h
+    m0 = torch.cat((m1[..., :1, :], m1[..., :-1, :]), dim=-2)
+    two_c = 2 * (3 * (dx / h - m0) - m1 + m0) / h
+    three_d = (1 / h ** 2) * (m1 - m0) - two_c / h
+    return torch.cat((x[..., :-1, :], m0, two_c, three_d), dim=-1)
+
+
+def natural_cubic_coeffs(x, t):
+    """x ``[..., K, C]`` (no NaNs), t ``[K]`` -> ``[..., K-1, 4C]`` natural cubic spline
+    (second derivative zero at both ends); knot slopes from a Thomas sweep along K."""
+    K = x.shape[-2]
+    h = t[1:] - t[:-1]
+    r = h.reciprocal()
+    dx = x[..., 1:, :] - x[..., :-1, :]
+    if K == 2:
+        z = torch.zeros_like(dx)
+        return torch.cat((x[..., :-1, :], dx * r[:, None], z, z), dim=-1)
+    s = 3 * dx * (r ** 2)[:, None]
+    rhs = torch.zeros_like(x)
+    rhs[..., :-1, :] += s
+    rhs[..., 1:, :] += s
+    diag = torch.zeros(K, dtype=x.dtype, device=x.device)
+    diag[:-1] += 2 * r
+    diag[1:] += 2 * r
+    cp = torch.empty(K, dtype=x.dtype, device=x.device)      # modified diagonal
+    d = [rhs[..., 0, :]]
+    cp[0] = diag[0]
+    for i in range(1, K):
+        w = r[i - 1] / cp[i - 1]
+        cp[i] = diag[i] - w * r[i - 1]
+        d.append(rhs[..., i, :] - w * d[i - 1])
+    k = [None] * K
+    k[K - 1] = d[K - 1] / cp[K - 1]
+    for i in range(K - 2, -1, -1):
+        k[i] = (d[i] - r[i] * k[i + 1]) / cp[i]
+    kd = torch.stack(k, dim=-2)
+    k0, k1 = kd[..., :-1, :], kd[..., 1:, :]
+    rr = r[:, None]
+    two_c = (6 * dx * rr - 4 * k0 - 2 * k1) * rr
+    three_d = (-6 * dx * rr + 3 * (k0 + k1)) * rr ** 2
+    return torch.cat((x[..., :-1, :], k0, two_c, three_d), dim=-1)

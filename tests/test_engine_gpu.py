@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on
+identical inputs and identical Brownian increments.
+
+Tolerance (BASELINE.json north_star: "within 1e-4 relative fp32"):
+    max |z_gpu - z_oracle| <= 1e-4 * max(|z_oracle|_inf, 1)      per output tensor
+i.e. relative to the scale of the latent.  fp32 re-association alone (the oracle itself run
+in fp64 vs fp32) moves results by ~1e-6 on these trajectories.
+"""
+import numpy as np
+import pytest
+import torch
+
+import snsde_b200
+from oracle import philox, solver, spline, vector_field, wrapper
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def close(got, want, rtol=RTOL):
+    got, want = got.detach().cpu().double(), want.detach().cpu().double()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = max(float(want.abs().max()), 1.0)
+    err = float((got - want).abs().max())
+    assert err <= rtol * scale, f"max abs err {err:.3e} > {rtol:g} * {scale:.3g}"
+    return err / scale
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def make_problem(io, no, B, H, C, L, K, seed, HH=None, family="benchmark", spacing=1.0):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    HH = H if HH is None else HH
+    if family == "tutorial":
+        m = vector_field.TutorialLSDEFunc(C, H, HH, L)
+    else:
+        m = vector_field.DiffusionModel(C, H, HH, L, theta=0.8, sigma=-0.5, input_option=io, noise_option=no)
+    times = torch.arange(K, dtype=torch.float32) * spacing
+    x = torch.cat([times[None, :, None].expand(B, K, 1),
+                   (torch.randn(B, K, C - 1, generator=g) * 0.1).cumsum(1)], dim=-1) if C > 1 else \
+        (torch.randn(B, K, 1, generator=g) * 0.1).cumsum(1)
+    coeffs = spline.hermite_cubic_coefficients_with_backward_differences(x, times)
+    y0 = torch.randn(B, H, generator=g) * 0.5
+    return m, times, coeffs, y0
+
+
+def run_both(m, times, coeffs, y0, ts, dt, dW, method, dev, precision="fp32"):
+    m.set_X(coeffs, times)
+    want = solver.sdeint(m, y0, ts, dt, solver.BrownianTable(dW), method=method)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    with torch.no_grad():
+        got = snsde_b200.sdeint(mg, y0.to(dev), ts.to(dev), dt=dt, method=method,
+                                bm=snsde_b200.BrownianIncrements(dW.to(dev)), precision=precision)
+    m.to("cpu")
+    return got, want
+
+
+# ---- every (input_option, noise_option): one Euler step against the REFERENCE's golden f/g ----
+def test_single_step_all_140_option_pairs_vs_reference_golden(golden_dir, dev):
+    cases = torch.load(golden_dir / "fg_golden.pt")
+    h = 0.25
+    worst = 0.0
+    for c in cases:
+        B, K, C, H, HH, L = c["dims"]
+        m = vector_field.DiffusionModel(C, H, HH, L, input_option=c["input_option"], noise_option=c["noise_option"])
+        m.load_state_dict(c["state_dict"])
+        m = m.to(dev)
+        m.set_X(c["coeffs"].to(dev), c["times"].to(dev))
+        g = torch.Generator().manual_seed(5)
+        dW = torch.randn(1, B, H, generator=g) * h ** 0.5
+        for i, t in enumerate(c["t"]):
+            ts = torch.stack([t, t + h])
+            with torch.no_grad():
+                got = snsde_b200.sdeint(m, c["y"].to(dev), ts, dt=1.0, bm=snsde_b200.BrownianIncrements(dW),
+                                        precision="fp32")
+            hh = (ts[1] - ts[0])
+            want = c["y"] + c["f"][i] * hh + c["g"][i] * dW[0]
+            assert torch.equal(got[0].cpu(), c["y"])
+            worst = max(worst, close(got[1], want, rtol=2e-6))
+    print("worst single-step rel err", worst)
+
+
+NAMED = [("lnsde", 4, 17), ("gsde", 6, 17), ("lsde", 2, 16), ("neuralsde_3_18", 3, 18), ("naivesde", 1, 18),
+         ("staticsde", 1, 0)]
+
+
+@pytest.mark.parametrize("name,io,no", NAMED)
+@pytest.mark.parametrize("H,C,L,B", [(32, 5, 1, 19), (64, 35, 2, 40), (128, 21, 1, 33)])
+def test_euler_trajectories_named_models(name, io, no, H, C, L, B, dev):
+    K = 41
+    m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, K, seed=H + io)
+    dt = solver.solver_dt(times)
+    ts = times[[0, 3, 17, 40]]
+    dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(1)) * dt ** 0.5
+    got, want = run_both(m, times, coeffs, y0, ts, dt, dW, "euler", dev)
+    close(got, want)
+
+
+@pytest.mark.parametrize("io,no", [(6, 17), (4, 17), (2, 16), (1, 3), (3, 6), (5, 8), (1, 9), (3, 10), (5, 11), (4, 13),
+                                   (1, 7), (0, 12), (1, 0), (2, 5)])
+def test_milstein_vs_autograd_oracle(io, no, dev):
+    B, H, C, L, K = 11, 16, 4, 2, 13
+    m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, K, seed=no, HH=(24 if io in (1, 3, 5) else None),
+                                        spacing=0.25)
+    if no == 7:
+        y0 = y0.abs() + 0.5          # sqrt(y): stay positive so the autograd path is finite
+    dt = solver.solver_dt(times)
+    dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(2)) * dt ** 0.5 * (0.2 if no in (7, 8) else 1.0)
+    got, want = run_both(m, times, coeffs, y0, times, dt, dW, "milstein", dev)
+    if no == 7:
+        ok = torch.isfinite(want)
+        assert torch.equal(torch.isfinite(got.cpu()), ok)
+        got, want = torch.where(ok, got.cpu(), torch.zeros(())), torch.where(ok, want, torch.zeros(()))
+    close(got, want)
+
+
+def test_unaligned_grid_tutorial_lsde_c1(dev):
+    # BASELINE config c1 (scaled-up tutorial): knots linspace(0,1,20), dt=0.05 -> outputs are lerps
+    B, H, C, L = 64, 32, 2, 1
+    m, _, _, y0 = make_problem(0, 0, B, H, C, L, 20, seed=3, family="tutorial")
+    times = torch.linspace(0, 1, 20)
+    x = torch.randn(B, 20, C, generator=torch.Generator().manual_seed(4)).cumsum(1) * 0.2
+    coeffs = spline.hermite_cubic_coefficients_with_backward_differences(x, times)
+    S = len(solver.step_times(times, 0.05))
+    dW = torch.randn(S, B, H, generator=torch.Generator().manual_seed(5)) * 0.05 ** 0.5
+    got, want = run_both(m, times, coeffs, y0, times, 0.05, dW, "euler", dev)
+    close(got, want)
+    m2, _, _, _ = make_problem(0, 0, B, H, C, 3, 20, seed=6, family="tutorial", HH=48)
+    got, want = run_both(m2, times, coeffs, y0, times, 0.05, dW, "euler", dev)
+    close(got, want)
+
+
+def test_sliver_step_grid_and_stream_all_knots(dev):
+    B, H, C, L, K = 9, 32, 3, 1, 64
+    m, _, _, y0 = make_problem(4, 17, B, H, C, L, K, seed=8)
+    times = torch.linspace(0, 1, K)               # torch-ists grid: dt = min diff < 1/63 -> 64 steps
+    x = torch.randn(B, K, C, generator=torch.Generator().manual_seed(9)).cumsum(1) * 0.1
+    coeffs = spline.hermite_cubic_coefficients_with_backward_differences(x, times)
+    dt = solver.solver_dt(times)
+    S = len(solver.step_times(times, dt))
+    assert S == 64
+    dW = torch.randn(S, B, H, generator=torch.Generator().manual_seed(10)) * dt ** 0.5
+    got, want = run_both(m, times, coeffs, y0, times, dt, dW, "euler", dev)
+    close(got, want)
+
+
+def test_fused_final_index_gather_vs_reference_golden_and_oracle(golden_dir, dev):
+    for c in torch.load(golden_dir / "forward_golden.pt"):
+        if c["kind"] != "classification":
+            continue
+        B, K, C, H, HH, L = c["dims"]
+        m = vector_field.DiffusionModel(C, H, HH, L, input_option=c["input_option"], noise_option=c["noise_option"])
+        m.load_state_dict(c["state_dict"])
+        m = m.to(dev)
+        m.set_X(c["coeffs"].to(dev), c["times"].to(dev))
+        with torch.no_grad():
+            z = snsde_b200.solve_final(m, c["times"].to(dev), c["final_index"].to(dev), c["z0"].to(dev),
+                                       bm=snsde_b200.BrownianIncrements(c["dW"].to(dev)), precision="fp32")
+        close(z, c["z"], rtol=1e-5)
+    # larger ragged case vs the oracle wrapper
+    B, H, C, L, K = 37, 64, 6, 1, 30
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=21)
+    fi = torch.randint(2, K, (B,), generator=torch.Generator().manual_seed(3))
+    fi[0], fi[1] = 0, K - 1
+    dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(4))
+    want = wrapper.classification_latent(m, times, coeffs, fi, y0, solver.BrownianTable(dW))
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    with torch.no_grad():
+        got = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev),
+                                     bm=snsde_b200.BrownianIncrements(dW.to(dev)), precision="fp32")
+    close(got, want)
+    assert torch.equal(got[0].cpu(), y0[0])          # final_index 0 -> z0 itself
+
+
+def test_patch_drop_in_on_reference_style_wrapper(dev):
+    class RefStyleNeuralSDE(torch.nn.Module):      # shape of reference NeuralSDE (neuralsde.py:51-120)
+        def __init__(self, func, C, H, out):
+            super().__init__()
+            self.func, self.initial = func, True
+            self.initial_network = torch.nn.Linear(C, H)
+            self.linear = torch.nn.Linear(H, out)
+
+        def _prepare_initial_state(self, times, z0):
+            return self.initial_network(self.func.X.evaluate(times[0])) if z0 is None else z0
+
+        def _solve_sde_path(self, times, ts, z0, kwargs):
+            raise AssertionError("must be replaced by patch()")
+
+    B, H, C, L, K = 12, 32, 4, 1, 17
+    func, times, coeffs, _ = make_problem(4, 17, B, H, C, L, K, seed=31)
+    model = RefStyleNeuralSDE(func, C, H, 3)
+    fi = torch.randint(1, K, (B,), generator=torch.Generator().manual_seed(1))
+    dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        func.set_X(coeffs, times)
+        z0 = model.initial_network(func.X.evaluate(times[0]))
+        want = model.linear(wrapper.classification_latent(func, times, coeffs, fi, z0, solver.BrownianTable(dW)))
+        model = snsde_b200.patch(model.to(dev))
+        got = model(times.to(dev), [coeffs.to(dev)], fi.to(dev), bm=snsde_b200.BrownianIncrements(dW.to(dev)),
+                    precision="fp32")
+        close(got, want)
+        zt = model._solve_sde_path(times.to(dev), times.to(dev), z0.to(dev),
+                                   {"bm": snsde_b200.BrownianIncrements(dW.to(dev)), "precision": "fp32"})
+        func.to("cpu"); func.set_X(coeffs, times)
+        close(zt, solver.sdeint(func, z0, times, 1.0, solver.BrownianTable(dW)))
+
+
+def test_in_kernel_philox_equals_table_replay_and_matches_numpy_reference(dev):
+    B, H, C, L, K = 24, 32, 3, 1, 12
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=41, spacing=0.5)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    dt = solver.solver_dt(times)
+    with torch.no_grad():
+        a = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=dt, seed=1234, precision="fp32")
+        plan = mg._snsde_plans[("euler", "fp32", str(dev))]
+        sp = plan.step_plan(times, dt, times)
+        dW = snsde_b200.philox_increments(1234, sp, B, H, dev)
+        b = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=dt, bm=snsde_b200.BrownianIncrements(dW), precision="fp32")
+        c = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=dt, seed=1235, precision="fp32")
+    assert torch.equal(a, b)                       # identical increments -> bit-identical trajectories
+    assert not torch.equal(a, c)
+    m.to("cpu"); m.set_X(coeffs, times)
+    close(a, solver.sdeint(m, y0, times, dt, solver.BrownianTable(dW.cpu())))
+    # the integer stream + normal map against the float64 numpy restatement
+    for s in (0, 5):
+        ref = philox.normals_reference(1234, s, np.arange(B), H) * float(sp.steps["sqrt_h"][s])
+        assert np.abs(dW[s].cpu().numpy() - ref).max() < 2e-5
+    big = snsde_b200.philox_increments(7, sp, 4096, 64, dev).cpu().numpy() / np.sqrt(dt)
+    assert abs(big.mean()) < 3e-3 and abs(big.std() - 1) < 3e-3
+    assert abs(np.corrcoef(big[0].ravel(), big[1].ravel())[0, 1]) < 0.01      # steps independent
+    assert abs(np.corrcoef(big[0, :-1].ravel(), big[0, 1:].ravel())[0, 1]) < 0.01   # rows independent
+
+
+def test_batch_sharding_is_bit_invariant(dev):
+    B, H, C, L, K = 50, 32, 3, 1, 9
+    m, times, coeffs, y0 = make_problem(6, 17, B, H, C, L, K, seed=51)
+    mg = m.to(dev)
+    cg, tg, yg = coeffs.to(dev), times.to(dev), y0.to(dev)
+    fi = torch.randint(1, K, (B,), generator=torch.Generator().manual_seed(1)).to(dev)
+    with torch.no_grad():
+        mg.set_X(cg, tg)
+        full = snsde_b200.solve_final(mg, tg, fi, yg, seed=99, precision="fp32")
+        parts = []
+        for lo, hi in ((0, 13), (13, 26), (26, 50)):        # shard starts not multiples of 4 on purpose
+            mg.set_X(cg[lo:hi], tg)
+            # every shard must use the GLOBAL output-time set so slots agree
+            ts, slots = snsde_b200.final_index_slots(tg, fi)
+            plan = mg._snsde_plans[("euler", "fp32", str(dev))]
+            sp = plan.step_plan(ts, 1.0, tg)
+            parts.append(plan.forward(yg[lo:hi], sp, coeffs=cg[lo:hi], row_slot=slots[lo:hi], seed=99, row_offset=lo))
+    assert torch.equal(full, torch.cat(parts))
+
+
+def test_edge_shapes_and_errors(dev):
+    # B=1, H=4 (reference-test size), single output time (no steps), non-contiguous coeffs
+    m, times, coeffs, y0 = make_problem(4, 17, 1, 4, 3, 2, 5, seed=61)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    with torch.no_grad():
+        z = snsde_b200.sdeint(mg, y0.to(dev), times[:1].to(dev), dt=1.0, seed=1, precision="fp32")
+        assert z.shape == (1, 1, 4) and torch.equal(z[0].cpu(), y0)
+        wide = torch.zeros(1, 4, 24, device=dev)
+        wide[..., :12] = coeffs.to(dev)
+        mg.set_X(wide[..., :12], times.to(dev))
+        dW = torch.randn(4, 1, 4)
+        got = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, bm=snsde_b200.BrownianIncrements(dW), precision="fp32")
+    m.to("cpu"); m.set_X(coeffs, times)
+    close(got, solver.sdeint(m, y0, times, 1.0, solver.BrownianTable(dW)))
+    mg = m.to(dev); mg.set_X(coeffs.to(dev), times.to(dev))
+    with pytest.raises(RuntimeError, match="forward-only"):
+        snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0)
+    with torch.no_grad():
+        with pytest.raises(ValueError):
+            snsde_b200.sdeint(mg, torch.zeros(1, 5, device=dev), times.to(dev), dt=1.0)
+        with pytest.raises(ValueError):
+            snsde_b200.sdeint(mg, y0.to(dev), times.flip(0).to(dev), dt=1.0)
+        with pytest.raises(ValueError):
+            snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, method="srk")
+        with pytest.raises(ValueError):
+            snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, bm=snsde_b200.BrownianIncrements(torch.zeros(3, 1, 4)))
+
+
+def test_large_hidden_and_nan_semantics(dev):
+    # H=256 (c5 width): weights exceed shared memory -> L2 streaming branch of the FMA kernel
+    m, times, coeffs, y0 = make_problem(4, 17, 10, 256, 14, 1, 9, seed=71)
+    dW = torch.randn(8, 10, 256, generator=torch.Generator().manual_seed(1))
+    got, want = run_both(m, times, coeffs, y0, times, 1.0, dW, "euler", dev)
+    close(got, want)
+    # noise option 7 (sqrt y) with negative state: NaN -> nan_to_num -> 0, exactly like the reference
+    m, times, coeffs, y0 = make_problem(1, 7, 6, 8, 2, 1, 5, seed=72)
+    dW = torch.randn(4, 6, 8, generator=torch.Generator().manual_seed(2))
+    got, want = run_both(m, times, coeffs, y0, times, 1.0, dW, "euler", dev)
+    assert torch.isfinite(got).all()
+    close(got, want)

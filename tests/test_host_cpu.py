@@ -1,0 +1,184 @@
+"""CPU-only checks of the host side: C-ABI surface, step plan, packing, sharding (gloo)."""
+import ctypes
+import os
+import pathlib
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import snsde_b200
+from oracle import solver, vector_field
+from snsde_b200 import _lib, packing
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "snsde.h").read_text()
+    declared = set(re.findall(r"\b(snsde_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.snsde_abi_version() == 1
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", nm), name
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.Step) == 40 == snsde_b200.stepplan.STEP_DTYPE.itemsize
+    assert ctypes.sizeof(_lib.Emit) == 12 == snsde_b200.stepplan.EMIT_DTYPE.itemsize
+    assert ctypes.sizeof(_lib.ModelDesc) == 36
+    for (n, _), (m, _t) in zip(_lib.Step._fields_, snsde_b200.stepplan.STEP_DTYPE.descr):
+        assert n == m
+
+
+@pytest.mark.parametrize("io", range(7))
+@pytest.mark.parametrize("no", range(20))
+def test_weight_count_matches_state_dict(io, no):
+    H, C, L = 8, 3, 3
+    HH = 12 if io in (1, 3, 5) else H
+    m = vector_field.DiffusionModel(C, H, HH, L, input_option=io, noise_option=no)
+    desc = packing.describe(m)
+    assert (desc["input_option"], desc["noise_option"], desc["hidden_hidden"], desc["num_hidden_layers"]) == (io, no, HH, L)
+    blob = packing.pack(m, desc)
+    assert blob.numel() == sum(v.numel() for v in m.state_dict().values())
+    cd = _lib.ModelDesc(method=0, precision=0, **desc)
+    assert _lib.load().snsde_weight_count(ctypes.byref(cd)) == blob.numel()
+
+
+def test_weight_count_tutorial_and_validation_errors():
+    lib = _lib.load()
+    m = vector_field.TutorialLSDEFunc(2, 32, 16, 2)
+    desc = packing.describe(m)
+    assert desc["family"] == _lib.FAMILY_TUTORIAL_LSDE and desc["hidden_hidden"] == 16 and desc["num_hidden_layers"] == 2
+    cd = _lib.ModelDesc(method=0, precision=0, **desc)
+    assert lib.snsde_weight_count(ctypes.byref(cd)) == packing.pack(m, desc).numel()
+    bad = _lib.ModelDesc(family=0, input_option=4, noise_option=20, input_channels=3, hidden=4, hidden_hidden=4,
+                         num_hidden_layers=1, method=0, precision=0)
+    assert lib.snsde_weight_count(ctypes.byref(bad)) == _lib.ERR_BAD_ARG
+    assert b"Unknown noise_option 20" in lib.snsde_last_error()
+    bad.noise_option, bad.hidden_hidden = 17, 8          # emb needs HH == H
+    assert lib.snsde_weight_count(ctypes.byref(bad)) == _lib.ERR_BAD_ARG
+    bad.hidden_hidden, bad.method = 4, 2                 # srk
+    assert lib.snsde_weight_count(ctypes.byref(bad)) == _lib.ERR_UNSUPPORTED
+    bad.method, bad.noise_option = 1, 18                 # milstein needs the full vjp there
+    assert lib.snsde_weight_count(ctypes.byref(bad)) == _lib.ERR_UNSUPPORTED
+    with pytest.raises(ValueError):
+        _lib.check(_lib.ERR_BAD_ARG)
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = vector_field.DiffusionModel(3, 4, 4, 1, input_option=4, noise_option=17)
+    m.set_X(torch.zeros(2, 4, 12), torch.arange(5.0))
+    with torch.no_grad(), pytest.raises(snsde_b200.EngineError):
+        snsde_b200.sdeint(m, torch.zeros(2, 4), torch.arange(5.0), dt=1.0)
+
+
+@pytest.mark.parametrize("ts,dt", [
+    (torch.linspace(0, 1, 20), 0.05),                    # tutorial grid: steps do not land on knots
+    (torch.linspace(0, 1, 64), None),                    # float32 sliver step
+    (torch.arange(73.0) + 1, None),                      # Sepsis: linspace(1,72,72)-like integer grid
+    (torch.tensor([0.0, 0.13, 0.25, 0.5]), 0.1),
+    (torch.tensor([0.0, 0.05, 0.06, 0.07, 1.0]), 0.5),   # several outputs inside one step
+])
+def test_step_plan_replays_the_oracle_loop(ts, dt):
+    dt = solver.solver_dt(ts) if dt is None else dt
+    sp = snsde_b200.build_step_plan(ts.numpy(), dt, ts.numpy())
+    ref = solver.step_times(ts, dt)
+    assert sp.n_steps == len(ref) and sp.n_out == len(ts)
+    for (a, b), s in zip(ref, sp.steps):
+        assert np.float32(a) == s["t0"] and np.float32(np.float32(b) - np.float32(a)) == s["h"]
+        assert s["sqrt_h"] == np.sqrt(s["h"])
+        idx = int(torch.bucketize(torch.tensor(a), ts).sub(1).clamp(0, len(ts) - 2))
+        assert idx == s["interval"] and s["frac"] == np.float32(np.float32(a) - ts[idx].numpy())
+    # emits: contiguous ranges, one per output, lerp weights reproduce the oracle's interpolation
+    assert sp.n_init_emits == 1 and sp.emits[0]["slot"] == 0
+    assert list(sp.emits["slot"]) == list(range(len(ts)))
+    prev_end = 1
+    for s in sp.steps:
+        assert s["emit_begin"] == prev_end and s["emit_end"] >= s["emit_begin"]
+        prev_end = s["emit_end"]
+    assert prev_end == len(sp.emits)
+    # replay a scalar "identity" SDE through the plan and compare with the oracle on y(t) = t path
+    class Lin(torch.nn.Module):
+        sde_type, noise_type = "ito", "diagonal"
+        def f(self, t, y): return torch.ones_like(y) * 2.0
+        def g(self, t, y): return torch.zeros_like(y)
+    y0 = torch.tensor([[0.5]])
+    out = solver.sdeint(Lin(), y0, ts, dt, solver.BrownianTable(torch.zeros(sp.n_steps, 1, 1)))
+    y, got, e = np.float32(0.5), {0: np.float32(0.5)}, 1
+    for s in sp.steps:
+        yn = np.float32(y + np.float32(2.0) * s["h"])
+        for em in sp.emits[s["emit_begin"]:s["emit_end"]]:
+            got[int(em["slot"])] = np.float32(em["w_prev"] * y + em["w_curr"] * yn)
+        y = yn
+    assert np.allclose([got[i] for i in range(len(ts))], out[:, 0, 0].numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_step_plan_rejects_bad_input():
+    with pytest.raises(ValueError):
+        snsde_b200.build_step_plan(np.array([0.0, 0.0, 1.0]), 0.1)
+    with pytest.raises(ValueError):
+        snsde_b200.build_step_plan(np.array([0.0, 1.0]), 0.0)
+    sp = snsde_b200.build_step_plan(np.array([3.0]), 0.1)          # a single output time: no steps
+    assert sp.n_steps == 0 and len(sp.emits) == 1
+
+
+def test_final_index_slots_match_reference_bookkeeping(golden_dir):
+    from oracle import wrapper
+    times = torch.arange(8.0)
+    for fi in ([3, 5, 7, 7, 2], [0, 7, 4, 1, 7], [7] * 5, [0] * 3, [1, 1, 6]):
+        fi = torch.tensor(fi)
+        ts_ref, g_ref = wrapper.output_times_for_final_index(times, fi)
+        ts, slots = snsde_b200.final_index_slots(times, fi)
+        assert torch.equal(ts, ts_ref) and torch.equal(slots, g_ref)
+        assert torch.equal(ts[slots], times[fi])
+
+
+def test_shard_bounds_cover_rows_exactly():
+    from snsde_b200.dist import shard_bounds
+    for n in (1, 7, 1024, 1025, 8191):
+        for w in (1, 2, 4, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+import snsde_b200
+from snsde_b200.dist import solve_final_sharded, shard_bounds
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+for n in (8, 7):
+    full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) * 1.5
+    def solve(lo, hi, out):          # stands in for engine.solve_final(..., row_offset=lo, out=out)
+        assert (lo, hi) == shard_bounds(n, rank, world)
+        out.copy_(full[lo:hi])
+    got = solve_final_sharded(solve, n, 3, "cpu")
+    assert torch.equal(got, full), (rank, n)
+dist.barrier(); dist.destroy_process_group(); print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_all_gather_of_latents(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=str(ROOT)))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
