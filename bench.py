@@ -348,10 +348,10 @@ def main():
         for i in range(args.warmup):
             step_resident(i)
         barrier()
-        launches0 = plan.launches
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         with ClockSampler(local_rank) as clocks:
             barrier()
+            launches0 = plan.launches
             t_wall = time.perf_counter()
             for i in range(args.steps):
                 evs[i][0].record()
@@ -359,6 +359,7 @@ def main():
                 evs[i][1].record()
             barrier()
             t_wall = time.perf_counter() - t_wall
+            launches = plan.launches - launches0         # engine kernels launched inside the timed region
             if t_wall < 1.5:                       # keep the GPU under load long enough for >= 10 clock samples
                 t_end = time.perf_counter() + 1.5
                 j = 0
@@ -367,7 +368,6 @@ def main():
                     if j % 8 == 0:
                         torch.cuda.synchronize()
                 torch.cuda.synchronize()
-        launches = plan.launches - launches0 if t_wall >= 1.5 else args.steps * ((plan.launches - launches0) // max(1, args.steps + j)) if False else None
         per_step_ms = [a.elapsed_time(b) for a, b in evs]
         dev_ms = max_over_ranks(evs[0][0].elapsed_time(evs[-1][1]))       # whole K-step region on the device
         kern_ms = statistics.mean(per_step_ms)
@@ -418,7 +418,7 @@ def main():
                        "brownian": "in-kernel Philox4x32-10"},
             "e2e": {"value": e2e_value, "unit": "SDE-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": (plan.launches - launches0) if False else args.steps * 1 * (2 if plan.kernel == "tcgen05" else 1),
+            "gpu_launches": launches,
             "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

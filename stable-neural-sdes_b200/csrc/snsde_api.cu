@@ -395,8 +395,9 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
   // pageable source: the runtime stages it before returning, so `ib` may die at scope exit
   CUDA_TRY(cudaMemcpyAsync(p->d_wimg, ib.img.data(), ib.img.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
   if (p->kind == 1) {
-    const int rc = tc_set_weights(p->tc, p->desc, blob, p->num_sms, p->smem_optin, stream);
-    if (rc != SNSDE_OK) return fail(rc, "tensor-core weight packing failed: %s", tc_unsupported_reason());
+    const int rc = tc_set_weights(p->tc, p->desc, p->prog, blob, p->num_sms, p->smem_optin, stream);
+    if (rc == SNSDE_ERR_UNSUPPORTED && p->desc.precision == SNSDE_PRECISION_AUTO) p->kind = 0;   // e.g. weights beyond fp16 range
+    else if (rc != SNSDE_OK) return fail(rc, "tensor-core weight packing failed: %s", tc_unsupported_reason());
   }
   p->has_weights = true;
   return SNSDE_OK;

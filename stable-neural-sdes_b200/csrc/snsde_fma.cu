@@ -18,22 +18,10 @@
 #include <math.h>
 
 #include "snsde_common.cuh"
+#include "snsde_math.cuh"
 #include "snsde_rng.cuh"
 
 namespace snsde {
-
-__device__ __forceinline__ float act_apply(float v, int act) {
-  if (act == ACT_RELU) return v < 0.f ? 0.f : v;                       // NaN passes like torch.relu
-  if (act == ACT_LIPSWISH) return 0.909f * (v / (1.f + expf(-v)));     // 0.909 * silu(v)
-  return v;
-}
-
-__device__ __forceinline__ float nan_to_num_f(float v) {               // torch.nan_to_num defaults
-  if (v != v) return 0.f;
-  if (v == INFINITY) return 3.4028234663852886e38f;
-  if (v == -INFINITY) return -3.4028234663852886e38f;
-  return v;
-}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -102,34 +90,6 @@ __device__ __forceinline__ void dense_eval(float (&acc)[ROWS], const DenseOp& op
   if (op.src2 >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src2), ld, wptr(op.w2_off, op.K2 * op.N), op.K2, op.N, j);
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) acc[r] = act_apply(acc[r], op.act);
-}
-
-// Diffusion value g and (for Milstein) d g / d y at one element.
-__device__ __forceinline__ void diffusion_eval(const TailOp& t, float coef, float y, float tt, float& g, float& dgdy) {
-  float raw, draw;
-  switch (t.special) {
-    case SP_ZERO: raw = 0.f; draw = 0.f; break;
-    case SP_SQRT: raw = sqrtf(y); draw = 0.5f / raw; break;
-    case SP_CUBE: raw = y * y * y; draw = 3.f * y * y; break;
-    case SP_SIGMOID: raw = 1.f / (1.f + expf(-y)); draw = raw * (1.f - raw); break;
-    case SP_RELU: raw = y < 0.f ? 0.f : y; draw = y > 0.f ? 1.f : 0.f; break;
-    default:
-      if (t.mult == MU_Y) { raw = coef * y; draw = coef; }
-      else if (t.mult == MU_TY) { raw = tt * y; draw = tt; }
-      else if (t.mult == MU_T) { raw = coef * tt; draw = 0.f; }
-      else { raw = coef; draw = 0.f; }
-  }
-  const bool state_dep = (t.special >= SP_SQRT) || (t.special == SP_NONE && (t.mult == MU_Y || t.mult == MU_TY));
-  if (t.bounded) {
-    const bool fin = (raw == raw) && (fabsf(raw) != INFINITY);
-    g = tanhf(t.s_theta * nan_to_num_f(raw));
-    // autograd chain of tanh(s * nan_to_num(raw)): (1-g^2) * s * isfinite(raw) * raw'.
-    // A g that does not depend on y has no gradient path: torchsde's vjp returns zeros.
-    dgdy = state_dep ? ((1.f - g * g) * t.s_theta) * (fin ? 1.f : 0.f) * draw : 0.f;
-  } else {
-    g = raw;
-    dgdy = draw;
-  }
 }
 
 template <int R, int NTMAX>
@@ -262,7 +222,7 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
         if (t.clip_drift) d = tanhf(d);
         const float coef = rcoef ? rcoef[r * ld + tid] : vcoef;
         float g, dgdy;
-        diffusion_eval(t, coef, y[r], st.t0, g, dgdy);
+        diffusion_eval<false>(t, coef, y[r], st.t0, g, dgdy);
         float w;
         if (p.dW != nullptr) {
           w = dw[r];

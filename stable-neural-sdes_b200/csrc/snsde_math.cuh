@@ -1,0 +1,58 @@
+// Device math shared by the FMA and tcgen05 kernels: activations, nan_to_num, the elementwise
+// diffusion g(t,y) of neuralsde.py:233-307 and its y-derivative for the Milstein term.
+#pragma once
+#include <math.h>
+#include "snsde_common.cuh"
+
+namespace snsde {
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ACT_RELU) return v < 0.f ? 0.f : v;                       // NaN passes like torch.relu
+  if (act == ACT_LIPSWISH) return 0.909f * (v / (1.f + expf(-v)));     // 0.909 * silu(v)
+  return v;
+}
+
+__device__ __forceinline__ float nan_to_num_f(float v) {               // torch.nan_to_num defaults
+  if (v != v) return 0.f;
+  if (v == INFINITY) return 3.4028234663852886e38f;
+  if (v == -INFINITY) return -3.4028234663852886e38f;
+  return v;
+}
+
+// tanh via one ex2 + one rcp (abs error ~2e-7): 1 - 2/(1+e^{2x}); exact limits at +-inf, NaN passes.
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
+// Diffusion value g and (for Milstein) d g / d y at one element.  FAST selects tanh_fast.
+template <bool FAST>
+__device__ __forceinline__ void diffusion_eval(const TailOp& t, float coef, float y, float tt, float& g, float& dgdy) {
+  float raw, draw;
+  switch (t.special) {
+    case SP_ZERO: raw = 0.f; draw = 0.f; break;
+    case SP_SQRT: raw = sqrtf(y); draw = 0.5f / raw; break;
+    case SP_CUBE: raw = y * y * y; draw = 3.f * y * y; break;
+    case SP_SIGMOID: raw = 1.f / (1.f + expf(-y)); draw = raw * (1.f - raw); break;
+    case SP_RELU: raw = y < 0.f ? 0.f : y; draw = y > 0.f ? 1.f : 0.f; break;
+    default:
+      if (t.mult == MU_Y) { raw = coef * y; draw = coef; }
+      else if (t.mult == MU_TY) { raw = tt * y; draw = tt; }
+      else if (t.mult == MU_T) { raw = coef * tt; draw = 0.f; }
+      else { raw = coef; draw = 0.f; }
+  }
+  const bool state_dep = (t.special >= SP_SQRT) || (t.special == SP_NONE && (t.mult == MU_Y || t.mult == MU_TY));
+  if (t.bounded) {
+    const bool fin = (raw == raw) && (fabsf(raw) != INFINITY);
+    const float arg = t.s_theta * nan_to_num_f(raw);
+    g = FAST ? tanh_fast(arg) : tanhf(arg);
+    // autograd chain of tanh(s * nan_to_num(raw)): (1-g^2) * s * isfinite(raw) * raw'.
+    // A g that does not depend on y has no gradient path: torchsde's vjp returns zeros.
+    dgdy = state_dep ? ((1.f - g * g) * t.s_theta) * (fin ? 1.f : 0.f) * draw : 0.f;
+  } else {
+    g = raw;
+    dgdy = draw;
+  }
+}
+
+}  // namespace snsde

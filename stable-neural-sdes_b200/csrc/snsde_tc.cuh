@@ -1,16 +1,55 @@
 // Tensor-core (tcgen05) path: host-visible interface used by snsde_api.cu.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include "snsde_common.cuh"
 
 namespace snsde {
 
+constexpr int kTcMaxLayers = 6;
+
+struct TcLayer {
+  int a_hi, a_lo;   // byte offsets of the fp16 hi / scaled-lo operand images inside the weight image
+  int K;            // contraction length (multiple of 16)
+  int bias;         // float offset into the vector region
+};
+
+// Everything the tcgen05 kernel needs; built by tc_set_weights (model part) and tc_forward (call part).
+struct TcParams {
+  int H, C, Cpad, NL, uses_control;
+  TcLayer layer[kTcMaxLayers];
+  int ax_hi, ax_lo;          // control segment of layer 0 (K = Cpad), byte offsets
+  int c_sin, c_cos;          // float offsets of the folded time-feature vectors of layer 0 (-1: none)
+  int coef_vec;              // float offset of a per-feature diffusion coefficient vector (-1: none)
+  TailOp tail;
+  const uint8_t* wimg; int wimg_bytes;
+  const float* vec;
+  const float* a_tab;        // [S][H] per-step diffusion coefficient (noise_t networks), or null
+  // per call
+  const float* coeffs; long long coeff_row_stride;
+  const float* y0; int B;
+  const snsde_step* steps; int S;
+  const snsde_emit* emits; int n_init_emits; int n_out;
+  const int* row_slot; const float* dW;
+  unsigned long long seed, row_offset;
+  float* out;
+  int nx, nstg;              // control-operand ring depth, coefficient staging depth
+};
+
+// Per-step table of the row-independent noise networks (options 12,13,16,17).
+struct TcNoiseNet {
+  int kind;                  // 0 none, 1 = Linear(2,H), 2 = relu(Linear(H,H)(relu(Linear(2,H))))
+  int w1t, b1, w2t, b2;      // float offsets into the vector region (w1t [2][H], w2t [H][H] transposed)
+};
+
 struct TcPlan {
-  void* d_image = nullptr;        // packed fp16 hi/lo operand images + fp32 vectors
-  size_t image_bytes = 0;
-  float* d_tables = nullptr;      // per-step bias / diffusion-coefficient tables [S][...]
-  size_t tables_floats = 0;
-  int cfg[32] = {0};
+  uint8_t* d_wimg = nullptr; int wimg_bytes = 0;
+  float* d_vec = nullptr; int vec_floats = 0;
+  float* d_atab = nullptr; int atab_cap = 0;
+  TcParams proto;            // model part of the params
+  TcNoiseNet noise;
+  int num_sms = 0, smem_optin = 0;
+  bool ready = false;
 };
 
 struct TcForwardArgs {
@@ -25,7 +64,8 @@ struct TcForwardArgs {
 
 bool tc_supported(const snsde_model_desc& d, int cc_major, int smem_optin);
 const char* tc_unsupported_reason();
-int tc_set_weights(TcPlan& tc, const snsde_model_desc& d, const float* blob, int num_sms, int smem_optin, cudaStream_t stream);
+int tc_set_weights(TcPlan& tc, const snsde_model_desc& d, const Program& pg, const float* blob, int num_sms,
+                   int smem_optin, cudaStream_t stream);
 cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, int* n_launches);
 void tc_release(TcPlan& tc);
 

@@ -300,3 +300,62 @@ def test_large_hidden_and_nan_semantics(dev):
     got, want = run_both(m, times, coeffs, y0, times, 1.0, dW, "euler", dev)
     assert torch.isfinite(got).all()
     close(got, want)
+
+
+# ================================ tcgen05 tensor-core kernel ======================================
+TC_CASES = [
+    # io, no, H, C, L, B, method
+    (4, 17, 128, 35, 1, 40, "euler"),        # c2 model (collapsed emb o linear_in, X(t) operand ring)
+    (6, 17, 64, 35, 1, 70, "milstein"),      # c3 model
+    (2, 16, 64, 5, 2, 19, "euler"),          # LSDE, additive noise, one hidden layer more
+    (4, 17, 32, 3, 3, 9, "euler"),
+    (3, 6, 64, 4, 1, 33, "milstein"),        # no control read, diagonal sigma * y
+    (1, 3, 128, 4, 1, 12, "euler"),
+    (5, 13, 48, 7, 2, 27, "euler"),          # geometric drift, Linear(2,H) noise * y
+    (2, 0, 16, 2, 1, 5, "euler"),
+    (6, 9, 64, 6, 1, 300, "euler"),          # B > 148*... multiple rows per CTA (NR=16)
+]
+
+
+@pytest.mark.parametrize("io,no,H,C,L,B,method", TC_CASES)
+def test_tc_kernel_matches_oracle(io, no, H, C, L, B, method, dev):
+    K = 25
+    m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, K, seed=7 * H + io + no)
+    dt = solver.solver_dt(times)
+    ts = times[[0, 1, 2, 11, 24]]
+    dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(1)) * dt ** 0.5
+    got, want = run_both(m, times, coeffs, y0, ts, dt, dW, method, dev, precision="tc")
+    assert m._snsde_plans[(method, "tc", str(dev))].kernel == "tcgen05"
+    close(got, want)
+
+
+def test_tc_kernel_long_trajectory_c2_shape_and_philox(dev):
+    # c2 shape at reduced batch: 200 steps, in-kernel Philox; FMA and tcgen05 kernels see the same increments
+    B, H, C, L, K = 64, 128, 35, 1, 201
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=5)
+    fi = torch.randint(2, K, (B,), generator=torch.Generator().manual_seed(3))
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    with torch.no_grad():
+        z_tc = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=77, precision="tc")
+        z_fma = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=77, precision="fp32")
+        plan = mg._snsde_plans[("euler", "tc", str(dev))]
+        assert plan.kernel == "tcgen05"
+        sp = plan.step_plan(times, 1.0, times)
+        dW = snsde_b200.philox_increments(77, sp, B, H, dev).cpu()
+    m.to("cpu")
+    want = wrapper.classification_latent(m, times, coeffs, fi, y0, solver.BrownianTable(dW))
+    e1 = close(z_fma, want)
+    e2 = close(z_tc, want)
+    print(f"200-step c2-shape rel err: fma {e1:.2e}  tcgen05 {e2:.2e}")
+
+
+def test_tc_auto_falls_back_to_fma_when_unsupported(dev):
+    m, times, coeffs, y0 = make_problem(3, 18, 4, 32, 3, 1, 5, seed=1)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    with torch.no_grad():
+        snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=1)
+        assert mg._snsde_plans[("euler", "auto", str(dev))].kernel == "fma_fp32"
+        with pytest.raises(ValueError, match="tensor-core"):
+            snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=1, precision="tc")
