@@ -21,13 +21,16 @@
 // (neuralsde.py:202,210), so layer 0 is collapsed on the host in double precision:
 //   z0 = (We1 Win_y) y + (We2 Wi) X(t) + [be + We1 bin + We2 bi] + (We1 Win_tau) [sin t, cos t].
 //
-// Warp roles (256 threads, 1 CTA/SM):
-//   warps 0-3  epilogue: tcgen05.ld accumulators -> bias/activation or SDE update -> split ->
-//              write the next B operand; Philox/Box-Muller, diffusion and emits run in the shadow
-//              of the in-flight MMAs
-//   warp  4    one elected lane issues every tcgen05.mma and commits to mbarriers
-//   warps 5-7  control producer: 1-D bulk async copies (TMA) of the spline rows several steps
-//              ahead, cubic evaluation, split, write of the X(t) operand ring
+// Warp roles (384 threads, 1 CTA/SM):
+//   warps 0-3   epilogue: tcgen05.ld accumulators -> bias/activation or SDE update -> split ->
+//               write the next B operand; diffusion of the new state and emits run in the shadow
+//               of the in-flight MMAs
+//   warp  4     one elected lane issues every tcgen05.mma and commits to mbarriers
+//   warps 5-7   control producer: 1-D bulk async copies (TMA) of the spline rows several steps
+//               ahead, cubic evaluation, split, write of the X(t) operand ring
+//   warps 8-11  step prefetch: everything that depends on time only - Philox/Box-Muller (or table)
+//               increments, folded layer-0 bias, diffusion coefficient, step/emit descriptors -
+//               one step ahead, through a 2-deep shared-memory ring
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -47,19 +50,28 @@ namespace snsde {
 
 using namespace ptx;
 
-constexpr int kTcThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kTcThreads = 384;
+constexpr int kEpiWarps = 4;
 constexpr int kProdWarps = 3;
 constexpr int kProdThreads = 32 * kProdWarps;
+constexpr int kPrepWarps = 4;
 constexpr uint32_t kASbo = 128, kALbo = 2048;      // A images: 16 row groups contiguous, then K chunks
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 
-struct TcSmem {
-  int w, b, x, stg, bars, total;
-  int lbo_b;            // bytes between K chunks (8 columns) of a B operand
-  int x_slot_bytes, stg_bytes;
+// Per-step broadcast block written by the step-prefetch warps (ring of 2).
+struct StepInfo {
+  float h, t0;
+  int n_emits, emit_begin;
+  snsde_emit first;          // the first emit of the step (almost every step has at most one)
 };
 
+struct TcSmem {
+  int w, b, x, stg, prep, bias, bars, total;
+  int lbo_b;            // bytes between K chunks (8 columns) of a B operand
+  int x_slot_bytes, stg_bytes, prep_bytes;
+};
+
+// prep slot: [NR][128] dW floats | [128] add0 | [128] coef | StepInfo
 __host__ __device__ inline TcSmem tc_smem_layout(int wimg_bytes, int H, int C, int Cpad, int N, int NR, int nx, int nstg,
                                                  int uses_control) {
   TcSmem s;
@@ -70,8 +82,11 @@ __host__ __device__ inline TcSmem tc_smem_layout(int wimg_bytes, int H, int C, i
   s.x_slot_bytes = uses_control ? (Cpad / 8) * s.lbo_b : 0;
   s.stg = s.x + nx * s.x_slot_bytes;
   s.stg_bytes = uses_control ? NR * 16 * C : 0;
-  s.bars = (s.stg + nstg * s.stg_bytes + 15) & ~15;
-  s.total = s.bars + 8 * (2 + 2 * nx + nstg) + 16;
+  s.prep = (s.stg + nstg * s.stg_bytes + 15) & ~15;
+  s.prep_bytes = (NR + 2) * 128 * 4 + 32;
+  s.bias = s.prep + 2 * s.prep_bytes;                // [kTcMaxLayers][128] per-layer bias vectors
+  s.bars = s.bias + kTcMaxLayers * 512;
+  s.total = s.bars + 8 * (2 + 2 * nx + nstg + 4) + 16;
   return s;
 }
 
@@ -103,7 +118,9 @@ __device__ __forceinline__ void issue_segment(uint32_t a_hi, uint32_t a_lo, uint
   }
 }
 
-template <int NR>
+// DIFF = 1: the diffusion is tanh(sigmoid(theta) * nan_to_num(coef * y)) (noise options 3,6,13,17) - the
+// form of every proposed model with multiplicative noise; DIFF = 0: generic (runtime-selected) form.
+template <int NR, int DIFF>
 __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams p) {
   constexpr int N = NR < 16 ? 16 : NR;              // MMA N (rows padded to >= 16)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -116,7 +133,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   const uint32_t bar_in = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
   const uint32_t bar_xfull = smem_u32(&bars[2]), bar_xempty = smem_u32(&bars[2 + p.nx]);
   const uint32_t bar_cfull = smem_u32(&bars[2 + 2 * p.nx]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 + 2 * p.nx + p.nstg]);
+  const uint32_t bar_pfull = smem_u32(&bars[2 + 2 * p.nx + p.nstg]), bar_pempty = bar_pfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 + 2 * p.nx + p.nstg + 4]);
   constexpr uint32_t kTmemCols = (6 * N <= 128) ? 128 : (6 * N <= 256 ? 256 : 512);
 
   // ---- one-time setup: weights -> smem, zero the operand buffers, barriers, TMEM ----
@@ -127,12 +145,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     uint4* z = reinterpret_cast<uint4*>(smem + L.b);
     const int zn = (L.stg - L.b) / 16;
     for (int i = tid; i < zn; i += kTcThreads) z[i] = make_uint4(0, 0, 0, 0);
+    float* sb = reinterpret_cast<float*>(smem + L.bias);
+    for (int i = tid; i < kTcMaxLayers * 128; i += kTcThreads) {
+      const int l = i >> 7, j = i & 127;
+      sb[i] = (l < NL && j < H) ? p.vec[p.layer[l].bias + j] : 0.f;
+    }
   }
   if (tid == 0) {
-    mbar_init(bar_in, kEpiThreads);
+    mbar_init(bar_in, kEpiWarps);
     mbar_init(bar_acc, 1);
     for (int i = 0; i < p.nx; ++i) { mbar_init(bar_xfull + 8 * i, kProdWarps); mbar_init(bar_xempty + 8 * i, 1); }
     for (int i = 0; i < p.nstg; ++i) mbar_init(bar_cfull + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_pfull + 8 * i, kPrepWarps); mbar_init(bar_pempty + 8 * i, kEpiWarps); }
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -157,15 +181,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       *reinterpret_cast<__half*>(q) = hi;
       *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
     };
-    float bias[kTcMaxLayers];
-#pragma unroll
-    for (int l = 0; l < kTcMaxLayers; ++l) bias[l] = (l < NL && act) ? p.vec[p.layer[l].bias + h] : 0.f;
-    const float csin = (p.c_sin >= 0 && act) ? p.vec[p.c_sin + h] : 0.f;
-    const float ccos = (p.c_cos >= 0 && act) ? p.vec[p.c_cos + h] : 0.f;
-    float coef = t.coef_scalar;
-    if (t.coef_src == CO_IMG && act) coef = p.vec[p.coef_vec + h];
+    auto hand_over = [&]() {                 // operands written -> MMA issuer (one arrival per warp)
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_in);
+    };
+    const float* sbias = reinterpret_cast<const float*>(smem + L.bias) + (h & 127);
+    const float bias_last = sbias[(NL - 1) * 128];
+    // small row counts: diffusion / tanh(y) are evaluated in the shadow of the layer-0 MMAs and kept in
+    // registers; NR = 32 has no registers to spare and evaluates them inside the update loop
+    constexpr bool PRE = NR <= 16;
+    constexpr int NP = PRE ? NR : 1;
 
-    float y[NR], yprev[NR], dwv[NR], gv[NR], dg[NR], thy[NR];
+    float y[NR], yprev[NR], gv[NP], dg[NP], thy[NP];
     int myslot[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -173,7 +202,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       y[r] = act ? p.y0[(size_t)b * H + h] : 0.f;
       yprev[r] = y[r];
       myslot[r] = p.row_slot ? p.row_slot[b] : -1;
-      dwv[r] = gv[r] = dg[r] = thy[r] = 0.f;
+      if (PRE) gv[r] = dg[r] = thy[r] = 0.f;
       if (act) write_operand(r, y[r]);
     }
     auto emit = [&](snsde_emit em) {
@@ -194,34 +223,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       em.w_prev = 0.f; em.w_curr = 1.f;
       emit(em);
     }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    mbar_arrive(bar_in);
+    hand_over();
 
-    // everything of step s that does not depend on the drift: increments, diffusion, tanh(y)
-    auto prepare_step = [&](int s, const snsde_step& st) {
-      if (!act) return;
-      float cf = coef;
-      if (t.coef_src == CO_VBUF) cf = p.a_tab[(size_t)s * H + h];
-      float nrm[4];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        if (p.dW != nullptr) {
-          dwv[r] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + h];
-        } else {
-          const unsigned long long gb = p.row_offset + (unsigned long long)(row0 + r);
-          if (r == 0 || (gb & 3ull) == 0ull) philox_normals4(p.seed, (uint32_t)h, (uint32_t)(gb >> 2), (uint32_t)s, nrm);
-          dwv[r] = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), st.sqrt_h);
-        }
-        diffusion_eval<true>(t, cf, y[r], st.t0, gv[r], dg[r]);
-        if (t.geometric) thy[r] = tanh_fast(y[r]);
+    // diffusion of the CURRENT state for the coming step (needs only y and the step's coefficient)
+    auto state_terms = [&](float yr, float cf, float t0, float& g, float& dgy, float& th) {
+      if (DIFF == 1) {
+        const float raw = cf * yr;
+        const bool fin = (raw == raw) && (fabsf(raw) != INFINITY);
+        g = tanh_fast(t.s_theta * nan_to_num_f(raw));
+        dgy = t.milstein ? ((1.f - g * g) * t.s_theta) * (fin ? 1.f : 0.f) * cf : 0.f;
+      } else {
+        diffusion_eval<true>(t, cf, yr, t0, g, dgy);
       }
+      th = t.geometric ? tanh_fast(yr) : 1.f;
+    };
+    auto prepare_state = [&](float cf, float t0) {
+      if (!act || !PRE) return;
+#pragma unroll
+      for (int r = 0; r < NP; ++r) state_terms(y[r], cf, t0, gv[r], dg[r], thy[r]);
     };
 
     uint32_t pacc = 0;
-    snsde_step st;
-    if (p.S > 0) { st = p.steps[0]; prepare_step(0, st); }
     for (int s = 0; s < p.S; ++s) {
+      // ---- step data from the prefetch warps (normally already there) ----
+      const uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
+      const float* sdw = reinterpret_cast<const float*>(slot);
+      mbar_wait(bar_pfull + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+      const StepInfo si = *reinterpret_cast<const StepInfo*>(slot + (NR + 2) * 512);
+      const float add0 = sdw[NR * 128 + h];
+      const float cf = sdw[(NR + 1) * 128 + h];
+      prepare_state(cf, si.t0);                       // in the shadow of the layer-0 MMAs
       for (int l = 0; l < NL; ++l) {
         mbar_wait(bar_acc, pacc);
         pacc ^= 1;
@@ -236,40 +267,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
           for (int i = 0; i < 8; ++i) { vm[c + i] = a8[i]; vc[c + i] = b8[i]; }
         }
         tmem_ld_wait();
-        if (act) {
-          float add = bias[l];
-          if (l == 0) add = fmaf(st.cos_t0, ccos, fmaf(st.sin_t0, csin, add));
-          if (l < NL - 1) {
+        if (l < NL - 1) {
+          if (act) {
+            const float add = (l == 0) ? add0 : sbias[l * 128];
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
               float v = fmaf(vc[r], kLoInv, vm[r]) + add;
               v = v < 0.f ? 0.f : v;                                   // relu feeding the next Linear
               write_operand(r, v);
             }
-          } else {
+          }
+        } else if (act) {
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              float d = fmaf(vc[r], kLoInv, vm[r]) + add;
-              if (t.geometric) d *= thy[r];
-              if (t.clip_drift) d = tanh_fast(d);
-              float yn = __fadd_rn(__fadd_rn(y[r], __fmul_rn(d, st.h)), __fmul_rn(gv[r], dwv[r]));
-              if (t.milstein) {
-                const float v2 = __fmul_rn(dwv[r], dwv[r]) - st.h;
-                yn = __fadd_rn(yn, 0.5f * ((gv[r] * v2) * dg[r]));
-              }
-              yprev[r] = y[r];
-              y[r] = yn;
-              write_operand(r, yn);
+          for (int r = 0; r < NR; ++r) {
+            float d = fmaf(vc[r], kLoInv, vm[r]) + bias_last;
+            float g, dgy, th;
+            if (PRE) { g = gv[r]; dgy = dg[r]; th = thy[r]; }
+            else state_terms(y[r], cf, si.t0, g, dgy, th);
+            if (t.geometric) d *= th;
+            if (t.clip_drift) d = tanh_fast(d);
+            const float dw = sdw[r * 128 + h];
+            float yn = __fadd_rn(__fadd_rn(y[r], __fmul_rn(d, si.h)), __fmul_rn(g, dw));
+            if (t.milstein) {
+              const float v2 = __fmul_rn(dw, dw) - si.h;
+              yn = __fadd_rn(yn, 0.5f * ((g * v2) * dgy));
             }
+            yprev[r] = y[r];
+            y[r] = yn;
+            write_operand(r, yn);
           }
         }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        mbar_arrive(bar_in);
+        hand_over();
       }
-      // in the shadow of the next step's layer-0 MMAs
-      for (int e = st.emit_begin; e < st.emit_end; ++e) emit(p.emits[e]);
-      if (s + 1 < p.S) { st = p.steps[s + 1]; prepare_step(s + 1, st); }
+      // ---- in the shadow of the next step's layer-0 MMAs ----
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pempty + 8 * (s & 1));             // slot consumed
+      if (si.n_emits > 0) emit(si.first);
+      for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);
     }
   } else if (warp == 4) {
     // =========================== MMA ISSUER ===========================
@@ -297,49 +331,99 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         if (p.uses_control && s + 1 < p.S) issue_x(s + 1);
       }
     }
-  } else if (p.uses_control) {
+  } else if (warp < 8) {
     // =========================== CONTROL PRODUCER ===========================
-    const int ptid = tid - 160;                       // 0..95
-    const int pwarp = warp - 5;
-    const uint32_t row_bytes = 16u * C;
-    auto fetch = [&](int s) {                         // spline rows of step s -> staging slot (warp 5 only)
-      if (pwarp != 0 || s >= p.S) return;
-      const int stg = s % p.nstg;
-      const uint32_t bar = bar_cfull + 8 * stg;
-      if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * NR);
-      __syncwarp();
-      const int interval = p.steps[s].interval;
-      for (int r = lane; r < NR; r += 32) {
-        const int b = min(row0 + r, p.B - 1);
-        const float* src = p.coeffs + (size_t)b * p.coeff_row_stride + (size_t)interval * 4 * C;
-        bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
+    if (p.uses_control) {
+      const int ptid = tid - 160;                       // 0..95
+      const int pwarp = warp - 5;
+      const uint32_t row_bytes = 16u * C;
+      auto fetch = [&](int s) {                         // spline rows of step s -> staging slot (warp 5 only)
+        if (pwarp != 0 || s >= p.S) return;
+        const int stg = s % p.nstg;
+        const uint32_t bar = bar_cfull + 8 * stg;
+        if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * NR);
+        __syncwarp();
+        const int interval = p.steps[s].interval;
+        for (int r = lane; r < NR; r += 32) {
+          const int b = min(row0 + r, p.B - 1);
+          const float* src = p.coeffs + (size_t)b * p.coeff_row_stride + (size_t)interval * 4 * C;
+          bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
+        }
+      };
+      for (int s = 0; s < p.nstg - 1; ++s) fetch(s);
+      for (int s = 0; s < p.S; ++s) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads));      // all producer warps are done with step s-1
+        fetch(s + p.nstg - 1);
+        const int stg = s % p.nstg, slot = s % p.nx;
+        const float frac = p.steps[s].frac;
+        mbar_wait(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
+        if (s >= p.nx) mbar_wait(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
+        const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
+        uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
+        for (int i = ptid; i < NR * C; i += kProdThreads) {
+          const int r = i / C, c = i - r * C;
+          const float* row = rows + r * 4 * C;
+          float inner = 0.5f * row[2 * C + c] + __fdiv_rn(row[3 * C + c] * frac, 3.0f);
+          inner = row[C + c] + inner * frac;
+          const float x = row[c] + inner * frac;
+          __half hi, lo;
+          split_f16(x, hi, lo);
+          uint8_t* q = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+          *reinterpret_cast<__half*>(q) = hi;
+          *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);
       }
-    };
-    for (int s = 0; s < p.nstg - 1; ++s) fetch(s);
+    }
+  } else {
+    // =========================== STEP PREFETCH (time-only work) ===========================
+    // Brownian increments (Philox or table), the folded layer-0 bias, the diffusion coefficient and the
+    // step/emit descriptors for step s, written to a 2-deep ring one step ahead of the epilogue.
+    const int h = tid - 256;
+    const bool act = h < H;
+    const TailOp t = p.tail;
+    const float c0 = act ? p.vec[p.layer[0].bias + h] : 0.f;
+    const float csin = (p.c_sin >= 0 && act) ? p.vec[p.c_sin + h] : 0.f;
+    const float ccos = (p.c_cos >= 0 && act) ? p.vec[p.c_cos + h] : 0.f;
+    float coef = t.coef_scalar;
+    if (t.coef_src == CO_IMG && act) coef = p.vec[p.coef_vec + h];
     for (int s = 0; s < p.S; ++s) {
-      asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads));      // all producer warps are done with step s-1
-      fetch(s + p.nstg - 1);
-      const int stg = s % p.nstg, slot = s % p.nx;
-      mbar_wait(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
-      if (s >= p.nx) mbar_wait(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
-      const float frac = p.steps[s].frac;
-      const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
-      uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
-      for (int i = ptid; i < NR * C; i += kProdThreads) {
-        const int r = i / C, c = i - r * C;
-        const float* row = rows + r * 4 * C;
-        float inner = 0.5f * row[2 * C + c] + __fdiv_rn(row[3 * C + c] * frac, 3.0f);
-        inner = row[C + c] + inner * frac;
-        const float x = row[c] + inner * frac;
-        __half hi, lo;
-        split_f16(x, hi, lo);
-        uint8_t* q = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
-        *reinterpret_cast<__half*>(q) = hi;
-        *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
+      const snsde_step st = p.steps[s];
+      uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
+      float* sdw = reinterpret_cast<float*>(slot);
+      float cf = coef;
+      if (t.coef_src == CO_VBUF && act) cf = p.a_tab[(size_t)s * H + h];
+      float dwv[NR];
+      if (act) {
+        if (p.dW != nullptr) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) dwv[r] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + h];
+        } else {
+          float nrm[4];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const unsigned long long gb = p.row_offset + (unsigned long long)(row0 + r);
+            if (r == 0 || (gb & 3ull) == 0ull) philox_normals4(p.seed, (uint32_t)h, (uint32_t)(gb >> 2), (uint32_t)s, nrm);
+            dwv[r] = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), st.sqrt_h);
+          }
+        }
       }
-      fence_proxy_async_smem();
+      StepInfo si;
+      si.h = st.h; si.t0 = st.t0; si.n_emits = st.emit_end - st.emit_begin; si.emit_begin = st.emit_begin;
+      si.first.slot = 0; si.first.w_prev = 0.f; si.first.w_curr = 0.f;
+      if (h == 0 && si.n_emits > 0) si.first = p.emits[st.emit_begin];
+      if (s >= 2) mbar_wait(bar_pempty + 8 * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
+      if (act) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) sdw[r * 128 + h] = dwv[r];
+        sdw[NR * 128 + h] = fmaf(st.cos_t0, ccos, fmaf(st.sin_t0, csin, c0));
+        sdw[(NR + 1) * 128 + h] = cf;
+      }
+      if (h == 0) *reinterpret_cast<StepInfo*>(slot + (NR + 2) * 512) = si;
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);
+      if (lane == 0) mbar_arrive(bar_pfull + 8 * (s & 1));
     }
   }
 
@@ -537,9 +621,9 @@ int tc_set_weights(TcPlan& tc, const snsde_model_desc& d, const Program& pg, con
   return SNSDE_OK;
 }
 
-template <int NR>
+template <int NR, int DIFF>
 static cudaError_t tc_launch_one(const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = snsde_tc_kernel<NR>;
+  auto kern = snsde_tc_kernel<NR, DIFF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, kTcThreads, smem, stream>>>(p);
@@ -584,10 +668,14 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
   }
   const int grid = (a.B + NR - 1) / NR;
   cudaError_t e;
-  switch (NR) {
-    case 8: e = tc_launch_one<8>(p, grid, L.total, stream); break;
-    case 16: e = tc_launch_one<16>(p, grid, L.total, stream); break;
-    default: e = tc_launch_one<32>(p, grid, L.total, stream); break;
+  const bool fast_diff = p.tail.bounded && p.tail.special == SP_NONE && p.tail.mult == MU_Y;
+  switch (NR * 2 + (fast_diff ? 1 : 0)) {
+    case 16: e = tc_launch_one<8, 0>(p, grid, L.total, stream); break;
+    case 17: e = tc_launch_one<8, 1>(p, grid, L.total, stream); break;
+    case 32: e = tc_launch_one<16, 0>(p, grid, L.total, stream); break;
+    case 33: e = tc_launch_one<16, 1>(p, grid, L.total, stream); break;
+    case 64: e = tc_launch_one<32, 0>(p, grid, L.total, stream); break;
+    default: e = tc_launch_one<32, 1>(p, grid, L.total, stream); break;
   }
   if (e == cudaSuccess) *n_launches += 1;
   return e;
