@@ -100,21 +100,40 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 
 __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-// All MMAs of one operand segment: D[:, 0:2N] (+)= Whi x [ahi;alo'],  D[:, N:2N] += Wlo' x ahi
-template <int N>
-__device__ __forceinline__ void issue_segment(uint32_t a_hi, uint32_t a_lo, uint32_t b_base, int nk, uint32_t lbo_b,
-                                              uint32_t d_tmem, bool accumulate_first) {
+// TMEM accumulator region of one layer.  Dependent tcgen05.mma's into the SAME accumulator are ~84 cycles
+// apart on B200 (measured, tests/cuda/umma_probe.cu) whatever the tile size, so the K chunks of a layer are
+// spread over CH independent chains per product and summed in the epilogue:
+//   [main|corrA] chains  (Whi x [ahi;alo'], 2N columns each) : columns [c*2N, (c+1)*2N),            c < CH
+//   corrB chains         (Wlo' x ahi,        N columns each) : columns [CH*2N + c*N, CH*2N+(c+1)*N)
+template <int N, int CH>
+struct AccRegion {
+  static constexpr int kCols = CH * 3 * N;
+  __device__ static constexpr uint32_t a(int c) { return (uint32_t)(c * 2 * N); }
+  __device__ static constexpr uint32_t b(int c) { return (uint32_t)(CH * 2 * N + c * N); }
+};
+
+// All MMAs of one operand segment (executed warp-uniformly; `leader` is the one issuing lane).
+// `touched` has bit c (resp. bit CH+c) set once [main|corrA] (resp. corrB) chain c holds a partial sum.
+template <int N, int CH>
+__device__ __forceinline__ void issue_segment(bool leader, uint32_t a_hi, uint32_t a_lo, uint32_t b_base, int nk,
+                                              uint32_t lbo_b, uint32_t d_tmem, uint32_t& touched, int& chunk) {
   constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * N), idesc1 = umma_idesc_f16(128, N);
   uint64_t da_hi = umma_smem_desc(a_hi, kALbo, kASbo);
   uint64_t da_lo = umma_smem_desc(a_lo, kALbo, kASbo);
   uint64_t db = umma_smem_desc(b_base, lbo_b, 128);
+  const uint64_t a_step = (uint64_t)((2 * kALbo) >> 4), b_step = (uint64_t)((2 * lbo_b) >> 4);
 #pragma unroll 4
   for (int kb = 0; kb < nk; ++kb) {
-    umma_f16(d_tmem, da_hi, db, idesc2, (accumulate_first || kb > 0) ? 1u : 0u);
-    umma_f16(d_tmem + N, da_lo, db, idesc1, 1u);
-    da_hi = desc_advance(da_hi, 2 * kALbo);
-    da_lo = desc_advance(da_lo, 2 * kALbo);
-    db = desc_advance(db, 2 * lbo_b);
+    const int c = chunk & (CH - 1);
+    if (leader) {
+      umma_f16(d_tmem + AccRegion<N, CH>::a(c), da_hi, db, idesc2, (touched >> c) & 1u);
+      umma_f16(d_tmem + AccRegion<N, CH>::b(c), da_lo, db, idesc1, (touched >> (CH + c)) & 1u);
+    }
+    touched |= (1u << c) | (1u << (CH + c));
+    ++chunk;
+    da_hi += a_step;
+    da_lo += a_step;
+    db += b_step;
   }
 }
 
@@ -123,6 +142,8 @@ __device__ __forceinline__ void issue_segment(uint32_t a_hi, uint32_t a_lo, uint
 template <int NR, int DIFF>
 __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams p) {
   constexpr int N = NR < 16 ? 16 : NR;              // MMA N (rows padded to >= 16)
+  constexpr int CH = N <= 16 ? 2 : 1;               // accumulator chains per product (TMEM: 3 regions x CH*3N columns)
+  using Acc = AccRegion<N, CH>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, C = p.C, Cpad = p.Cpad, NL = p.NL;
@@ -135,7 +156,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   const uint32_t bar_cfull = smem_u32(&bars[2 + 2 * p.nx]);
   const uint32_t bar_pfull = smem_u32(&bars[2 + 2 * p.nx + p.nstg]), bar_pempty = bar_pfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 + 2 * p.nx + p.nstg + 4]);
-  constexpr uint32_t kTmemCols = (6 * N <= 128) ? 128 : (6 * N <= 256 ? 256 : 512);
+  constexpr uint32_t kTmemCols = (3 * Acc::kCols <= 128) ? 128 : (3 * Acc::kCols <= 256 ? 256 : 512);
+  static_assert(3 * Acc::kCols <= 512, "TMEM budget");
 
   // ---- one-time setup: weights -> smem, zero the operand buffers, barriers, TMEM ----
   {
@@ -165,7 +187,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  auto dcol = [&](int l) -> uint32_t { return (uint32_t)((l == 0 ? 0 : 1 + ((l - 1) & 1)) * 2 * N); };
+  auto dcol = [&](int l) -> uint32_t { return (uint32_t)((l == 0 ? 0 : 1 + ((l - 1) & 1)) * Acc::kCols); };
 
   if (warp < 4) {
     // =========================== EPILOGUE / SDE STATE ===========================
@@ -258,15 +280,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         pacc ^= 1;
         tc_fence_after();
         float vm[NR], vc[NR];
+        const uint32_t dreg = tmem + lane_base + dcol(l);
 #pragma unroll
         for (int c = 0; c < NR; c += 8) {
-          float a8[8], b8[8];
-          tmem_ld8(tmem + lane_base + dcol(l) + c, a8);
-          tmem_ld8(tmem + lane_base + dcol(l) + N + c, b8);
+          float m8[CH][8], a8[CH][8], b8[CH][8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { vm[c + i] = a8[i]; vc[c + i] = b8[i]; }
+          for (int ch = 0; ch < CH; ++ch) {
+            tmem_ld8(dreg + Acc::a(ch) + c, m8[ch]);
+            tmem_ld8(dreg + Acc::a(ch) + N + c, a8[ch]);
+            tmem_ld8(dreg + Acc::b(ch) + c, b8[ch]);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float m = m8[0][i], cc = a8[0][i] + b8[0][i];
+#pragma unroll
+            for (int ch = 1; ch < CH; ++ch) { m += m8[ch][i]; cc += a8[ch][i] + b8[ch][i]; }
+            vm[c + i] = m; vc[c + i] = cc;
+          }
         }
-        tmem_ld_wait();
         if (l < NL - 1) {
           if (act) {
             const float add = (l == 0) ? add0 : sbias[l * 128];
@@ -307,29 +339,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     }
   } else if (warp == 4) {
     // =========================== MMA ISSUER ===========================
-    if (lane == 0) {
-      const uint32_t w_base = smem_u32(smem + L.w), b_base = smem_u32(smem + L.b), x_base = smem_u32(smem + L.x);
-      uint32_t pin = 0;
-      auto issue_x = [&](int s) {
-        const int slot = s % p.nx;
-        mbar_wait(bar_xfull + 8 * slot, (uint32_t)((s / p.nx) & 1));
+    // The whole warp runs this code (descriptor arithmetic stays on the uniform datapath); one elected
+    // lane issues the tcgen05 instructions.
+    const bool leader = elect_one();
+    const uint32_t w_base = smem_u32(smem + L.w), b_base = smem_u32(smem + L.b), x_base = smem_u32(smem + L.x);
+    uint32_t pin = 0;
+    uint32_t touched0 = 0;                 // chain state of layer 0's region (the X(t) segment is issued early)
+    int chunk0 = 0;
+    auto issue_x = [&](int s) {
+      const int slot = s % p.nx;
+      mbar_wait(bar_xfull + 8 * slot, (uint32_t)((s / p.nx) & 1));
+      tc_fence_after();
+      touched0 = 0; chunk0 = 0;
+      issue_segment<N, CH>(leader, w_base + p.ax_hi, w_base + p.ax_lo, x_base + slot * L.x_slot_bytes, Cpad / 16, L.lbo_b,
+                           tmem + dcol(0), touched0, chunk0);
+      if (leader) umma_commit(bar_xempty + 8 * slot);
+      __syncwarp();
+    };
+    if (p.uses_control && p.S > 0) issue_x(0);
+    for (int s = 0; s < p.S; ++s) {
+      for (int l = 0; l < NL; ++l) {
+        mbar_wait(bar_in, pin);
+        pin ^= 1;
         tc_fence_after();
-        issue_segment<N>(w_base + p.ax_hi, w_base + p.ax_lo, x_base + slot * L.x_slot_bytes, Cpad / 16, L.lbo_b,
-                         tmem + dcol(0), false);
-        umma_commit(bar_xempty + 8 * slot);
-      };
-      if (p.uses_control && p.S > 0) issue_x(0);
-      for (int s = 0; s < p.S; ++s) {
-        for (int l = 0; l < NL; ++l) {
-          mbar_wait(bar_in, pin);
-          pin ^= 1;
-          tc_fence_after();
-          issue_segment<N>(w_base + p.layer[l].a_hi, w_base + p.layer[l].a_lo, b_base, p.layer[l].K / 16, L.lbo_b,
-                           tmem + dcol(l), l == 0 && p.uses_control);
-          umma_commit(bar_acc);
-        }
-        if (p.uses_control && s + 1 < p.S) issue_x(s + 1);
+        uint32_t touched = 0;
+        int chunk = 0;
+        if (l == 0 && p.uses_control) { touched = touched0; chunk = chunk0; }
+        issue_segment<N, CH>(leader, w_base + p.layer[l].a_hi, w_base + p.layer[l].a_lo, b_base, p.layer[l].K / 16, L.lbo_b,
+                             tmem + dcol(l), touched, chunk);
+        if (leader) umma_commit(bar_acc);
+        __syncwarp();
       }
+      if (p.uses_control && s + 1 < p.S) issue_x(s + 1);
     }
   } else if (warp < 8) {
     // =========================== CONTROL PRODUCER ===========================
@@ -477,7 +518,8 @@ bool tc_supported(const snsde_model_desc& d, int cc_major, int smem_optin) {
   if (io == 0) { g_reason = "input_option 0 (control only) runs on the FMA kernel"; return false; }
   if (no == 14 || no == 15 || no == 18 || no == 19) { g_reason = "state-network noise options run on the FMA kernel"; return false; }
   if (d.hidden != d.hidden_hidden) { g_reason = "needs hidden_hidden == hidden"; return false; }
-  if (d.hidden % 16 || d.hidden < 16 || d.hidden > 128) { g_reason = "needs hidden in {16,32,...,128}"; return false; }
+  // hidden >= 32: every layer must feed each of the 2 accumulator chains at least one 16-wide K chunk
+  if (d.hidden % 16 || d.hidden < 32 || d.hidden > 128) { g_reason = "needs hidden in {32,48,...,128}"; return false; }
   if (d.num_hidden_layers + 1 > kTcMaxLayers) { g_reason = "too many hidden layers"; return false; }
   const int Cpad = (d.input_channels + 15) & ~15;
   const TcSmem L = tc_smem_layout((int)tc_weight_bytes(d), d.hidden, d.input_channels, Cpad, 16, 8, 2, 2, is_emb_opt(io));
