@@ -21,14 +21,14 @@
 // (neuralsde.py:202,210), so layer 0 is collapsed on the host in double precision:
 //   z0 = (We1 Win_y) y + (We2 Wi) X(t) + [be + We1 bin + We2 bi] + (We1 Win_tau) [sin t, cos t].
 //
-// Warp roles (384 threads, 1 CTA/SM):
-//   warps 0-3   epilogue: tcgen05.ld accumulators -> bias/activation or SDE update -> split ->
-//               write the next B operand; diffusion of the new state and emits run in the shadow
-//               of the in-flight MMAs
-//   warp  4     one elected lane issues every tcgen05.mma and commits to mbarriers
-//   warps 5-7   control producer: 1-D bulk async copies (TMA) of the spline rows several steps
+// Warp roles (512 threads, 1 CTA/SM):
+//   warps 0-7   epilogue (two warps per TMEM lane quadrant, each thread owns one feature of half the
+//               rows): tcgen05.ld accumulators -> bias/activation or SDE update -> split -> write the
+//               next B operand; diffusion of the new state and emits run in the shadow of the MMAs
+//   warp  8     issues every tcgen05.mma (warp-uniform code, one elected lane) and commits to mbarriers
+//   warps 9-11  control producer: 1-D bulk async copies (TMA) of the spline rows several steps
 //               ahead, cubic evaluation, split, write of the X(t) operand ring
-//   warps 8-11  step prefetch: everything that depends on time only - Philox/Box-Muller (or table)
+//   warps 12-15 step prefetch: everything that depends on time only - Philox/Box-Muller (or table)
 //               increments, folded layer-0 bias, diffusion coefficient, step/emit descriptors -
 //               one step ahead, through a 2-deep shared-memory ring
 #include <cuda_fp16.h>
@@ -50,8 +50,10 @@ namespace snsde {
 
 using namespace ptx;
 
-constexpr int kTcThreads = 384;
-constexpr int kEpiWarps = 4;
+constexpr int kTcThreads = 512;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, each owning half the rows
+constexpr int kMmaWarp = 8;
+constexpr int kProdWarp0 = 9, kPrepWarp0 = 12;
 constexpr int kProdWarps = 3;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kPrepWarps = 4;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     for (int i = 0; i < 2; ++i) { mbar_init(bar_pfull + 8 * i, kPrepWarps); mbar_init(bar_pempty + 8 * i, kEpiWarps); }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -189,12 +191,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   const uint32_t tmem = *tmem_slot;
   auto dcol = [&](int l) -> uint32_t { return (uint32_t)((l == 0 ? 0 : 1 + ((l - 1) & 1)) * Acc::kCols); };
 
-  if (warp < 4) {
+  if (warp < kEpiWarps) {
     // =========================== EPILOGUE / SDE STATE ===========================
-    const int h = tid;
+    // thread = (feature h, row half): TMEM lane quadrant = warp % 4, rows [half*RT, half*RT + RT)
+    constexpr int RT = NR / 2;                         // rows per thread
+    constexpr int LW = RT < 8 ? RT : 8;                // TMEM load width
+    const int h = (warp & 3) * 32 + lane;
+    const int rbase = (warp >> 2) * RT;
     const bool act = h < H;
     const TailOp t = p.tail;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* bact = smem + L.b + (h >> 3) * L.lbo_b + (h & 7) * 2;       // + (r/8)*128 + (r%8)*16 ; lo: + (N/8)*128
     auto write_operand = [&](int r, float v) {
       __half hi, lo;
@@ -209,34 +215,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_in);
     };
-    const float* sbias = reinterpret_cast<const float*>(smem + L.bias) + (h & 127);
+    const float* sbias = reinterpret_cast<const float*>(smem + L.bias) + h;
     const float bias_last = sbias[(NL - 1) * 128];
     // small row counts: diffusion / tanh(y) are evaluated in the shadow of the layer-0 MMAs and kept in
-    // registers; NR = 32 has no registers to spare and evaluates them inside the update loop
-    constexpr bool PRE = NR <= 16;
-    constexpr int NP = PRE ? NR : 1;
+    // registers; RT = 16 has no registers to spare and evaluates them inside the update loop
+    constexpr bool PRE = RT <= 8;
+    constexpr int NP = PRE ? RT : 1;
 
-    float y[NR], yprev[NR], gv[NP], dg[NP], thy[NP];
-    int myslot[NR];
+    float y[RT], yprev[RT], gv[NP], dg[NP], thy[NP];
+    int myslot[RT];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const int b = min(row0 + r, p.B - 1);
-      y[r] = act ? p.y0[(size_t)b * H + h] : 0.f;
-      yprev[r] = y[r];
-      myslot[r] = p.row_slot ? p.row_slot[b] : -1;
-      if (PRE) gv[r] = dg[r] = thy[r] = 0.f;
-      if (act) write_operand(r, y[r]);
+    for (int i = 0; i < RT; ++i) {
+      const int b = min(row0 + rbase + i, p.B - 1);
+      y[i] = act ? p.y0[(size_t)b * H + h] : 0.f;
+      yprev[i] = y[i];
+      myslot[i] = p.row_slot ? p.row_slot[b] : -1;
+      if (PRE) gv[i] = dg[i] = thy[i] = 0.f;
+      if (act) write_operand(rbase + i, y[i]);
     }
     auto emit = [&](snsde_emit em) {
       if (!act) return;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        if (row0 + r >= p.B) continue;
-        const float v = em.w_prev * yprev[r] + em.w_curr * y[r];
+      for (int i = 0; i < RT; ++i) {
+        const int gr = row0 + rbase + i;
+        if (gr >= p.B) continue;
+        const float v = em.w_prev * yprev[i] + em.w_curr * y[i];
         if (p.row_slot) {
-          if (myslot[r] == em.slot) p.out[(size_t)(row0 + r) * H + h] = v;
+          if (myslot[i] == em.slot) p.out[(size_t)gr * H + h] = v;
         } else {
-          p.out[((size_t)em.slot * p.B + row0 + r) * H + h] = v;
+          p.out[((size_t)em.slot * p.B + gr) * H + h] = v;
         }
       }
     };
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     auto prepare_state = [&](float cf, float t0) {
       if (!act || !PRE) return;
 #pragma unroll
-      for (int r = 0; r < NP; ++r) state_terms(y[r], cf, t0, gv[r], dg[r], thy[r]);
+      for (int i = 0; i < NP; ++i) state_terms(y[i], cf, t0, gv[i], dg[i], thy[i]);
     };
 
     uint32_t pacc = 0;
@@ -279,20 +286,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         mbar_wait(bar_acc, pacc);
         pacc ^= 1;
         tc_fence_after();
-        float vm[NR], vc[NR];
-        const uint32_t dreg = tmem + lane_base + dcol(l);
+        float vm[RT], vc[RT];
+        const uint32_t dreg = tmem + lane_base + dcol(l) + rbase;
 #pragma unroll
-        for (int c = 0; c < NR; c += 8) {
-          float m8[CH][8], a8[CH][8], b8[CH][8];
+        for (int c = 0; c < RT; c += LW) {
+          float m8[CH][LW], a8[CH][LW], b8[CH][LW];
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch) {
-            tmem_ld8(dreg + Acc::a(ch) + c, m8[ch]);
-            tmem_ld8(dreg + Acc::a(ch) + N + c, a8[ch]);
-            tmem_ld8(dreg + Acc::b(ch) + c, b8[ch]);
+            tmem_ldw<LW>(dreg + Acc::a(ch) + c, m8[ch]);
+            tmem_ldw<LW>(dreg + Acc::a(ch) + N + c, a8[ch]);
+            tmem_ldw<LW>(dreg + Acc::b(ch) + c, b8[ch]);
           }
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < LW; ++i) {
             float m = m8[0][i], cc = a8[0][i] + b8[0][i];
 #pragma unroll
             for (int ch = 1; ch < CH; ++ch) { m += m8[ch][i]; cc += a8[ch][i] + b8[ch][i]; }
@@ -303,30 +310,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
           if (act) {
             const float add = (l == 0) ? add0 : sbias[l * 128];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              float v = fmaf(vc[r], kLoInv, vm[r]) + add;
+            for (int i = 0; i < RT; ++i) {
+              float v = fmaf(vc[i], kLoInv, vm[i]) + add;
               v = v < 0.f ? 0.f : v;                                   // relu feeding the next Linear
-              write_operand(r, v);
+              write_operand(rbase + i, v);
             }
           }
         } else if (act) {
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            float d = fmaf(vc[r], kLoInv, vm[r]) + bias_last;
+          for (int i = 0; i < RT; ++i) {
+            float d = fmaf(vc[i], kLoInv, vm[i]) + bias_last;
             float g, dgy, th;
-            if (PRE) { g = gv[r]; dgy = dg[r]; th = thy[r]; }
-            else state_terms(y[r], cf, si.t0, g, dgy, th);
+            if (PRE) { g = gv[i]; dgy = dg[i]; th = thy[i]; }
+            else state_terms(y[i], cf, si.t0, g, dgy, th);
             if (t.geometric) d *= th;
             if (t.clip_drift) d = tanh_fast(d);
-            const float dw = sdw[r * 128 + h];
-            float yn = __fadd_rn(__fadd_rn(y[r], __fmul_rn(d, si.h)), __fmul_rn(g, dw));
+            const float dw = sdw[(rbase + i) * 128 + h];
+            float yn = __fadd_rn(__fadd_rn(y[i], __fmul_rn(d, si.h)), __fmul_rn(g, dw));
             if (t.milstein) {
               const float v2 = __fmul_rn(dw, dw) - si.h;
               yn = __fadd_rn(yn, 0.5f * ((g * v2) * dgy));
             }
-            yprev[r] = y[r];
-            y[r] = yn;
-            write_operand(r, yn);
+            yprev[i] = y[i];
+            y[i] = yn;
+            write_operand(rbase + i, yn);
           }
         }
         hand_over();
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       if (si.n_emits > 0) emit(si.first);
       for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
     // The whole warp runs this code (descriptor arithmetic stays on the uniform datapath); one elected
     // lane issues the tcgen05 instructions.
@@ -372,11 +379,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       }
       if (p.uses_control && s + 1 < p.S) issue_x(s + 1);
     }
-  } else if (warp < 8) {
+  } else if (warp < kPrepWarp0) {
     // =========================== CONTROL PRODUCER ===========================
     if (p.uses_control) {
-      const int ptid = tid - 160;                       // 0..95
-      const int pwarp = warp - 5;
+      const int ptid = tid - 32 * kProdWarp0;            // 0..95
+      const int pwarp = warp - kProdWarp0;
       const uint32_t row_bytes = 16u * C;
       auto fetch = [&](int s) {                         // spline rows of step s -> staging slot (warp 5 only)
         if (pwarp != 0 || s >= p.S) return;
@@ -397,8 +404,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         fetch(s + p.nstg - 1);
         const int stg = s % p.nstg, slot = s % p.nx;
         const float frac = p.steps[s].frac;
-        mbar_wait(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
-        if (s >= p.nx) mbar_wait(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
+        mbar_wait_relaxed(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
+        if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
         for (int i = ptid; i < NR * C; i += kProdThreads) {
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     // =========================== STEP PREFETCH (time-only work) ===========================
     // Brownian increments (Philox or table), the folded layer-0 bias, the diffusion coefficient and the
     // step/emit descriptors for step s, written to a 2-deep ring one step ahead of the epilogue.
-    const int h = tid - 256;
+    const int h = tid - 32 * kPrepWarp0;
     const bool act = h < H;
     const TailOp t = p.tail;
     const float c0 = act ? p.vec[p.layer[0].bias + h] : 0.f;
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       si.h = st.h; si.t0 = st.t0; si.n_emits = st.emit_end - st.emit_begin; si.emit_begin = st.emit_begin;
       si.first.slot = 0; si.first.w_prev = 0.f; si.first.w_curr = 0.f;
       if (h == 0 && si.n_emits > 0) si.first = p.emits[st.emit_begin];
-      if (s >= 2) mbar_wait(bar_pempty + 8 * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
+      if (s >= 2) mbar_wait_relaxed(bar_pempty + 8 * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
       if (act) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) sdw[r * 128 + h] = dwv[r];
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 // Per-step coefficient of the row-independent noise networks: a_tab[s][h]

@@ -41,6 +41,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Wait used by the roles that run AHEAD of the critical path: back off so the polling does not steal issue
+// slots from the epilogue warp sharing the scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
 // ---- fences -------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -103,6 +114,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
                : "r"(taddr) : "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int W>
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[W]) {
+  static_assert(W == 4 || W == 8, "tmem_ldw width");
+  if constexpr (W == 4) tmem_ld4(taddr, v); else tmem_ld8(taddr, v);
 }
 // registers -> TMEM: thread i of the warp writes 8 consecutive 32-bit columns of TMEM lane (lane_base + i).
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
