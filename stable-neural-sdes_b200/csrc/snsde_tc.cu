@@ -50,10 +50,11 @@ namespace snsde {
 
 using namespace ptx;
 
-constexpr int kTcThreads = 512;
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, each owning half the rows
-constexpr int kMmaWarp = 8;
-constexpr int kProdWarp0 = 9, kPrepWarp0 = 12;
+constexpr int kEpiPerQuad = 2;                     // epilogue warps per TMEM lane quadrant, each owning NR/kEpiPerQuad rows
+constexpr int kEpiWarps = 4 * kEpiPerQuad;
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kProdWarp0 = kMmaWarp + 1, kPrepWarp0 = kProdWarp0 + 3;
+constexpr int kTcThreads = 32 * (kPrepWarp0 + 4);
 constexpr int kProdWarps = 3;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kPrepWarps = 4;
@@ -115,27 +116,30 @@ struct AccRegion {
 };
 
 // All MMAs of one operand segment (executed warp-uniformly; `leader` is the one issuing lane).
-// `touched` has bit c (resp. bit CH+c) set once [main|corrA] (resp. corrB) chain c holds a partial sum.
+// nk (16-wide K chunks) is a multiple of CH; chunk j feeds chain j % CH, so the chain index is a compile-time
+// constant inside the unrolled body.  `fresh`: the region holds no partial sums yet (first segment of a layer).
 template <int N, int CH>
 __device__ __forceinline__ void issue_segment(bool leader, uint32_t a_hi, uint32_t a_lo, uint32_t b_base, int nk,
-                                              uint32_t lbo_b, uint32_t d_tmem, uint32_t& touched, int& chunk) {
+                                              uint32_t lbo_b, uint32_t d_tmem, bool fresh) {
   constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * N), idesc1 = umma_idesc_f16(128, N);
   uint64_t da_hi = umma_smem_desc(a_hi, kALbo, kASbo);
   uint64_t da_lo = umma_smem_desc(a_lo, kALbo, kASbo);
   uint64_t db = umma_smem_desc(b_base, lbo_b, 128);
   const uint64_t a_step = (uint64_t)((2 * kALbo) >> 4), b_step = (uint64_t)((2 * lbo_b) >> 4);
-#pragma unroll 4
-  for (int kb = 0; kb < nk; ++kb) {
-    const int c = chunk & (CH - 1);
-    if (leader) {
-      umma_f16(d_tmem + AccRegion<N, CH>::a(c), da_hi, db, idesc2, (touched >> c) & 1u);
-      umma_f16(d_tmem + AccRegion<N, CH>::b(c), da_lo, db, idesc1, (touched >> (CH + c)) & 1u);
+  uint32_t acc = fresh ? 0u : 1u;
+#pragma unroll 2
+  for (int kb = 0; kb < nk; kb += CH) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      if (leader) {
+        umma_f16(d_tmem + AccRegion<N, CH>::a(c), da_hi, db, idesc2, acc);
+        umma_f16(d_tmem + AccRegion<N, CH>::b(c), da_lo, db, idesc1, acc);
+      }
+      da_hi += a_step;
+      da_lo += a_step;
+      db += b_step;
     }
-    touched |= (1u << c) | (1u << (CH + c));
-    ++chunk;
-    da_hi += a_step;
-    da_lo += a_step;
-    db += b_step;
+    acc = 1u;
   }
 }
 
@@ -193,8 +197,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
 
   if (warp < kEpiWarps) {
     // =========================== EPILOGUE / SDE STATE ===========================
-    // thread = (feature h, row half): TMEM lane quadrant = warp % 4, rows [half*RT, half*RT + RT)
-    constexpr int RT = NR / 2;                         // rows per thread
+    // thread = (feature h, row group): TMEM lane quadrant = warp % 4, rows [(warp/4)*RT, (warp/4)*RT + RT)
+    constexpr int RT = NR / kEpiPerQuad;               // rows per thread
     constexpr int LW = RT < 8 ? RT : 8;                // TMEM load width
     const int h = (warp & 3) * 32 + lane;
     const int rbase = (warp >> 2) * RT;
@@ -351,33 +355,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     const bool leader = elect_one();
     const uint32_t w_base = smem_u32(smem + L.w), b_base = smem_u32(smem + L.b), x_base = smem_u32(smem + L.x);
     uint32_t pin = 0;
-    uint32_t touched0 = 0;                 // chain state of layer 0's region (the X(t) segment is issued early)
-    int chunk0 = 0;
-    auto issue_x = [&](int s) {
-      const int slot = s % p.nx;
-      mbar_wait(bar_xfull + 8 * slot, (uint32_t)((s / p.nx) & 1));
+    int xslot = 0;
+    uint32_t xphase = 0;
+    auto issue_x = [&]() {                 // X(t) segment of the NEXT step's layer 0, issued a layer early
+      mbar_wait(bar_xfull + 8 * xslot, xphase);
       tc_fence_after();
-      touched0 = 0; chunk0 = 0;
-      issue_segment<N, CH>(leader, w_base + p.ax_hi, w_base + p.ax_lo, x_base + slot * L.x_slot_bytes, Cpad / 16, L.lbo_b,
-                           tmem + dcol(0), touched0, chunk0);
-      if (leader) umma_commit(bar_xempty + 8 * slot);
+      issue_segment<N, CH>(leader, w_base + p.ax_hi, w_base + p.ax_lo, x_base + xslot * L.x_slot_bytes, Cpad / 16, L.lbo_b,
+                           tmem + dcol(0), true);
+      if (leader) umma_commit(bar_xempty + 8 * xslot);
       __syncwarp();
+      if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
     };
-    if (p.uses_control && p.S > 0) issue_x(0);
+    if (p.uses_control && p.S > 0) issue_x();
     for (int s = 0; s < p.S; ++s) {
       for (int l = 0; l < NL; ++l) {
         mbar_wait(bar_in, pin);
         pin ^= 1;
         tc_fence_after();
-        uint32_t touched = 0;
-        int chunk = 0;
-        if (l == 0 && p.uses_control) { touched = touched0; chunk = chunk0; }
         issue_segment<N, CH>(leader, w_base + p.layer[l].a_hi, w_base + p.layer[l].a_lo, b_base, p.layer[l].K / 16, L.lbo_b,
-                             tmem + dcol(l), touched, chunk);
+                             tmem + dcol(l), !(l == 0 && p.uses_control));
         if (leader) umma_commit(bar_acc);
         __syncwarp();
       }
-      if (p.uses_control && s + 1 < p.S) issue_x(s + 1);
+      if (p.uses_control && s + 1 < p.S) issue_x();
     }
   } else if (warp < kPrepWarp0) {
     // =========================== CONTROL PRODUCER ===========================
@@ -513,7 +513,7 @@ static bool is_emb_opt(int io) { return io == 2 || io == 4 || io == 6; }
 
 static size_t tc_weight_bytes(const snsde_model_desc& d) {
   const int H = d.hidden, L = d.num_hidden_layers;
-  const int Cpad = (d.input_channels + 15) & ~15;
+  const int Cpad = (d.input_channels + 31) & ~31;
   size_t k_total = (size_t)H * (L + 1) + (is_emb_opt(d.input_option) ? Cpad : 0);
   return k_total * 128 * 2 * 2;
 }
@@ -525,10 +525,10 @@ bool tc_supported(const snsde_model_desc& d, int cc_major, int smem_optin) {
   if (io == 0) { g_reason = "input_option 0 (control only) runs on the FMA kernel"; return false; }
   if (no == 14 || no == 15 || no == 18 || no == 19) { g_reason = "state-network noise options run on the FMA kernel"; return false; }
   if (d.hidden != d.hidden_hidden) { g_reason = "needs hidden_hidden == hidden"; return false; }
-  // hidden >= 32: every layer must feed each of the 2 accumulator chains at least one 16-wide K chunk
-  if (d.hidden % 16 || d.hidden < 32 || d.hidden > 128) { g_reason = "needs hidden in {32,48,...,128}"; return false; }
+  // K chunks are issued in pairs, one per accumulator chain
+  if (d.hidden % 32 || d.hidden < 32 || d.hidden > 128) { g_reason = "needs hidden in {32,64,96,128}"; return false; }
   if (d.num_hidden_layers + 1 > kTcMaxLayers) { g_reason = "too many hidden layers"; return false; }
-  const int Cpad = (d.input_channels + 15) & ~15;
+  const int Cpad = (d.input_channels + 31) & ~31;
   const TcSmem L = tc_smem_layout((int)tc_weight_bytes(d), d.hidden, d.input_channels, Cpad, 16, 8, 2, 2, is_emb_opt(io));
   if (L.total > smem_optin) { g_reason = "weights + operand buffers exceed shared memory"; return false; }
   return true;
@@ -568,7 +568,7 @@ int tc_set_weights(TcPlan& tc, const snsde_model_desc& d, const Program& pg, con
                    cudaStream_t stream) {
   const int C = d.input_channels, H = d.hidden, L = d.num_hidden_layers, io = d.input_option, no = d.noise_option;
   const int tau = is_time_opt(io) ? 2 : 0;
-  const int Cpad = (C + 15) & ~15;
+  const int Cpad = (C + 31) & ~31;          // whole pairs of 16-wide K chunks (two accumulator chains)
   const float* q = blob;
   auto take = [&](size_t n) { const float* r = q; q += n; return r; };
   const float* Wi = take((size_t)H * C); const float* bi = take(H);

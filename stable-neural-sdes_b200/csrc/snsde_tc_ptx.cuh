@@ -122,10 +122,15 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float (&v)[2]) {
+  uint32_t r[2];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+  v[0] = __uint_as_float(r[0]); v[1] = __uint_as_float(r[1]);
+}
 template <int W>
 __device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[W]) {
-  static_assert(W == 4 || W == 8, "tmem_ldw width");
-  if constexpr (W == 4) tmem_ld4(taddr, v); else tmem_ld8(taddr, v);
+  static_assert(W == 2 || W == 4 || W == 8, "tmem_ldw width");
+  if constexpr (W == 2) tmem_ld2(taddr, v); else if constexpr (W == 4) tmem_ld4(taddr, v); else tmem_ld8(taddr, v);
 }
 // registers -> TMEM: thread i of the warp writes 8 consecutive 32-bit columns of TMEM lane (lane_base + i).
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {

@@ -311,7 +311,7 @@ TC_CASES = [
     (4, 17, 32, 3, 3, 9, "euler"),
     (3, 6, 64, 4, 1, 33, "milstein"),        # no control read, diagonal sigma * y
     (1, 3, 128, 4, 1, 12, "euler"),
-    (5, 13, 48, 7, 2, 27, "euler"),          # geometric drift, Linear(2,H) noise * y
+    (5, 13, 96, 7, 2, 27, "euler"),          # geometric drift, Linear(2,H) noise * y
     (2, 0, 32, 2, 1, 5, "euler"),
     (6, 9, 64, 6, 1, 300, "euler"),          # B > 148*... multiple rows per CTA (NR=16)
 ]
