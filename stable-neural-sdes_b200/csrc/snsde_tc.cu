@@ -34,6 +34,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -60,6 +62,11 @@ constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kPrepWarps = 4;
 constexpr uint32_t kASbo = 128, kALbo = 2048;      // A images: 16 row groups contiguous, then K chunks
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+
+// clock64 trace (debug aid, enabled by the SNSDE_TC_TRACE environment variable): 16 events per step, CTA 0.
+enum TraceEv { EV_EPI_ACC0 = 0, EV_EPI_LD0, EV_EPI_DONE0, EV_EPI_ACC1, EV_EPI_LD1, EV_EPI_DONE1, EV_EPI_SHADOW_END,
+               EV_MMA_WAKE0, EV_MMA_COMMIT0, EV_MMA_WAKE1, EV_MMA_COMMIT1, EV_MMA_X_DONE, EV_PREP_DONE, EV_PROD_DONE };
+#define TC_TRACE(cond, step, ev) do { if (p.dbg != nullptr && blockIdx.x == 0 && (cond)) p.dbg[(size_t)(step) * 16 + (ev)] = clock64(); } while (0)
 
 // Per-step broadcast block written by the step-prefetch warps (ring of 2).
 struct StepInfo {
@@ -145,11 +152,10 @@ __device__ __forceinline__ void issue_segment(bool leader, uint32_t a_hi, uint32
 
 // DIFF = 1: the diffusion is tanh(sigmoid(theta) * nan_to_num(coef * y)) (noise options 3,6,13,17) - the
 // form of every proposed model with multiplicative noise; DIFF = 0: generic (runtime-selected) form.
-template <int NR, int DIFF>
+template <int NR, int DIFF, int CH>
 __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams p) {
   constexpr int N = NR < 16 ? 16 : NR;              // MMA N (rows padded to >= 16)
-  constexpr int CH = N <= 16 ? 2 : 1;               // accumulator chains per product (TMEM: 3 regions x CH*3N columns)
-  using Acc = AccRegion<N, CH>;
+  using Acc = AccRegion<N, CH>;                     // CH accumulator chains per product; 2 regions of CH*3N columns
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, C = p.C, Cpad = p.Cpad, NL = p.NL;
@@ -162,8 +168,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   const uint32_t bar_cfull = smem_u32(&bars[2 + 2 * p.nx]);
   const uint32_t bar_pfull = smem_u32(&bars[2 + 2 * p.nx + p.nstg]), bar_pempty = bar_pfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 + 2 * p.nx + p.nstg + 4]);
-  constexpr uint32_t kTmemCols = (3 * Acc::kCols <= 128) ? 128 : (3 * Acc::kCols <= 256 ? 256 : 512);
-  static_assert(3 * Acc::kCols <= 512, "TMEM budget");
+  // Two accumulator regions suffice: layer 0 owns region 0 (the X(t) segment of the NEXT step is issued into it
+  // while the last layer's epilogue still reads), every later layer reuses region 1 (its MMAs are only issued
+  // after the previous layer's epilogue has drained that region).
+  constexpr uint32_t kTmemCols = (2 * Acc::kCols <= 128) ? 128 : (2 * Acc::kCols <= 256 ? 256 : 512);
+  static_assert(2 * Acc::kCols <= 512, "TMEM budget");
 
   // ---- one-time setup: weights -> smem, zero the operand buffers, barriers, TMEM ----
   {
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  auto dcol = [&](int l) -> uint32_t { return (uint32_t)((l == 0 ? 0 : 1 + ((l - 1) & 1)) * Acc::kCols); };
+  auto dcol = [&](int l) -> uint32_t { return (uint32_t)((l == 0 ? 0 : 1) * Acc::kCols); };
 
   if (warp < kEpiWarps) {
     // =========================== EPILOGUE / SDE STATE ===========================
@@ -290,6 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         mbar_wait(bar_acc, pacc);
         pacc ^= 1;
         tc_fence_after();
+        TC_TRACE(tid == 0 && l < 2, s, l == 0 ? EV_EPI_ACC0 : EV_EPI_ACC1);
         float vm[RT], vc[RT];
         const uint32_t dreg = tmem + lane_base + dcol(l) + rbase;
 #pragma unroll
@@ -302,6 +312,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
             tmem_ldw<LW>(dreg + Acc::b(ch) + c, b8[ch]);
           }
           tmem_ld_wait();
+          TC_TRACE(tid == 0 && l < 2 && c == 0, s, l == 0 ? EV_EPI_LD0 : EV_EPI_LD1);
 #pragma unroll
           for (int i = 0; i < LW; ++i) {
             float m = m8[0][i], cc = a8[0][i] + b8[0][i];
@@ -341,12 +352,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
           }
         }
         hand_over();
+        TC_TRACE(tid == 0 && l < 2, s, l == 0 ? EV_EPI_DONE0 : EV_EPI_DONE1);
       }
       // ---- in the shadow of the next step's layer-0 MMAs ----
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pempty + 8 * (s & 1));             // slot consumed
       if (si.n_emits > 0) emit(si.first);
       for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);
+      TC_TRACE(tid == 0, s, EV_EPI_SHADOW_END);
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
@@ -372,12 +385,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         mbar_wait(bar_in, pin);
         pin ^= 1;
         tc_fence_after();
+        TC_TRACE(lane == 0 && l < 2, s, l == 0 ? EV_MMA_WAKE0 : EV_MMA_WAKE1);
         issue_segment<N, CH>(leader, w_base + p.layer[l].a_hi, w_base + p.layer[l].a_lo, b_base, p.layer[l].K / 16, L.lbo_b,
                              tmem + dcol(l), !(l == 0 && p.uses_control));
         if (leader) umma_commit(bar_acc);
         __syncwarp();
+        TC_TRACE(lane == 0 && l < 2, s, l == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1);
       }
       if (p.uses_control && s + 1 < p.S) issue_x();
+      TC_TRACE(lane == 0, s, EV_MMA_X_DONE);
     }
   } else if (warp < kPrepWarp0) {
     // =========================== CONTROL PRODUCER ===========================
@@ -423,6 +439,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);
+        TC_TRACE(ptid == 0, s, EV_PROD_DONE);
       }
     }
   } else {
@@ -472,6 +489,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       if (h == 0) *reinterpret_cast<StepInfo*>(slot + (NR + 2) * 512) = si;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pfull + 8 * (s & 1));
+      TC_TRACE(h == 0, s, EV_PREP_DONE);
     }
   }
 
@@ -670,9 +688,9 @@ int tc_set_weights(TcPlan& tc, const snsde_model_desc& d, const Program& pg, con
   return SNSDE_OK;
 }
 
-template <int NR, int DIFF>
+template <int NR, int DIFF, int CH>
 static cudaError_t tc_launch_one(const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = snsde_tc_kernel<NR, DIFF>;
+  auto kern = snsde_tc_kernel<NR, DIFF, CH>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, kTcThreads, smem, stream>>>(p);
@@ -698,6 +716,13 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
     *n_launches += 1;
   }
   p.a_tab = tc.d_atab;
+  p.dbg = nullptr;
+  static long long* s_dbg = nullptr;
+  if (getenv("SNSDE_TC_TRACE") != nullptr && a.S > 0) {
+    if (s_dbg == nullptr) cudaMalloc(&s_dbg, sizeof(long long) * 16 * 4096);
+    cudaMemsetAsync(s_dbg, 0, sizeof(long long) * 16 * 4096, stream);
+    if (a.S <= 4096) p.dbg = s_dbg;
+  }
   // rows per CTA: the fewest that still covers the batch in one wave; then whatever shared memory allows
   int NR = 8;
   while (NR < 32 && (a.B + NR - 1) / NR > tc.num_sms) NR *= 2;
@@ -718,15 +743,29 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
   const int grid = (a.B + NR - 1) / NR;
   cudaError_t e;
   const bool fast_diff = p.tail.bounded && p.tail.special == SP_NONE && p.tail.mult == MU_Y;
+  // Two accumulator chains per product.  (Four chains were measured on c2/c3: the MMA phase gets shorter but
+  // the extra TMEM loads/adds in the epilogue cost more - the template parameter is kept for experiments.)
   switch (NR * 2 + (fast_diff ? 1 : 0)) {
-    case 16: e = tc_launch_one<8, 0>(p, grid, L.total, stream); break;
-    case 17: e = tc_launch_one<8, 1>(p, grid, L.total, stream); break;
-    case 32: e = tc_launch_one<16, 0>(p, grid, L.total, stream); break;
-    case 33: e = tc_launch_one<16, 1>(p, grid, L.total, stream); break;
-    case 64: e = tc_launch_one<32, 0>(p, grid, L.total, stream); break;
-    default: e = tc_launch_one<32, 1>(p, grid, L.total, stream); break;
+    case 16: e = tc_launch_one<8, 0, 2>(p, grid, L.total, stream); break;
+    case 17: e = tc_launch_one<8, 1, 2>(p, grid, L.total, stream); break;
+    case 32: e = tc_launch_one<16, 0, 2>(p, grid, L.total, stream); break;
+    case 33: e = tc_launch_one<16, 1, 2>(p, grid, L.total, stream); break;
+    case 64: e = tc_launch_one<32, 0, 2>(p, grid, L.total, stream); break;
+    default: e = tc_launch_one<32, 1, 2>(p, grid, L.total, stream); break;
   }
   if (e == cudaSuccess) *n_launches += 1;
+  if (p.dbg != nullptr && e == cudaSuccess) {             // debug only: synchronous dump of the trace
+    std::vector<long long> hbuf((size_t)16 * a.S);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(getenv("SNSDE_TC_TRACE"), "w");
+    if (f) {
+      for (int s2 = 0; s2 < a.S; ++s2) {
+        for (int k = 0; k < 16; ++k) fprintf(f, "%lld%c", hbuf[(size_t)s2 * 16 + k], k == 15 ? '\n' : ' ');
+      }
+      fclose(f);
+    }
+  }
   return e;
 }
 

@@ -34,6 +34,7 @@ struct TcParams {
   unsigned long long seed, row_offset;
   float* out;
   int nx, nstg;              // control-operand ring depth, coefficient staging depth
+  long long* dbg;            // optional: clock64 trace of CTA 0 (SNSDE_TC_TRACE env), [step][event]
 };
 
 // Per-step table of the row-independent noise networks (options 12,13,16,17).
