@@ -191,13 +191,14 @@ def cpu_reference_solver(w, B, seed=0):
     return run, w["S"]
 
 
-def time_cpu_reference(w, B, repeats, warmup=1):
+def time_cpu_reference(w, B, budget_s=12.0, max_repeats=200, warmup=1):
+    """Bounded sample: full solves of the workload until ~budget_s of CPU work (10-30 s band of the contract)."""
     torch.set_num_threads(os.cpu_count())
     run, S = cpu_reference_solver(w, B)
     for _ in range(warmup):
         run()
     ts = []
-    for _ in range(repeats):
+    while sum(ts) < budget_s and len(ts) < max_repeats:
         t0 = time.perf_counter(); run(); ts.append(time.perf_counter() - t0)
     return B * S / statistics.median(ts), ts
 
@@ -306,10 +307,13 @@ def main():
                 dist.all_gather_into_tensor(gather.view(n_out, world, B, H).transpose(0, 1).contiguous(), z)
         return gather
 
-    # end-to-end step: the public API with HOST (pinned) inputs; H2D + solve + D2H of the latents
-    host_out = torch.empty((B, H) if w["out"] == "final_index" else (n_out, B, H)).pin_memory()
+    # end-to-end step: the public API with HOST (pinned) inputs; H2D + solve + D2H of the latents.  Steps are
+    # double-buffered over two CUDA streams so the H2D of step i+1 overlaps the solve of step i; every step's
+    # copies and result read-back are inside the timed region.
+    e2e_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    host_outs = [torch.empty((B, H) if w["out"] == "final_index" else (n_out, B, H)).pin_memory() for _ in range(2)]
 
-    def step_e2e(i):
+    def enqueue_e2e(i):
         times, coeffs, z0, fi = pinned[i % N_INPUT_SETS]
         t_d = times.to(dev, non_blocking=True)
         c_d = coeffs.to(dev, non_blocking=True)
@@ -325,9 +329,19 @@ def main():
         if world > 1:
             buf = torch.empty((world, *z.shape), device=dev)
             dist.all_gather_into_tensor(buf, z)
-        host_out.copy_(z, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return host_out
+        host_outs[i % 2].copy_(z, non_blocking=True)
+
+    def run_e2e(n):
+        pending = None
+        for i in range(n):
+            st = e2e_streams[i % 2]
+            with torch.cuda.stream(st):
+                enqueue_e2e(i)
+            if pending is not None:
+                pending.synchronize()              # step i-1 fully done (result is in host memory)
+            pending = st
+        pending.synchronize()
+    host_out = host_outs[0]
 
     h2d = sum(t.numel() * t.element_size() for t in pinned[0])
     d2h = host_out.numel() * 4
@@ -372,12 +386,10 @@ def main():
         dev_ms = max_over_ranks(evs[0][0].elapsed_time(evs[-1][1]))       # whole K-step region on the device
         kern_ms = statistics.mean(per_step_ms)
 
-        for i in range(args.warmup):
-            step_e2e(i)
+        run_e2e(args.warmup)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            step_e2e(i)
+        run_e2e(args.steps)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
 
@@ -404,9 +416,9 @@ def main():
                      "note": "latency-bound chain of small dependent GEMMs (SURVEY 8d); both fractions reported"})
         cpu = None
         if not args.no_cpu_baseline:
-            v, ts_cpu = time_cpu_reference(w, B, repeats=3)
+            v, ts_cpu = time_cpu_reference(w, B)
             cpu = {"value": v, "unit": "SDE-steps/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"median of 3 full solves of the workload (B={B}, S={S}); {sum(ts_cpu):.1f}s of CPU work"}
+                   "sample": f"median of {len(ts_cpu)} full solves of the workload (B={B}, S={S}); {sum(ts_cpu):.1f}s of CPU work"}
         line = {
             "metric": "SDE-steps/sec", "value": value, "unit": "SDE-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
