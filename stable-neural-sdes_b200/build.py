@@ -2,9 +2,11 @@
 
     python stable-neural-sdes_b200/build.py [--force] [--verbose]
 
-Produces ``stable-neural-sdes_b200/libsnsde.so`` next to this file; it is git-ignored but
-travels to the GPU box with the repo snapshot.
+Each csrc/*.cu is compiled to an object (cached by content hash of the unit + all headers, in parallel) and
+linked into ``stable-neural-sdes_b200/libsnsde.so``; objects and the library are git-ignored but travel to the
+GPU box with the repo snapshot.
 """
+import concurrent.futures
 import hashlib
 import pathlib
 import subprocess
@@ -12,34 +14,49 @@ import sys
 
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
+OBJ = HERE / "build"
 LIB = HERE / "libsnsde.so"
-STAMP = HERE / ".libsnsde.stamp"
-SOURCES = ["snsde_api.cu", "snsde_fma.cu", "snsde_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
-def _fingerprint():
+def _headers_hash():
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "snsde.h"]):
+    for p in sorted(list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "snsde.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    fp = _fingerprint()
-    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text() == fp:
-        return LIB
-    cmd = ["nvcc", *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB),
-           *[str(CSRC / s) for s in SOURCES]]
+def _compile(src, hdr_hash, force, verbose):
+    obj = OBJ / (src.stem + ".o")
+    stamp = OBJ / (src.stem + ".stamp")
+    fp = hashlib.sha256(src.read_bytes() + hdr_hash.encode()).hexdigest()
+    if not force and obj.exists() and stamp.exists() and stamp.read_text() == fp:
+        return obj, False, ""
+    cmd = ["nvcc", *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", str(obj), str(src)]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libsnsde.so")
-    STAMP.write_text(fp)
+        raise RuntimeError(f"nvcc failed on {src.name}:\n{res.stdout}{res.stderr}")
+    stamp.write_text(fp)
+    return obj, True, res.stdout + res.stderr
+
+
+def build(force=False, verbose=False):
+    OBJ.mkdir(exist_ok=True)
+    hdr_hash = _headers_hash()
+    sources = sorted(CSRC.glob("*.cu"))
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        results = list(ex.map(lambda s: _compile(s, hdr_hash, force, verbose), sources))
+    if verbose:
+        for _, _, log in results:
+            sys.stderr.write(log)
+    if any(changed for _, changed, _ in results) or not LIB.exists():
+        cmd = ["nvcc", "-shared", "-o", str(LIB), *[str(o) for o, _, _ in results]]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,6 +14,7 @@
 #include "snsde_common.cuh"
 #include "snsde_rng.cuh"
 #include "snsde_tc.cuh"
+#include "snsde_tcg.cuh"
 
 namespace snsde {
 size_t fma_smem_bytes(const Program& pg, int R, int smem_w_floats);
@@ -41,12 +43,13 @@ static int fail(int code, const char* fmt, ...) {
 struct snsde_plan {
   snsde_model_desc desc;
   int device = 0, num_sms = 0, smem_optin = 0;
-  int kind = 0;                       // 0 FMA, 1 tcgen05
+  int kind = 0;                       // 0 FMA, 1 tcgen05 (weights resident), 2 tcgen05 (general: streamed weights, 2 M tiles, noise nets)
   bool has_weights = false;
   Program prog;
   float* d_wimg = nullptr;
   int wimg_floats = 0;
-  TcPlan tc;                          // tensor-core path state (unused when kind == 0)
+  TcPlan tc;                          // tensor-core path state (kind == 1)
+  TcgPlan tcg;                        // general tensor-core path state (kind == 2)
   snsde_step* d_steps = nullptr; int steps_cap = 0; std::vector<snsde_step> h_steps;
   snsde_emit* d_emits = nullptr; int emits_cap = 0; std::vector<snsde_emit> h_emits;
   int64_t launches = 0;
@@ -341,12 +344,14 @@ int snsde_plan_create(const snsde_model_desc* desc, int device, snsde_plan** out
   if (e != cudaSuccess) { delete p; return fail(SNSDE_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
   p->num_sms = prop.multiProcessorCount;
   p->smem_optin = (int)prop.sharedMemPerBlockOptin;
-  const bool tc_ok = tc_supported(*desc, prop.major, p->smem_optin);
-  if (desc->precision == SNSDE_PRECISION_TC && !tc_ok) {
+  const bool force_general = getenv("SNSDE_FORCE_TCG") != nullptr;           // testing aid: general kernel even where the resident one applies
+  const bool tc_ok = tc_supported(*desc, prop.major, p->smem_optin) && !force_general;
+  const bool tcg_ok = tcg_supported(*desc, prop.major, p->smem_optin);
+  if (desc->precision == SNSDE_PRECISION_TC && !tc_ok && !tcg_ok) {
     delete p;
-    return fail(SNSDE_ERR_UNSUPPORTED, "tensor-core path does not support this model/shape/device: %s", tc_unsupported_reason());
+    return fail(SNSDE_ERR_UNSUPPORTED, "tensor-core path does not support this model/shape/device: %s", tcg_unsupported_reason());
   }
-  p->kind = (desc->precision != SNSDE_PRECISION_FP32 && tc_ok) ? 1 : 0;
+  p->kind = desc->precision == SNSDE_PRECISION_FP32 ? 0 : (tc_ok ? 1 : (tcg_ok ? 2 : 0));
   *out_plan = p;
   return SNSDE_OK;
 }
@@ -358,6 +363,7 @@ int snsde_plan_destroy(snsde_plan* p) {
   cudaFree(p->d_steps);
   cudaFree(p->d_emits);
   tc_release(p->tc);
+  tcg_release(p->tcg);
   delete p;
   return SNSDE_OK;
 }
@@ -398,6 +404,11 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
     const int rc = tc_set_weights(p->tc, p->desc, p->prog, blob, p->num_sms, p->smem_optin, stream);
     if (rc == SNSDE_ERR_UNSUPPORTED && p->desc.precision == SNSDE_PRECISION_AUTO) p->kind = 0;   // e.g. weights beyond fp16 range
     else if (rc != SNSDE_OK) return fail(rc, "tensor-core weight packing failed: %s", tc_unsupported_reason());
+  }
+  if (p->kind == 2) {
+    const int rc = tcg_set_weights(p->tcg, p->desc, p->prog, blob, p->num_sms, p->smem_optin, stream);
+    if (rc == SNSDE_ERR_UNSUPPORTED && p->desc.precision == SNSDE_PRECISION_AUTO) p->kind = 0;
+    else if (rc != SNSDE_OK) return fail(rc, "tensor-core weight packing failed: %s", tcg_unsupported_reason());
   }
   p->has_weights = true;
   return SNSDE_OK;
@@ -465,13 +476,13 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
   int rc = upload_tables(p, steps_host, S, emits_host, E, stream);
   if (rc != SNSDE_OK) return rc;
 
-  if (p->kind == 1) {
+  if (p->kind >= 1) {
     TcForwardArgs a;
     a.coeffs = coeffs_dev; a.coeff_row_stride = coeff_row_stride; a.y0 = y0_dev; a.B = B;
     a.steps = p->d_steps; a.steps_host = steps_host; a.S = S; a.emits = p->d_emits; a.n_init_emits = n_init_emits;
     a.n_out = n_out; a.row_slot = row_slot_dev; a.dW = dW_dev; a.seed = seed; a.row_offset = row_offset; a.out = out_dev;
     int nl = 0;
-    cudaError_t e = tc_forward(p->tc, a, stream, &nl);
+    cudaError_t e = p->kind == 1 ? tc_forward(p->tc, a, stream, &nl) : tcg_forward(p->tcg, a, stream, &nl);
     if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "tcgen05 kernel launch: %s", cudaGetErrorString(e));
     p->launches += nl;
     return SNSDE_OK;

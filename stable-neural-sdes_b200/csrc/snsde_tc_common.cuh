@@ -1,0 +1,48 @@
+// Device helpers shared by the two tcgen05 kernels (snsde_tc.cu: weights resident; snsde_tcg_kernel.cuh: general).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "snsde_common.cuh"
+#include "snsde_tc_ptx.cuh"
+
+namespace snsde {
+
+using namespace ptx;
+
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+
+// clock64 trace (debug aid, enabled by the SNSDE_TC_TRACE environment variable): 16 events per step, CTA 0.
+enum TraceEv { EV_EPI_ACC0 = 0, EV_EPI_LD0, EV_EPI_DONE0, EV_EPI_ACC1, EV_EPI_LD1, EV_EPI_DONE1, EV_EPI_SHADOW_END,
+               EV_MMA_WAKE0, EV_MMA_COMMIT0, EV_MMA_WAKE1, EV_MMA_COMMIT1, EV_MMA_X_DONE, EV_PREP_DONE, EV_PROD_DONE };
+#define TC_TRACE(cond, step, ev) do { if (p.dbg != nullptr && blockIdx.x == 0 && (cond)) p.dbg[(size_t)(step) * 16 + (ev)] = clock64(); } while (0)
+
+// Per-step broadcast block written by the step-prefetch warps (ring of 2).
+struct StepInfo {
+  float h, t0;
+  int n_emits, emit_begin;
+  snsde_emit first;          // the first emit of the step (almost every step has at most one)
+};
+
+// fp16 split of an fp32 value: hi (saturating) and the 2^11-scaled residual
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  hi = __ushort_as_half(h);
+  lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
+}
+
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
+// TMEM accumulator region of one layer.  Dependent tcgen05.mma's into the SAME accumulator are ~84 cycles
+// apart on B200 (measured, tests/cuda/umma_probe.cu) whatever the tile size, so the K chunks of a layer are
+// spread over CH independent chains per product and summed in the epilogue:
+//   [main|corrA] chains  (Whi x [ahi;alo'], 2N columns each) : columns [c*2N, (c+1)*2N),            c < CH
+//   corrB chains         (Wlo' x ahi,        N columns each) : columns [CH*2N + c*N, CH*2N+(c+1)*N)
+template <int N, int CH>
+struct AccRegion {
+  static constexpr int kCols = CH * 3 * N;
+  __device__ static constexpr uint32_t a(int c) { return (uint32_t)(c * 2 * N); }
+  __device__ static constexpr uint32_t b(int c) { return (uint32_t)(CH * 2 * N + c * N); }
+};
+
+}  // namespace snsde

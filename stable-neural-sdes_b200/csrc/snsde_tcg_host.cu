@@ -1,0 +1,328 @@
+// Host side of the general tcgen05 path: weight images (fp64 collapse, fp16 hi/lo tiles), MMA job table,
+// residency/streaming decision per launch, dispatch to the instantiated kernels.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "snsde_tcg_kernel.cuh"
+
+namespace snsde {
+
+__global__ void snsde_tc_tables_kernel(const float* __restrict__ vec, TcNoiseNet nn, int H,
+                                       const snsde_step* __restrict__ steps, float* __restrict__ a_tab);
+
+static std::string g_greason = "";
+const char* tcg_unsupported_reason() { return g_greason.c_str(); }
+
+static bool g_is_time_opt(int io) { return io >= 3 && io <= 6; }
+static bool g_is_emb_opt(int io) { return io == 2 || io == 4 || io == 6; }
+static int g_noise_layers(int no) { return (no == 14 || no == 15) ? 1 : ((no == 18 || no == 19) ? 2 : 0); }
+
+bool tcg_supported(const snsde_model_desc& d, int cc_major, int smem_optin) {
+  (void)smem_optin;
+  const int io = d.input_option, no = d.noise_option, H = d.hidden;
+  if (cc_major != 10) { g_greason = "needs an sm_100 device"; return false; }
+  if (d.family != SNSDE_FAMILY_BENCHMARK) { g_greason = "tutorial family runs on the FMA kernel"; return false; }
+  if (io == 0) { g_greason = "input_option 0 (control only) runs on the FMA kernel"; return false; }
+  if (d.hidden != d.hidden_hidden) { g_greason = "needs hidden_hidden == hidden"; return false; }
+  if (H % 32 || H < 32 || H > 256) { g_greason = "needs hidden in {32,64,...,256}"; return false; }
+  const int MT = H > 128 ? 2 : 1, nets = g_noise_layers(no) ? 2 : 1;
+  if (nets * MT > 2) { g_greason = "hidden > 128 with a state-dependent noise network exceeds the TMEM accumulator budget"; return false; }
+  if (d.num_hidden_layers + 1 > kTcgMaxPhases) { g_greason = "too many hidden layers"; return false; }
+  return true;
+}
+
+namespace {
+struct GImage {
+  std::vector<uint8_t> bytes;          // all job tiles, job after job: [chunk][hi 4 KB | lo 4 KB]
+  std::vector<float> vec;
+  float max_abs = 0.f;
+  // W: [rows][K] row-major (fp64); tile = rows [m0, m0+128) ; returns byte offset, nk chunks (Kpad/16)
+  int add_tile(const std::vector<double>& W, int rows, int K, int Kpad, int m0) {
+    const int off = (int)bytes.size();
+    bytes.resize(bytes.size() + (size_t)(Kpad / 16) * kTcgSlotBytes, 0);
+    for (int m = m0; m < std::min(rows, m0 + 128); ++m)
+      for (int k = 0; k < K; ++k) {
+        const float w = (float)W[(size_t)m * K + k];
+        max_abs = std::max(max_abs, fabsf(w));
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
+        const int ml = m - m0, kc = k / 16, kk = k % 16;
+        const size_t o = (size_t)off + (size_t)kc * kTcgSlotBytes + (size_t)(kk / 8) * kGALbo + (size_t)(ml / 8) * kGASbo +
+                         (ml % 8) * 16 + (kk % 8) * 2;
+        memcpy(&bytes[o], &hi, 2);
+        memcpy(&bytes[o + 4096], &lo, 2);
+      }
+    return off;
+  }
+  int add_vec(const std::vector<double>& v, int HP) {
+    const int off = (int)vec.size();
+    for (double x : v) vec.push_back((float)x);
+    while ((int)vec.size() - off < HP) vec.push_back(0.f);
+    return off;
+  }
+};
+}  // namespace
+
+int tcg_set_weights(TcgPlan& tc, const snsde_model_desc& d, const Program& pg, const float* blob, int num_sms, int smem_optin,
+                    cudaStream_t stream) {
+  const int C = d.input_channels, H = d.hidden, L = d.num_hidden_layers, io = d.input_option, no = d.noise_option;
+  const int tau = g_is_time_opt(io) ? 2 : 0;
+  const int Cpad = (C + 31) & ~31;
+  const int MT = H > 128 ? 2 : 1, HP = 128 * MT;
+  const int NN = g_noise_layers(no), nets = NN ? 2 : 1;
+  const float* q = blob;
+  auto take = [&](size_t n) { const float* r = q; q += n; return r; };
+  const float* Wi = take((size_t)H * C); const float* bi = take(H);
+  const float* Win = take((size_t)H * (H + tau)); const float* bin = take(H);
+  const float *We = nullptr, *be = nullptr;
+  if (g_is_emb_opt(io)) { We = take((size_t)H * 2 * H); be = take(H); }
+  std::vector<const float*> Wl(L - 1), bl(L - 1);
+  for (int l = 0; l < L - 1; ++l) { Wl[l] = take((size_t)H * H); bl[l] = take(H); }
+  const float* Wo = take((size_t)H * H); const float* bo = take(H);
+  take(1);                                                      // theta (folded into pg.tail.s_theta)
+
+  GImage img;
+  TcgParams& P = tc.proto;
+  memset(&P, 0, sizeof(P));
+  P.H = H; P.HP = HP; P.MT = MT; P.C = C; P.Cpad = Cpad; P.NP = L + 1; P.NN = NN; P.nets = nets;
+  P.uses_control = g_is_emb_opt(io);
+  P.coef_vec = -1;
+  for (int i = 0; i < 2; ++i) P.c_sin[i] = P.c_cos[i] = -1;
+  for (int ph = 0; ph < kTcgMaxPhases; ++ph) P.bias[ph][0] = P.bias[ph][1] = -1;
+  P.tail = pg.tail;
+
+  // ---- drift layer 0 (emb o linear_in collapsed in fp64 for input options 2,4,6) ----
+  std::vector<double> W0((size_t)H * H, 0.0), W0x, c0(H), cs(H, 0.0), cc(H, 0.0);
+  if (g_is_emb_opt(io)) {
+    W0x.assign((size_t)H * C, 0.0);
+    for (int i = 0; i < H; ++i) {
+      double acc0 = be[i];
+      for (int j = 0; j < H; ++j) {
+        const double e1 = We[(size_t)i * 2 * H + j], e2 = We[(size_t)i * 2 * H + H + j];
+        acc0 += e1 * bin[j] + e2 * bi[j];
+        if (tau) { cs[i] += e1 * Win[(size_t)j * (H + tau)]; cc[i] += e1 * Win[(size_t)j * (H + tau) + 1]; }
+        for (int k = 0; k < H; ++k) W0[(size_t)i * H + k] += e1 * Win[(size_t)j * (H + tau) + tau + k];
+        for (int c = 0; c < C; ++c) W0x[(size_t)i * C + c] += e2 * Wi[(size_t)j * C + c];
+      }
+      c0[i] = acc0;
+    }
+  } else {
+    for (int i = 0; i < H; ++i) {
+      c0[i] = bin[i];
+      if (tau) { cs[i] = Win[(size_t)i * (H + tau)]; cc[i] = Win[(size_t)i * (H + tau) + 1]; }
+      for (int k = 0; k < H; ++k) W0[(size_t)i * H + k] = Win[(size_t)i * (H + tau) + tau + k];
+    }
+  }
+  auto as_double = [&](const float* W, size_t n) { return std::vector<double>(W, W + n); };
+  P.bias[0][0] = img.add_vec(c0, HP);
+  if (tau) { P.c_sin[0] = img.add_vec(cs, HP); P.c_cos[0] = img.add_vec(cc, HP); }
+
+  // ---- diffusion: coefficient vectors / row-independent nets (table) / state-dependent nets (second network) ----
+  tc.noise.kind = 0;
+  std::vector<double> N1, N2;                                   // noise-net matrices [H][H]
+  if (no >= 1 && no <= 3) take(1);
+  if (no >= 4 && no <= 6) {
+    const float* sd = take(H);
+    std::vector<double> e(H);
+    for (int j = 0; j < H; ++j) e[j] = expf(sd[j]);
+    P.coef_vec = img.add_vec(e, HP);
+  }
+  if (no == 12 || no == 13 || no == 16 || no == 17) {
+    const float* W1 = take((size_t)H * 2); const float* b1 = take(H);
+    std::vector<double> w1t(2 * (size_t)H);
+    for (int j = 0; j < H; ++j) { w1t[j] = W1[2 * j]; w1t[H + j] = W1[2 * j + 1]; }
+    tc.noise.kind = 1;
+    tc.noise.w1t = img.add_vec(w1t, 2 * H);
+    tc.noise.b1 = img.add_vec(as_double(b1, H), H);
+    if (no >= 16) {
+      const float* W2 = take((size_t)H * H); const float* b2 = take(H);
+      std::vector<double> w2t((size_t)H * H);
+      for (int j = 0; j < H; ++j)
+        for (int k = 0; k < H; ++k) w2t[(size_t)k * H + j] = W2[(size_t)j * H + k];
+      tc.noise.kind = 2;
+      tc.noise.w2t = img.add_vec(w2t, H * H);
+      tc.noise.b2 = img.add_vec(as_double(b2, H), H);
+    }
+  }
+  if (NN) {
+    const float* W1 = take((size_t)H * (H + 2)); const float* b1 = take(H);
+    N1.assign((size_t)H * H, 0.0);
+    std::vector<double> ns(H), nc(H);
+    for (int i = 0; i < H; ++i) {
+      ns[i] = W1[(size_t)i * (H + 2)]; nc[i] = W1[(size_t)i * (H + 2) + 1];
+      for (int k = 0; k < H; ++k) N1[(size_t)i * H + k] = W1[(size_t)i * (H + 2) + 2 + k];
+    }
+    P.bias[0][1] = img.add_vec(as_double(b1, H), HP);
+    P.c_sin[1] = img.add_vec(ns, HP); P.c_cos[1] = img.add_vec(nc, HP);
+    P.noise_act[0] = NN == 2 ? ACT_RELU : ACT_NONE;             // Sequential(Linear, ReLU, Linear) then .relu() for 18/19
+    if (NN == 2) {
+      const float* W2 = take((size_t)H * H); const float* b2 = take(H);
+      N2 = as_double(W2, (size_t)H * H);
+      P.bias[1][1] = img.add_vec(as_double(b2, H), HP);
+      P.noise_act[1] = ACT_RELU;
+    }
+  }
+
+  // ---- MMA jobs in issue order; every tile image goes into one global blob (residency is decided per launch) ----
+  int nj = 0;
+  auto add_jobs = [&](const std::vector<double>& W, int K, int Kpad, int phase, int net, int b_src, int fresh) {
+    for (int mt = 0; mt < MT; ++mt) {
+      TcgJob& jb = P.jobs[nj++];
+      jb.phase = phase; jb.acc = net * MT + mt; jb.nk = Kpad / 16; jb.b_src = b_src; jb.b_chunk0 = 0;
+      jb.fresh = fresh; jb.stream = 0; jb.a_off = 0;
+      jb.g_off = img.add_tile(W, H, K, Kpad, mt * 128);
+    }
+  };
+  add_jobs(W0, H, H, 0, 0, 0, P.uses_control ? 0 : 1);
+  if (NN) add_jobs(N1, H, H, 0, 1, 0, 1);
+  for (int l = 0; l < L - 1; ++l) {
+    add_jobs(as_double(Wl[l], (size_t)H * H), H, H, 1 + l, 0, 0, 1);
+    P.bias[1 + l][0] = img.add_vec(as_double(bl[l], H), HP);
+    if (NN == 2 && l == 0) add_jobs(N2, H, H, 1, 1, 1, 1);
+  }
+  add_jobs(as_double(Wo, (size_t)H * H), H, H, L, 0, 0, 1);
+  P.bias[L][0] = img.add_vec(as_double(bo, H), HP);
+  if (NN == 2 && L == 1) add_jobs(N2, H, H, 1, 1, 1, 1);
+  P.n_xjobs = 0;
+  if (P.uses_control) { add_jobs(W0x, C, Cpad, 0, 0, 2, 1); P.n_xjobs = MT; }
+  P.n_jobs = nj;
+  // jobs must be grouped by phase in issue order (the noise layer 1 of a deep drift lands after the drift job of phase 1)
+  std::stable_sort(P.jobs, P.jobs + (P.n_jobs - P.n_xjobs), [](const TcgJob& a, const TcgJob& b) { return a.phase < b.phase; });
+
+  if (!(img.max_abs < 6.0e4f)) { g_greason = "a weight exceeds the fp16 range of the split-precision operands"; return SNSDE_ERR_UNSUPPORTED; }
+
+  auto ensure = [&](void** ptr, int& cap, size_t bytes) -> bool {
+    if ((int)bytes > cap) {
+      cudaFree(*ptr); *ptr = nullptr;
+      if (cudaMalloc(ptr, bytes) != cudaSuccess) return false;
+      cap = (int)bytes;
+    }
+    return true;
+  };
+  if (!ensure((void**)&tc.d_wblob, tc.wblob_cap, img.bytes.size()) ||
+      !ensure((void**)&tc.d_vec, tc.vec_cap, img.vec.size() * sizeof(float))) { g_greason = "cudaMalloc failed"; return SNSDE_ERR_CUDA; }
+  cudaMemcpyAsync(tc.d_wblob, img.bytes.data(), img.bytes.size(), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(tc.d_vec, img.vec.data(), img.vec.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+  P.wblob = tc.d_wblob; P.vec = tc.d_vec;
+  tc.num_sms = num_sms; tc.smem_optin = smem_optin;
+  tc.ready = true;
+  return SNSDE_OK;
+}
+
+cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream, int* n_launches) {
+  TcgParams p = tc.proto;
+  p.coeffs = a.coeffs; p.coeff_row_stride = a.coeff_row_stride; p.y0 = a.y0; p.B = a.B;
+  p.steps = a.steps; p.S = a.S; p.emits = a.emits; p.n_init_emits = a.n_init_emits; p.n_out = a.n_out;
+  p.row_slot = a.row_slot; p.dW = a.dW; p.seed = a.seed; p.row_offset = a.row_offset; p.out = a.out;
+  *n_launches = 0;
+  if (tc.noise.kind != 0 && a.S > 0) {
+    if (a.S * p.H > tc.atab_cap) {
+      cudaFree(tc.d_atab); tc.d_atab = nullptr;
+      cudaError_t e = cudaMalloc(&tc.d_atab, sizeof(float) * (size_t)a.S * p.H);
+      if (e != cudaSuccess) return e;
+      tc.atab_cap = a.S * p.H;
+    }
+    snsde_tc_tables_kernel<<<a.S, 256, 0, stream>>>(tc.d_vec, tc.noise, p.H, a.steps, tc.d_atab);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    *n_launches += 1;
+  }
+  p.a_tab = tc.d_atab;
+  p.dbg = nullptr;
+  static long long* s_dbg = nullptr;
+  if (getenv("SNSDE_TC_TRACE") != nullptr && a.S > 0 && a.S <= 4096) {
+    if (s_dbg == nullptr) cudaMalloc(&s_dbg, sizeof(long long) * 16 * 4096);
+    cudaMemsetAsync(s_dbg, 0, sizeof(long long) * 16 * 4096, stream);
+    p.dbg = s_dbg;
+  }
+
+  const int nacc = p.nets * p.MT;
+  // rows per CTA: fewest that covers the batch in one wave; MT = 2 keeps the state of two features per thread
+  int NR = 8;
+  const int nr_max = p.MT == 2 ? 16 : 32;
+  while (NR < nr_max && (a.B + NR - 1) / NR > tc.num_sms) NR *= 2;
+  TcgSmem L;
+  int CH = 2;
+  for (;;) {
+    const int N = NR < 16 ? 16 : NR;
+    CH = (2 * nacc * 2 * 3 * N <= 512) ? 2 : 1;
+    // X(t) jobs are always resident; then as many others as fit (in issue order), the rest is streamed
+    bool ok = false;
+    for (int cfg = 0; cfg < 3 && !ok; ++cfg) {
+      p.nx = cfg == 0 ? 4 : 2;
+      p.nstg = cfg == 2 ? 2 : 4;
+      size_t total_tiles = 0;
+      for (int j = 0; j < p.n_jobs; ++j) total_tiles += (size_t)p.jobs[j].nk * kTcgSlotBytes;
+      const TcgSmem base = tcg_smem_layout(0, 0, p.HP, p.nets, p.C, p.Cpad, N, NR, p.nx, p.nstg, p.NP, p.uses_control);
+      const long long room = (long long)tc.smem_optin - base.total - 256;
+      if (room < 0) continue;
+      int nslot = 0;
+      if ((long long)total_tiles > room) nslot = 8;
+      long long budget = room - (long long)nslot * kTcgSlotBytes - 16 * nslot;
+      if (budget < 0) continue;
+      int res_bytes = 0, n_stream = 0;
+      std::vector<int> order;
+      for (int j = p.n_jobs - p.n_xjobs; j < p.n_jobs; ++j) order.push_back(j);
+      for (int j = 0; j < p.n_jobs - p.n_xjobs; ++j) order.push_back(j);
+      bool x_ok = true;
+      for (int j : order) {
+        TcgJob& jb = p.jobs[j];
+        const int sz = jb.nk * kTcgSlotBytes;
+        if (nslot == 0 || sz <= budget) { jb.stream = 0; budget -= sz; res_bytes += sz; }
+        else { jb.stream = 1; n_stream += jb.nk; if (jb.b_src == 2) x_ok = false; }
+      }
+      if (!x_ok) continue;
+      // resident jobs are copied once from the global blob (g_off) into a packed smem area (a_off)
+      int packed = 0;
+      for (int j : order) if (!p.jobs[j].stream) { p.jobs[j].a_off = packed; packed += p.jobs[j].nk * kTcgSlotBytes; }
+      p.nslot = nslot; p.n_stream_chunks = n_stream; p.wres_bytes = res_bytes;
+      L = tcg_smem_layout(res_bytes, nslot, p.HP, p.nets, p.C, p.Cpad, N, NR, p.nx, p.nstg, p.NP, p.uses_control);
+      ok = L.total <= tc.smem_optin;
+    }
+    if (ok) break;
+    if (NR == 8) return cudaErrorInvalidConfiguration;
+    NR /= 2;
+  }
+  const int grid = (a.B + NR - 1) / NR;
+  const bool fast_diff = p.tail.bounded && p.tail.special == SP_NONE && p.tail.mult == MU_Y;
+  cudaError_t e = cudaErrorInvalidConfiguration;
+  const int key = NR * 100 + CH * 10 + p.MT;
+#define TCG_CASE(nr, ch, mt)                                                              \
+  case nr * 100 + ch * 10 + mt:                                                          \
+    e = fast_diff ? tcg_launch<nr, ch, mt, 1>(p, grid, L.total, stream) : tcg_launch<nr, ch, mt, 0>(p, grid, L.total, stream); \
+    break;
+  switch (key) {
+    TCG_CASE(8, 2, 1) TCG_CASE(16, 2, 1) TCG_CASE(32, 2, 1) TCG_CASE(32, 1, 1)
+    TCG_CASE(8, 2, 2) TCG_CASE(16, 2, 2)
+    default: break;
+  }
+#undef TCG_CASE
+  if (e == cudaSuccess) *n_launches += 1;
+  if (p.dbg != nullptr && e == cudaSuccess) {
+    std::vector<long long> hbuf((size_t)16 * a.S);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(getenv("SNSDE_TC_TRACE"), "w");
+    if (f) {
+      for (int s2 = 0; s2 < a.S; ++s2)
+        for (int k = 0; k < 16; ++k) fprintf(f, "%lld%c", hbuf[(size_t)s2 * 16 + k], k == 15 ? '\n' : ' ');
+      fclose(f);
+    }
+  }
+  return e;
+}
+
+void tcg_release(TcgPlan& tc) {
+  cudaFree(tc.d_wblob); cudaFree(tc.d_vec); cudaFree(tc.d_atab);
+  tc.d_wblob = nullptr; tc.d_vec = nullptr; tc.d_atab = nullptr; tc.ready = false;
+}
+
+}  // namespace snsde

@@ -1,0 +1,511 @@
+// General tcgen05 kernel (see snsde_tcg.cuh).  Included by the instantiation units only.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "snsde_common.cuh"
+#include "snsde_math.cuh"
+#include "snsde_rng.cuh"
+#include "snsde_tc_common.cuh"
+#include "snsde_tc_ptx.cuh"
+#include "snsde_tcg.cuh"
+
+namespace snsde {
+
+constexpr int kGEpiPerQuad = 2;
+constexpr int kGEpiWarps = 4 * kGEpiPerQuad;          // warps 0..7
+constexpr int kGMmaWarp = kGEpiWarps;                 // warp 8
+constexpr int kGProdWarp0 = kGMmaWarp + 1;            // warps 9..10 : X(t) producer
+constexpr int kGProdWarps = 2;
+constexpr int kGStreamWarp = kGProdWarp0 + kGProdWarps; // warp 11 : weight streamer
+constexpr int kGPrepWarp0 = kGStreamWarp + 1;         // warps 12..15 : step prefetch
+constexpr int kGPrepWarps = 4;
+constexpr int kTcgThreads = 32 * (kGPrepWarp0 + kGPrepWarps);
+constexpr int kGProdThreads = 32 * kGProdWarps;
+constexpr uint32_t kGALbo = 2048, kGASbo = 128;       // inside one 4 KB tile image: [k/8][row/8][row%8][k%8]
+
+struct TcgSmem {
+  int w, ring, b0, b1, x, stg, prep, bias, bars, total;
+  int lbo_b, b_bytes, x_slot_bytes, stg_bytes, prep_bytes, n_bars;
+};
+
+__host__ __device__ inline TcgSmem tcg_smem_layout(int wres_bytes, int nslot, int HP, int nets, int C, int Cpad, int N, int NR,
+                                                   int nx, int nstg, int NP, int uses_control) {
+  TcgSmem s;
+  s.lbo_b = (2 * N / 8) * 128 + 16;
+  s.w = 0;
+  s.ring = (wres_bytes + 127) & ~127;
+  s.b0 = s.ring + nslot * kTcgSlotBytes;
+  s.b_bytes = (HP / 8) * s.lbo_b;
+  s.b1 = s.b0 + s.b_bytes;
+  s.x = s.b1 + (nets > 1 ? s.b_bytes : 0);
+  s.x_slot_bytes = uses_control ? (Cpad / 8) * s.lbo_b : 0;
+  s.stg = s.x + nx * s.x_slot_bytes;
+  s.stg_bytes = uses_control ? NR * 16 * C : 0;
+  s.prep = (s.stg + nstg * s.stg_bytes + 15) & ~15;
+  s.prep_bytes = (NR + 2) * HP * 4 + 32;
+  s.bias = s.prep + 2 * s.prep_bytes;
+  s.bars = s.bias + NP * nets * HP * 4;
+  s.n_bars = 2 + 2 * nx + nstg + 4 + 2 * nslot;
+  s.total = s.bars + 8 * s.n_bars + 16;
+  return s;
+}
+
+template <int NR, int CH, int MT, int DIFF>
+__global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgParams p) {
+  constexpr int N = NR < 16 ? 16 : NR;
+  using Acc = AccRegion<N, CH>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H, HP = p.HP, C = p.C, Cpad = p.Cpad, NP = p.NP, nets = p.nets;
+  const TcgSmem L = tcg_smem_layout(p.wres_bytes, p.nslot, HP, nets, C, Cpad, N, NR, p.nx, p.nstg, NP, p.uses_control);
+  const int row0 = blockIdx.x * NR;
+  const uint32_t region_cols = (uint32_t)(nets * MT) * Acc::kCols;       // 2 regions: phase 0 | later phases
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  const uint32_t bar_in = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
+  const uint32_t bar_xfull = smem_u32(&bars[2]), bar_xempty = bar_xfull + 8 * p.nx;
+  const uint32_t bar_cfull = bar_xempty + 8 * p.nx;
+  const uint32_t bar_pfull = bar_cfull + 8 * p.nstg, bar_pempty = bar_pfull + 16;
+  const uint32_t bar_rfull = bar_pempty + 16, bar_rempty = bar_rfull + 8 * p.nslot;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[L.n_bars]);
+
+  // ---- one-time setup ----
+  for (int j = 0; j < p.n_jobs; ++j) {                 // resident weight segments -> smem
+    const TcgJob& jb = p.jobs[j];
+    if (jb.stream) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(p.wblob + jb.g_off);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L.w + jb.a_off);
+    for (int i = tid; i < jb.nk * (kTcgSlotBytes / 16); i += kTcgThreads) dst[i] = src[i];
+  }
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem + L.b0);
+    const int zn = (L.stg - L.b0) / 16;
+    for (int i = tid; i < zn; i += kTcgThreads) z[i] = make_uint4(0, 0, 0, 0);
+    float* sb = reinterpret_cast<float*>(smem + L.bias);
+    for (int i = tid; i < NP * nets * HP; i += kTcgThreads) {
+      const int f = i % HP, pn = i / HP, net = pn % nets, ph = pn / nets;
+      const int off = p.bias[ph][net];
+      sb[i] = (off >= 0 && f < H) ? p.vec[off + f] : 0.f;
+    }
+  }
+  if (tid == 0) {
+    mbar_init(bar_in, kGEpiWarps);
+    mbar_init(bar_acc, 1);
+    for (int i = 0; i < p.nx; ++i) { mbar_init(bar_xfull + 8 * i, kGProdWarps); mbar_init(bar_xempty + 8 * i, 1); }
+    for (int i = 0; i < p.nstg; ++i) mbar_init(bar_cfull + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_pfull + 8 * i, kGPrepWarps); mbar_init(bar_pempty + 8 * i, kGEpiWarps); }
+    for (int i = 0; i < p.nslot; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rempty + 8 * i, 1); }
+    mbar_fence_init();
+  }
+  if (warp == kGMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < kGEpiWarps) {
+    // =========================== EPILOGUE / SDE STATE ===========================
+    constexpr int RT = NR / kGEpiPerQuad;
+    constexpr int LW = RT < 8 ? RT : 8;
+    const int h = (warp & 3) * 32 + lane;
+    const int rbase = (warp >> 2) * RT;
+    const TailOp t = p.tail;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const bool net2 = nets > 1;
+    auto write_operand = [&](int buf_off, int f, int r, float v) {
+      __half hi, lo;
+      split_f16(v, hi, lo);
+      uint8_t* q = smem + buf_off + (f >> 3) * L.lbo_b + (f & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+      *reinterpret_cast<__half*>(q) = hi;
+      *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
+    };
+    auto hand_over = [&]() {
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_in);
+    };
+    const float* sbias = reinterpret_cast<const float*>(smem + L.bias);
+    auto bias_of = [&](int ph, int net, int f) { return sbias[(ph * nets + net) * HP + f]; };
+    // accumulators of set `acc` in the region of phase `ph` -> vm (main) / vc (scaled correction), this thread's rows
+    auto load_acc = [&](int ph, int acc, float (&vm)[RT], float (&vc)[RT]) {
+      const uint32_t dreg = tmem + lane_base + (ph == 0 ? 0u : region_cols) + (uint32_t)acc * Acc::kCols + rbase;
+#pragma unroll
+      for (int c = 0; c < RT; c += LW) {
+        float m8[CH][LW], a8[CH][LW], b8[CH][LW];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          tmem_ldw<LW>(dreg + Acc::a(ch) + c, m8[ch]);
+          tmem_ldw<LW>(dreg + Acc::a(ch) + N + c, a8[ch]);
+          tmem_ldw<LW>(dreg + Acc::b(ch) + c, b8[ch]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < LW; ++i) {
+          float m = m8[0][i], cc = a8[0][i] + b8[0][i];
+#pragma unroll
+          for (int ch = 1; ch < CH; ++ch) { m += m8[ch][i]; cc += a8[ch][i] + b8[ch][i]; }
+          vm[c + i] = m; vc[c + i] = cc;
+        }
+      }
+    };
+
+    constexpr bool PRE_OK = RT <= 8;
+    const bool pre = PRE_OK && !net2;                 // diffusion precomputed in the MMA shadow (needs no net output)
+    constexpr int NPRE = PRE_OK ? RT : 1;
+    float y[MT][RT], yprev[MT][RT], qn[MT][RT], gv[MT][NPRE], dg[MT][NPRE], thy[MT][NPRE];
+    int myslot[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      const int b = min(row0 + rbase + i, p.B - 1);
+      myslot[i] = p.row_slot ? p.row_slot[b] : -1;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int f = h + 128 * mt;
+        y[mt][i] = f < H ? p.y0[(size_t)b * H + f] : 0.f;
+        yprev[mt][i] = y[mt][i];
+        qn[mt][i] = 0.f;
+        if (f < H) write_operand(L.b0, f, rbase + i, y[mt][i]);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < NPRE; ++i) gv[mt][i] = dg[mt][i] = thy[mt][i] = 0.f;
+
+    auto emit = [&](snsde_emit em) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int f = h + 128 * mt;
+        if (f >= H) continue;
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+          const int gr = row0 + rbase + i;
+          if (gr >= p.B) continue;
+          const float v = em.w_prev * yprev[mt][i] + em.w_curr * y[mt][i];
+          if (p.row_slot) {
+            if (myslot[i] == em.slot) p.out[(size_t)gr * H + f] = v;
+          } else {
+            p.out[((size_t)em.slot * p.B + gr) * H + f] = v;
+          }
+        }
+      }
+    };
+    for (int e = 0; e < p.n_init_emits; ++e) {
+      snsde_emit em = p.emits[e];
+      em.w_prev = 0.f; em.w_curr = 1.f;
+      emit(em);
+    }
+    hand_over();
+
+    auto state_terms = [&](float yr, float cf, float t0, float& g, float& dgy, float& th) {
+      if (DIFF == 1) {
+        const float raw = cf * yr;
+        const bool fin = (raw == raw) && (fabsf(raw) != INFINITY);
+        g = tanh_fast(t.s_theta * nan_to_num_f(raw));
+        dgy = t.milstein ? ((1.f - g * g) * t.s_theta) * (fin ? 1.f : 0.f) * cf : 0.f;
+      } else {
+        diffusion_eval<true>(t, cf, yr, t0, g, dgy);
+      }
+      th = t.geometric ? tanh_fast(yr) : 1.f;
+    };
+
+    uint32_t pacc = 0;
+    for (int s = 0; s < p.S; ++s) {
+      const uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
+      const float* sdw = reinterpret_cast<const float*>(slot);
+      mbar_wait(bar_pfull + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+      const StepInfo si = *reinterpret_cast<const StepInfo*>(slot + (NR + 2) * HP * 4);
+      float add0[MT], vec1[MT];                       // folded layer-0 bias; diffusion coefficient or noise-net layer-0 bias
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        add0[mt] = sdw[NR * HP + h + 128 * mt];
+        vec1[mt] = sdw[(NR + 1) * HP + h + 128 * mt];
+      }
+      if (pre) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int i = 0; i < NPRE; ++i)
+            if (h + 128 * mt < H) state_terms(y[mt][i], vec1[mt], si.t0, gv[mt][i], dg[mt][i], thy[mt][i]);
+      }
+      for (int ph = 0; ph < NP; ++ph) {
+        mbar_wait(bar_acc, pacc);
+        pacc ^= 1;
+        tc_fence_after();
+        TC_TRACE(tid == 0 && ph < 2, s, ph == 0 ? EV_EPI_ACC0 : EV_EPI_ACC1);
+        // ---- noise network (state-dependent noise options), layers 0..NN-1 ride on phases 0..NN-1 ----
+        if (net2 && ph < p.NN) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int f = h + 128 * mt;
+            float vm[RT], vc[RT];
+            load_acc(ph, MT + mt, vm, vc);
+            if (f < H) {
+              const float add = (ph == 0) ? vec1[mt] : bias_of(ph, 1, f);
+#pragma unroll
+              for (int i = 0; i < RT; ++i) {
+                const float v = act_apply(fmaf(vc[i], kLoInv, vm[i]) + add, p.noise_act[ph]);
+                if (ph < p.NN - 1) write_operand(L.b1, f, rbase + i, v);
+                else qn[mt][i] = v;
+              }
+            }
+          }
+        }
+        // ---- drift network ----
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int f = h + 128 * mt;
+          float vm[RT], vc[RT];
+          load_acc(ph, mt, vm, vc);
+          if (f >= H) continue;
+          if (ph < NP - 1) {
+            const float add = (ph == 0) ? add0[mt] : bias_of(ph, 0, f);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+              float v = fmaf(vc[i], kLoInv, vm[i]) + add;
+              v = v < 0.f ? 0.f : v;
+              write_operand(L.b0, f, rbase + i, v);
+            }
+          } else {
+            const float bl = bias_of(ph, 0, f);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+              float d = fmaf(vc[i], kLoInv, vm[i]) + bl;
+              float g, dgy, th;
+              if (PRE_OK && pre) { g = gv[mt][i < NPRE ? i : 0]; dgy = dg[mt][i < NPRE ? i : 0]; th = thy[mt][i < NPRE ? i : 0]; }
+              else state_terms(y[mt][i], net2 ? qn[mt][i] : vec1[mt], si.t0, g, dgy, th);
+              if (t.geometric) d *= th;
+              if (t.clip_drift) d = tanh_fast(d);
+              const float dw = sdw[(rbase + i) * HP + f];
+              float yn = __fadd_rn(__fadd_rn(y[mt][i], __fmul_rn(d, si.h)), __fmul_rn(g, dw));
+              if (t.milstein) {
+                const float v2 = __fmul_rn(dw, dw) - si.h;
+                yn = __fadd_rn(yn, 0.5f * ((g * v2) * dgy));
+              }
+              yprev[mt][i] = y[mt][i];
+              y[mt][i] = yn;
+              write_operand(L.b0, f, rbase + i, yn);
+            }
+          }
+        }
+        hand_over();
+        TC_TRACE(tid == 0 && ph < 2, s, ph == 0 ? EV_EPI_DONE0 : EV_EPI_DONE1);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pempty + 8 * (s & 1));
+      if (si.n_emits > 0) emit(si.first);
+      for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);
+      TC_TRACE(tid == 0, s, EV_EPI_SHADOW_END);
+    }
+  } else if (warp == kGMmaWarp) {
+    // =========================== MMA ISSUER (warp-uniform, one elected lane) ===========================
+    const bool leader = elect_one();
+    const uint32_t w_base = smem_u32(smem + L.w), ring_base = smem_u32(smem + L.ring);
+    const uint32_t b_bases[2] = {smem_u32(smem + L.b0), smem_u32(smem + L.b1)};
+    const uint32_t x_base = smem_u32(smem + L.x);
+    constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * N), idesc1 = umma_idesc_f16(128, N);
+    const uint64_t b_step = (uint64_t)((2 * L.lbo_b) >> 4);
+    uint32_t pin = 0, rslot = 0, rphase = 0, xphase = 0;
+    int xslot = 0;
+    auto issue_job = [&](const TcgJob& jb, uint32_t bbase) {
+      const uint32_t d = tmem + (jb.phase == 0 ? 0u : region_cols) + (uint32_t)jb.acc * Acc::kCols;
+      uint64_t db = umma_smem_desc(bbase + jb.b_chunk0 * 2 * L.lbo_b, L.lbo_b, 128);
+      uint32_t acc = jb.fresh ? 0u : 1u;
+      uint32_t a_addr = w_base + jb.a_off;
+      for (int kb = 0; kb < jb.nk; kb += CH) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          if (jb.stream) {
+            mbar_wait(bar_rfull + 8 * rslot, rphase);
+            tc_fence_after();
+            a_addr = ring_base + rslot * kTcgSlotBytes;
+          }
+          const uint64_t da_hi = umma_smem_desc(a_addr, kGALbo, kGASbo);
+          const uint64_t da_lo = umma_smem_desc(a_addr + 4096, kGALbo, kGASbo);
+          if (leader) {
+            umma_f16(d + Acc::a(c), da_hi, db, idesc2, acc);
+            umma_f16(d + Acc::b(c), da_lo, db, idesc1, acc);
+            if (jb.stream) umma_commit(bar_rempty + 8 * rslot);
+          }
+          if (jb.stream) {
+            __syncwarp();
+            if (++rslot == (uint32_t)p.nslot) { rslot = 0; rphase ^= 1; }
+          } else {
+            a_addr += kTcgSlotBytes;
+          }
+          db += b_step;
+        }
+        acc = 1u;
+      }
+    };
+    auto issue_x = [&]() {
+      mbar_wait(bar_xfull + 8 * xslot, xphase);
+      tc_fence_after();
+      for (int j = p.n_jobs - p.n_xjobs; j < p.n_jobs; ++j) issue_job(p.jobs[j], x_base + xslot * L.x_slot_bytes);
+      if (leader) umma_commit(bar_xempty + 8 * xslot);
+      __syncwarp();
+      if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
+    };
+    if (p.n_xjobs > 0 && p.S > 0) issue_x();
+    for (int s = 0; s < p.S; ++s) {
+      int j = 0;
+      for (int ph = 0; ph < NP; ++ph) {
+        mbar_wait(bar_in, pin);
+        pin ^= 1;
+        tc_fence_after();
+        TC_TRACE(lane == 0 && ph < 2, s, ph == 0 ? EV_MMA_WAKE0 : EV_MMA_WAKE1);
+        for (; j < p.n_jobs - p.n_xjobs && p.jobs[j].phase == ph; ++j) issue_job(p.jobs[j], b_bases[p.jobs[j].b_src]);
+        if (leader) umma_commit(bar_acc);
+        __syncwarp();
+        TC_TRACE(lane == 0 && ph < 2, s, ph == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1);
+      }
+      if (p.n_xjobs > 0 && s + 1 < p.S) issue_x();
+      TC_TRACE(lane == 0, s, EV_MMA_X_DONE);
+    }
+  } else if (warp < kGStreamWarp) {
+    // =========================== CONTROL PRODUCER ===========================
+    if (p.uses_control) {
+      const int ptid = tid - 32 * kGProdWarp0;
+      const int pwarp = warp - kGProdWarp0;
+      const uint32_t row_bytes = 16u * C;
+      auto fetch = [&](int s) {
+        if (pwarp != 0 || s >= p.S) return;
+        const int stg = s % p.nstg;
+        const uint32_t bar = bar_cfull + 8 * stg;
+        if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * NR);
+        __syncwarp();
+        const int interval = p.steps[s].interval;
+        for (int r = lane; r < NR; r += 32) {
+          const int b = min(row0 + r, p.B - 1);
+          const float* src = p.coeffs + (size_t)b * p.coeff_row_stride + (size_t)interval * 4 * C;
+          bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
+        }
+      };
+      for (int s = 0; s < p.nstg - 1; ++s) fetch(s);
+      for (int s = 0; s < p.S; ++s) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads));
+        fetch(s + p.nstg - 1);
+        const int stg = s % p.nstg, slot = s % p.nx;
+        const float frac = p.steps[s].frac;
+        mbar_wait_relaxed(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
+        if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
+        const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
+        uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
+        for (int i = ptid; i < NR * C; i += kGProdThreads) {
+          const int r = i / C, c = i - r * C;
+          const float* row = rows + r * 4 * C;
+          float inner = 0.5f * row[2 * C + c] + __fdiv_rn(row[3 * C + c] * frac, 3.0f);
+          inner = row[C + c] + inner * frac;
+          const float x = row[c] + inner * frac;
+          __half hi, lo;
+          split_f16(x, hi, lo);
+          uint8_t* q = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+          *reinterpret_cast<__half*>(q) = hi;
+          *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);
+      }
+    }
+  } else if (warp >= kGPrepWarp0) {
+    // =========================== STEP PREFETCH (time-only work) ===========================
+    const int h = tid - 32 * kGPrepWarp0;
+    const TailOp t = p.tail;
+    float c0[MT], csin[MT], ccos[MT], n0[MT], nsin[MT], ncos[MT], coef[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int f = h + 128 * mt;
+      const bool a = f < H;
+      c0[mt] = (a && p.bias[0][0] >= 0) ? p.vec[p.bias[0][0] + f] : 0.f;
+      csin[mt] = (a && p.c_sin[0] >= 0) ? p.vec[p.c_sin[0] + f] : 0.f;
+      ccos[mt] = (a && p.c_cos[0] >= 0) ? p.vec[p.c_cos[0] + f] : 0.f;
+      n0[mt] = (a && nets > 1 && p.bias[0][1] >= 0) ? p.vec[p.bias[0][1] + f] : 0.f;
+      nsin[mt] = (a && p.c_sin[1] >= 0) ? p.vec[p.c_sin[1] + f] : 0.f;
+      ncos[mt] = (a && p.c_cos[1] >= 0) ? p.vec[p.c_cos[1] + f] : 0.f;
+      coef[mt] = t.coef_scalar;
+      if (t.coef_src == CO_IMG && a) coef[mt] = p.vec[p.coef_vec + f];
+    }
+    for (int s = 0; s < p.S; ++s) {
+      const snsde_step st = p.steps[s];
+      uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
+      float* sdw = reinterpret_cast<float*>(slot);
+      float dwv[MT][NR], v1[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int f = h + 128 * mt;
+        if (f >= H) continue;
+        v1[mt] = coef[mt];
+        if (nets > 1) v1[mt] = fmaf(st.cos_t0, ncos[mt], fmaf(st.sin_t0, nsin[mt], n0[mt]));
+        else if (t.coef_src == CO_VBUF) v1[mt] = p.a_tab[(size_t)s * H + f];
+        if (p.dW != nullptr) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) dwv[mt][r] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + f];
+        } else {
+          float nrm[4];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const unsigned long long gb = p.row_offset + (unsigned long long)(row0 + r);
+            if (r == 0 || (gb & 3ull) == 0ull) philox_normals4(p.seed, (uint32_t)f, (uint32_t)(gb >> 2), (uint32_t)s, nrm);
+            dwv[mt][r] = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), st.sqrt_h);
+          }
+        }
+      }
+      StepInfo si;
+      si.h = st.h; si.t0 = st.t0; si.n_emits = st.emit_end - st.emit_begin; si.emit_begin = st.emit_begin;
+      si.first.slot = 0; si.first.w_prev = 0.f; si.first.w_curr = 0.f;
+      if (h == 0 && si.n_emits > 0) si.first = p.emits[st.emit_begin];
+      if (s >= 2) mbar_wait_relaxed(bar_pempty + 8 * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int f = h + 128 * mt;
+        if (f >= H) continue;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) sdw[r * HP + f] = dwv[mt][r];
+        sdw[NR * HP + f] = fmaf(st.cos_t0, ccos[mt], fmaf(st.sin_t0, csin[mt], c0[mt]));
+        sdw[(NR + 1) * HP + f] = v1[mt];
+      }
+      if (h == 0) *reinterpret_cast<StepInfo*>(slot + (NR + 2) * HP * 4) = si;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pfull + 8 * (s & 1));
+    }
+  } else {
+    // =========================== WEIGHT STREAMER ===========================
+    // The streamed segments are consumed in the same order every step, so one lane keeps the ring full with
+    // 8 KB bulk copies, running ahead of the MMA warp across layers and steps.
+    if (lane == 0 && p.n_stream_chunks > 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int s = 0; s < p.S; ++s) {
+        for (int j = 0; j < p.n_jobs; ++j) {
+          const TcgJob& jb = p.jobs[j];
+          if (!jb.stream) continue;
+          for (int kb = 0; kb < jb.nk; ++kb) {
+            mbar_wait_relaxed(bar_rempty + 8 * slot, phase ^ 1);
+            mbar_arrive_expect_tx(bar_rfull + 8 * slot, kTcgSlotBytes);
+            bulk_g2s(smem_u32(smem + L.ring + slot * kTcgSlotBytes), p.wblob + jb.g_off + (size_t)kb * kTcgSlotBytes,
+                     kTcgSlotBytes, bar_rfull + 8 * slot);
+            if (++slot == (uint32_t)p.nslot) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGMmaWarp) tmem_dealloc(tmem, 512);
+}
+
+template <int NR, int CH, int MT, int DIFF>
+cudaError_t tcg_launch(const TcgParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = snsde_tcg_kernel<NR, CH, MT, DIFF>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kTcgThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace snsde

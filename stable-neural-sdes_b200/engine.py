@@ -96,7 +96,7 @@ class Plan:
 
     @property
     def kernel(self):
-        return {0: "fma_fp32", 1: "tcgen05"}[_lib.check(self.lib.snsde_plan_kernel_kind(self._h))]
+        return {0: "fma_fp32", 1: "tcgen05", 2: "tcgen05_general"}[_lib.check(self.lib.snsde_plan_kernel_kind(self._h))]
 
     @property
     def launches(self):

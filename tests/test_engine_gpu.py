@@ -351,7 +351,7 @@ def test_tc_kernel_long_trajectory_c2_shape_and_philox(dev):
 
 
 def test_tc_auto_falls_back_to_fma_when_unsupported(dev):
-    m, times, coeffs, y0 = make_problem(3, 18, 4, 32, 3, 1, 5, seed=1)
+    m, times, coeffs, y0 = make_problem(0, 17, 4, 32, 3, 1, 5, seed=1)
     mg = m.to(dev)
     mg.set_X(coeffs.to(dev), times.to(dev))
     with torch.no_grad():
@@ -359,3 +359,48 @@ def test_tc_auto_falls_back_to_fma_when_unsupported(dev):
         assert mg._snsde_plans[("euler", "auto", str(dev))].kernel == "fma_fp32"
         with pytest.raises(ValueError, match="tensor-core"):
             snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=1, precision="tc")
+
+
+# ======================= general tcgen05 kernel (streamed weights, 2 M tiles, noise networks) =======================
+TCG_CASES = [
+    # io, no, H, C, L, B, method      what it exercises
+    (3, 18, 128, 21, 1, 24, "euler"),      # c4 model: state-dependent 2-layer noise net beside the drift; 4 H x H matrices
+    (1, 19, 64, 3, 1, 40, "euler"),        # 2-layer noise net * y
+    (5, 15, 32, 4, 2, 9, "euler"),         # 1-layer noise net * y, geometric drift, deeper drift than noise net
+    (4, 14, 64, 6, 1, 17, "euler"),        # 1-layer noise net with control
+    (4, 18, 96, 5, 3, 11, "euler"),        # noise net finishes two phases before the drift
+    (4, 17, 256, 14, 1, 20, "euler"),      # c5 model: two M tiles, weights (557 KB) streamed through the ring
+    (6, 17, 192, 7, 1, 13, "milstein"),    # two M tiles with a partial second tile
+    (4, 17, 128, 35, 2, 30, "euler"),      # H=128 with a hidden layer: exceeds smem -> partly streamed
+    (2, 16, 128, 9, 4, 8, "euler"),        # 5 drift phases
+    (3, 13, 256, 3, 2, 150, "euler"),      # H=256, no control, NR=8 with >148... single wave, Linear(2,H) noise table
+]
+
+
+@pytest.mark.parametrize("io,no,H,C,L,B,method", TCG_CASES)
+def test_general_tc_kernel_matches_oracle(io, no, H, C, L, B, method, dev):
+    K = 21
+    m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, K, seed=3 * H + io + no)
+    dt = solver.solver_dt(times)
+    ts = times[[0, 1, 2, 9, 20]]
+    dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(1)) * dt ** 0.5
+    got, want = run_both(m, times, coeffs, y0, ts, dt, dW, method, dev, precision="tc")
+    assert m._snsde_plans[(method, "tc", str(dev))].kernel == "tcgen05_general"
+    close(got, want)
+
+
+def test_general_kernel_agrees_with_resident_kernel(dev, monkeypatch):
+    """Same model through both tensor-core kernels (SNSDE_FORCE_TCG selects the general one)."""
+    B, H, C, L, K = 70, 128, 35, 1, 41
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=9)
+    fi = torch.randint(1, K, (B,), generator=torch.Generator().manual_seed(3))
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    with torch.no_grad():
+        a = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
+        assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05"
+        del mg._snsde_plans
+        monkeypatch.setenv("SNSDE_FORCE_TCG", "1")
+        b = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
+        assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05_general"
+    close(b, a, rtol=1e-5)
