@@ -44,9 +44,15 @@ def _compile(src, hdr_hash, force, verbose):
 
 
 def build(force=False, verbose=False):
-    OBJ.mkdir(exist_ok=True)
     hdr_hash = _headers_hash()
     sources = sorted(CSRC.glob("*.cu"))
+    # whole-library fingerprint next to the .so: lets a snapshot without the object cache (GPU box) skip the build
+    lib_fp = hashlib.sha256("".join(hashlib.sha256(s.read_bytes()).hexdigest() for s in sources).encode()
+                            + hdr_hash.encode()).hexdigest()
+    lib_stamp = HERE / ".libsnsde.stamp"
+    if not force and LIB.exists() and lib_stamp.exists() and lib_stamp.read_text() == lib_fp:
+        return LIB
+    OBJ.mkdir(exist_ok=True)
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
         results = list(ex.map(lambda s: _compile(s, hdr_hash, force, verbose), sources))
     if verbose:
@@ -57,6 +63,7 @@ def build(force=False, verbose=False):
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    lib_stamp.write_text(lib_fp)
     return LIB
 
 

@@ -249,6 +249,7 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
   int NR = 8;
   const int nr_max = p.MT == 2 ? 16 : 32;
   while (NR < nr_max && (a.B + NR - 1) / NR > tc.num_sms) NR *= 2;
+  if (getenv("SNSDE_TCG_NR") != nullptr) NR = std::min(nr_max, std::max(8, atoi(getenv("SNSDE_TCG_NR"))));   // experiment knob
   TcgSmem L;
   int CH = 2;
   for (;;) {

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
           const int f = h + 128 * mt;
           float vm[RT], vc[RT];
           load_acc(ph, mt, vm, vc);
+          TC_TRACE(tid == 0 && ph < 2 && mt == 0, s, ph == 0 ? EV_EPI_LD0 : EV_EPI_LD1);
           if (f >= H) continue;
           if (ph < NP - 1) {
             const float add = (ph == 0) ? add0[mt] : bias_of(ph, 0, f);
@@ -304,47 +305,59 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     // =========================== MMA ISSUER (warp-uniform, one elected lane) ===========================
     const bool leader = elect_one();
     const uint32_t w_base = smem_u32(smem + L.w), ring_base = smem_u32(smem + L.ring);
-    const uint32_t b_bases[2] = {smem_u32(smem + L.b0), smem_u32(smem + L.b1)};
+    const uint32_t b_base0 = smem_u32(smem + L.b0), b_base1 = smem_u32(smem + L.b1);
     const uint32_t x_base = smem_u32(smem + L.x);
     constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * N), idesc1 = umma_idesc_f16(128, N);
     const uint64_t b_step = (uint64_t)((2 * L.lbo_b) >> 4);
     uint32_t pin = 0, rslot = 0, rphase = 0, xphase = 0;
     int xslot = 0;
-    auto issue_job = [&](const TcgJob& jb, uint32_t bbase) {
-      const uint32_t d = tmem + (jb.phase == 0 ? 0u : region_cols) + (uint32_t)jb.acc * Acc::kCols;
-      uint64_t db = umma_smem_desc(bbase + jb.b_chunk0 * 2 * L.lbo_b, L.lbo_b, 128);
-      uint32_t acc = jb.fresh ? 0u : 1u;
-      uint32_t a_addr = w_base + jb.a_off;
-      for (int kb = 0; kb < jb.nk; kb += CH) {
+    // Descriptor arithmetic is incremental (one 64-bit add per operand and chunk) and the resident / streamed
+    // cases are separate loops: the issue rate of this warp bounds the step time.
+    const uint64_t ring_desc0 = umma_smem_desc(ring_base, kGALbo, kGASbo);
+    auto issue_job = [&](int j, uint32_t bbase) {
+      const int nk = p.jobs[j].nk;
+      const uint32_t d = tmem + (p.jobs[j].phase == 0 ? 0u : region_cols) + (uint32_t)p.jobs[j].acc * Acc::kCols;
+      uint64_t db = umma_smem_desc(bbase + p.jobs[j].b_chunk0 * 2 * L.lbo_b, L.lbo_b, 128);
+      uint32_t acc = p.jobs[j].fresh ? 0u : 1u;
+      if (!p.jobs[j].stream) {
+        uint64_t da = umma_smem_desc(w_base + p.jobs[j].a_off, kGALbo, kGASbo);
+#pragma unroll 2
+        for (int kb = 0; kb < nk; kb += CH) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          if (jb.stream) {
+          for (int c = 0; c < CH; ++c) {
+            if (leader) {
+              umma_f16(d + Acc::a(c), da, db, idesc2, acc);
+              umma_f16(d + Acc::b(c), da + (4096 >> 4), db, idesc1, acc);
+            }
+            da += (uint64_t)(kTcgSlotBytes >> 4);
+            db += b_step;
+          }
+          acc = 1u;
+        }
+      } else {
+        for (int kb = 0; kb < nk; kb += CH) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
             mbar_wait(bar_rfull + 8 * rslot, rphase);
             tc_fence_after();
-            a_addr = ring_base + rslot * kTcgSlotBytes;
-          }
-          const uint64_t da_hi = umma_smem_desc(a_addr, kGALbo, kGASbo);
-          const uint64_t da_lo = umma_smem_desc(a_addr + 4096, kGALbo, kGASbo);
-          if (leader) {
-            umma_f16(d + Acc::a(c), da_hi, db, idesc2, acc);
-            umma_f16(d + Acc::b(c), da_lo, db, idesc1, acc);
-            if (jb.stream) umma_commit(bar_rempty + 8 * rslot);
-          }
-          if (jb.stream) {
+            const uint64_t da = ring_desc0 + (uint64_t)(rslot * (kTcgSlotBytes >> 4));
+            if (leader) {
+              umma_f16(d + Acc::a(c), da, db, idesc2, acc);
+              umma_f16(d + Acc::b(c), da + (4096 >> 4), db, idesc1, acc);
+              umma_commit(bar_rempty + 8 * rslot);
+            }
             __syncwarp();
             if (++rslot == (uint32_t)p.nslot) { rslot = 0; rphase ^= 1; }
-          } else {
-            a_addr += kTcgSlotBytes;
+            db += b_step;
           }
-          db += b_step;
+          acc = 1u;
         }
-        acc = 1u;
       }
     };
     auto issue_x = [&]() {
       mbar_wait(bar_xfull + 8 * xslot, xphase);
       tc_fence_after();
-      for (int j = p.n_jobs - p.n_xjobs; j < p.n_jobs; ++j) issue_job(p.jobs[j], x_base + xslot * L.x_slot_bytes);
+      for (int j = p.n_jobs - p.n_xjobs; j < p.n_jobs; ++j) issue_job(j, x_base + xslot * L.x_slot_bytes);
       if (leader) umma_commit(bar_xempty + 8 * xslot);
       __syncwarp();
       if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
@@ -357,7 +370,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         pin ^= 1;
         tc_fence_after();
         TC_TRACE(lane == 0 && ph < 2, s, ph == 0 ? EV_MMA_WAKE0 : EV_MMA_WAKE1);
-        for (; j < p.n_jobs - p.n_xjobs && p.jobs[j].phase == ph; ++j) issue_job(p.jobs[j], b_bases[p.jobs[j].b_src]);
+        for (; j < p.n_jobs - p.n_xjobs && p.jobs[j].phase == ph; ++j) issue_job(j, p.jobs[j].b_src ? b_base1 : b_base0);
         if (leader) umma_commit(bar_acc);
         __syncwarp();
         TC_TRACE(lane == 0 && ph < 2, s, ph == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1);
