@@ -265,21 +265,30 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
       const TcgSmem base = tcg_smem_layout(0, 0, p.HP, p.nets, p.C, p.Cpad, N, NR, p.nx, p.nstg, p.NP, p.uses_control);
       const long long room = (long long)tc.smem_optin - base.total - 256;
       if (room < 0) continue;
-      int nslot = 0;
-      if ((long long)total_tiles > room) nslot = 8;
-      long long budget = room - (long long)nslot * kTcgSlotBytes - 16 * nslot;
-      if (budget < 0) continue;
-      int res_bytes = 0, n_stream = 0;
+      // Ring depth when the tiles do not all fit: a deeper ring raises the per-SM streaming rate
+      // (bytes in flight / L2 latency, ~2300 cycles under load: 8 slots gave 28 B/cycle on B200) but leaves
+      // less room for resident segments; pick the depth with the smallest estimated streaming time per step.
       std::vector<int> order;
       for (int j = p.n_jobs - p.n_xjobs; j < p.n_jobs; ++j) order.push_back(j);
       for (int j = 0; j < p.n_jobs - p.n_xjobs; ++j) order.push_back(j);
+      auto plan_residency = [&](int nslot, bool commit, int& res_bytes, int& n_stream, bool& x_ok) {
+        long long budget = room - (long long)nslot * kTcgSlotBytes - 16 * nslot;
+        res_bytes = 0; n_stream = 0; x_ok = budget >= 0;
+        for (int j : order) {
+          const int sz = p.jobs[j].nk * kTcgSlotBytes;
+          const bool resident = x_ok && (nslot == 0 || sz <= budget);
+          if (resident) { budget -= sz; res_bytes += sz; }
+          else { n_stream += p.jobs[j].nk; if (p.jobs[j].b_src == 2) x_ok = false; }
+          if (commit) p.jobs[j].stream = resident ? 0 : 1;
+        }
+      };
+      // Ring depth: 8 slots (64 KB in flight).  With one CTA per SM all streaming the same tiles the limit is the
+      // chip-wide L2 throughput (c5: 128 CTAs x 444 KB per step ~ 6 TB/s), not the ring; deeper rings only take
+      // shared memory away from resident segments (measured: no gain on c5, a loss on c4).
+      const int nslot = ((long long)total_tiles > room) ? 8 : 0;
+      int res_bytes = 0, n_stream = 0;
       bool x_ok = true;
-      for (int j : order) {
-        TcgJob& jb = p.jobs[j];
-        const int sz = jb.nk * kTcgSlotBytes;
-        if (nslot == 0 || sz <= budget) { jb.stream = 0; budget -= sz; res_bytes += sz; }
-        else { jb.stream = 1; n_stream += jb.nk; if (jb.b_src == 2) x_ok = false; }
-      }
+      plan_residency(nslot, true, res_bytes, n_stream, x_ok);
       if (!x_ok) continue;
       // resident jobs are copied once from the global blob (g_off) into a packed smem area (a_off)
       int packed = 0;

@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
           const TcgJob& jb = p.jobs[j];
           if (!jb.stream) continue;
           for (int kb = 0; kb < jb.nk; ++kb) {
-            mbar_wait_relaxed(bar_rempty + 8 * slot, phase ^ 1);
+            mbar_wait(bar_rempty + 8 * slot, phase ^ 1);      // tight poll: a sleeping streamer caps the ring at ~30 B/cycle
             mbar_arrive_expect_tx(bar_rfull + 8 * slot, kTcgSlotBytes);
             bulk_g2s(smem_u32(smem + L.ring + slot * kTcgSlotBytes), p.wblob + jb.g_off + (size_t)kb * kTcgSlotBytes,
                      kTcgSlotBytes, bar_rfull + 8 * slot);
