@@ -409,7 +409,13 @@ def main():
             roof = {"bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_frac}
         else:
             roof = {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac}
-        roof.update({"traffic": None, "kernel": plan.kernel, "kernel_ms_per_launch": kern_ms, "peak_source": peak_src,
+        traffic = None
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists():
+            rec = json.loads(tj.read_text()).get(args.workload)
+            if rec and rec["kernel"] == plan.kernel and B == WORKLOADS[args.workload]["B"]:
+                traffic = rec["bytes"]                 # measured once with ncu --set full (see profiles/)
+        roof.update({"traffic": traffic, "alg_bytes_per_launch": abytes * B * S, "kernel": plan.kernel, "kernel_ms_per_launch": kern_ms, "peak_source": peak_src,
                      "alg_bytes_per_sde_step": abytes, "alg_flops_per_sde_step": aflops,
                      "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_frac},
                      "tensor": {"achieved_tflops": tflops, "peak_tflops": tf_peak, "frac": tf_frac},
