@@ -106,7 +106,8 @@ int snsde_plan_destroy(snsde_plan* plan);
 int snsde_plan_set_weights(snsde_plan* plan, const float* blob, int64_t n_floats, int on_device,
                            void* stream);
 
-/* Which kernel the plan will run: 0 = fp32 FMA, 1 = tcgen05.  Negative on error. */
+/* Which kernel the plan will run: 0 = fp32 FMA, 1 = tcgen05 with resident weights, 2 = general tcgen05
+ * (streamed weights / two M tiles / noise networks).  Negative on error. */
 int snsde_plan_kernel_kind(const snsde_plan* plan);
 
 /* The solve.  Replaces torchsde.sdeint as called at neuralsde.py:78-82.
@@ -136,6 +137,14 @@ int snsde_forward(snsde_plan* plan,
  * scaled by sqrt_h_host[s].  Used to feed the oracle the identical Brownian path. */
 int snsde_philox_fill(uint64_t seed, uint64_t row_offset, int32_t S, int32_t B, int32_t H,
                       const float* sqrt_h_host, float* dW_dev, int device, void* stream);
+
+/* Sticky device-side status of the plan's solves since the last call (synchronises `stream`, then clears):
+ *   bit 0: a tensor-core kernel met an operand beyond the fp16 range (|v| > 65504) of its split-precision
+ *          format and saturated it - the affected rows are NOT within the parity tolerance; rerun the solve
+ *          with precision = SNSDE_PRECISION_FP32.  (States of the reference models stay far below this:
+ *          |z| <= |z0| + sum(h + 6.7 sqrt(h)) because drift and diffusion are tanh-clipped.)
+ * Returns the flags (>= 0) or a negative snsde_status. */
+int snsde_plan_status(snsde_plan* plan, void* stream);
 
 /* Number of engine kernels launched by this plan so far (for bench.py's gpu_launches). */
 int64_t snsde_plan_launch_count(const snsde_plan* plan);

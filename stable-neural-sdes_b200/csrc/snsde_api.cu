@@ -53,6 +53,7 @@ struct snsde_plan {
   snsde_step* d_steps = nullptr; int steps_cap = 0; std::vector<snsde_step> h_steps;
   snsde_emit* d_emits = nullptr; int emits_cap = 0; std::vector<snsde_emit> h_emits;
   int64_t launches = 0;
+  int* d_status = nullptr;            // sticky device flags (snsde_plan_status)
 };
 
 static bool is_time_opt(int io) { return io >= 3 && io <= 6; }
@@ -352,6 +353,11 @@ int snsde_plan_create(const snsde_model_desc* desc, int device, snsde_plan** out
     return fail(SNSDE_ERR_UNSUPPORTED, "tensor-core path does not support this model/shape/device: %s", tcg_unsupported_reason());
   }
   p->kind = desc->precision == SNSDE_PRECISION_FP32 ? 0 : (tc_ok ? 1 : (tcg_ok ? 2 : 0));
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p->d_status, sizeof(int)) != cudaSuccess ||
+      cudaMemset(p->d_status, 0, sizeof(int)) != cudaSuccess) {
+    delete p;
+    return fail(SNSDE_ERR_CUDA, "cannot allocate the plan status word");
+  }
   *out_plan = p;
   return SNSDE_OK;
 }
@@ -362,6 +368,7 @@ int snsde_plan_destroy(snsde_plan* p) {
   cudaFree(p->d_wimg);
   cudaFree(p->d_steps);
   cudaFree(p->d_emits);
+  cudaFree(p->d_status);
   tc_release(p->tc);
   tcg_release(p->tcg);
   delete p;
@@ -374,6 +381,17 @@ int snsde_plan_kernel_kind(const snsde_plan* p) {
 }
 
 int64_t snsde_plan_launch_count(const snsde_plan* p) { return p ? p->launches : 0; }
+
+int snsde_plan_status(snsde_plan* p, void* stream_v) {
+  if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  int flags = 0;
+  CUDA_TRY(cudaSetDevice(p->device));
+  CUDA_TRY(cudaMemcpyAsync(&flags, p->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaMemsetAsync(p->d_status, 0, sizeof(int), stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return flags;
+}
 
 int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, int on_device, void* stream_v) {
   if (!p || !blob) return fail(SNSDE_ERR_BAD_ARG, "plan/blob is NULL");
@@ -481,6 +499,7 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
     a.coeffs = coeffs_dev; a.coeff_row_stride = coeff_row_stride; a.y0 = y0_dev; a.B = B;
     a.steps = p->d_steps; a.steps_host = steps_host; a.S = S; a.emits = p->d_emits; a.n_init_emits = n_init_emits;
     a.n_out = n_out; a.row_slot = row_slot_dev; a.dW = dW_dev; a.seed = seed; a.row_offset = row_offset; a.out = out_dev;
+    a.status = p->d_status;
     int nl = 0;
     cudaError_t e = p->kind == 1 ? tc_forward(p->tc, a, stream, &nl) : tcg_forward(p->tcg, a, stream, &nl);
     if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "tcgen05 kernel launch: %s", cudaGetErrorString(e));

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     auto write_operand = [&](int r, float v) {
       __half hi, lo;
       split_f16(v, hi, lo);
+      if (fabsf(v) > 65504.f) *p.status = 1;        // saturated: outside the split-fp16 operand range
       uint8_t* q = bact + (r >> 3) * 128 + (r & 7) * 16;
       *reinterpret_cast<__half*>(q) = hi;
       *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
@@ -398,6 +399,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
           const float x = row[c] + inner * frac;
           __half hi, lo;
           split_f16(x, hi, lo);
+          if (fabsf(x) > 65504.f) *p.status = 1;
           uint8_t* q = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
           *reinterpret_cast<__half*>(q) = hi;
           *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
@@ -668,6 +670,7 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
   p.coeffs = a.coeffs; p.coeff_row_stride = a.coeff_row_stride; p.y0 = a.y0; p.B = a.B;
   p.steps = a.steps; p.S = a.S; p.emits = a.emits; p.n_init_emits = a.n_init_emits; p.n_out = a.n_out;
   p.row_slot = a.row_slot; p.dW = a.dW; p.seed = a.seed; p.row_offset = a.row_offset; p.out = a.out;
+  p.status = a.status;
   *n_launches = 0;
   if (tc.noise.kind != 0 && a.S > 0) {
     if (a.S * p.H > tc.atab_cap) {

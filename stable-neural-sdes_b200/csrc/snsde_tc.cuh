@@ -35,6 +35,7 @@ struct TcParams {
   float* out;
   int nx, nstg;              // control-operand ring depth, coefficient staging depth
   long long* dbg;            // optional: clock64 trace of CTA 0 (SNSDE_TC_TRACE env), [step][event]
+  int* status;               // sticky flags (bit 0: operand beyond the fp16 range was saturated)
 };
 
 // Per-step table of the row-independent noise networks (options 12,13,16,17).
@@ -61,6 +62,7 @@ struct TcForwardArgs {
   const int* row_slot; const float* dW;
   unsigned long long seed, row_offset;
   float* out;
+  int* status;
 };
 
 bool tc_supported(const snsde_model_desc& d, int cc_major, int smem_optin);

@@ -56,6 +56,7 @@ struct TcgParams {
   float* out;
   int nx, nstg, nslot;
   long long* dbg;
+  int* status;               // sticky flags (bit 0: operand beyond the fp16 range was saturated)
 };
 
 struct TcgPlan {

@@ -222,6 +222,7 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
   p.coeffs = a.coeffs; p.coeff_row_stride = a.coeff_row_stride; p.y0 = a.y0; p.B = a.B;
   p.steps = a.steps; p.S = a.S; p.emits = a.emits; p.n_init_emits = a.n_init_emits; p.n_out = a.n_out;
   p.row_slot = a.row_slot; p.dW = a.dW; p.seed = a.seed; p.row_offset = a.row_offset; p.out = a.out;
+  p.status = a.status;
   *n_launches = 0;
   if (tc.noise.kind != 0 && a.S > 0) {
     if (a.S * p.H > tc.atab_cap) {

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     auto write_operand = [&](int buf_off, int f, int r, float v) {
       __half hi, lo;
       split_f16(v, hi, lo);
+      if (fabsf(v) > 65504.f) *p.status = 1;        // saturated: outside the split-fp16 operand range
       uint8_t* q = smem + buf_off + (f >> 3) * L.lbo_b + (f & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
       *reinterpret_cast<__half*>(q) = hi;
       *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
           const float x = row[c] + inner * frac;
           __half hi, lo;
           split_f16(x, hi, lo);
+          if (fabsf(x) > 65504.f) *p.status = 1;
           uint8_t* q = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
           *reinterpret_cast<__half*>(q) = hi;
           *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;

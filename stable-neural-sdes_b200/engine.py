@@ -102,6 +102,12 @@ class Plan:
     def launches(self):
         return int(self.lib.snsde_plan_launch_count(self._h))
 
+    def status(self):
+        """Sticky device flags since the last call (synchronises the current stream): bit 0 = a tensor-core
+        kernel saturated an operand beyond the fp16 range; rerun with ``precision='fp32'``."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        return _lib.check(self.lib.snsde_plan_status(self._h, ctypes.c_void_p(stream)))
+
     def set_weights(self, blob):
         blob = blob.detach().to(torch.float32).contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream

@@ -404,3 +404,21 @@ def test_general_kernel_agrees_with_resident_kernel(dev, monkeypatch):
         b = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
         assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05_general"
     close(b, a, rtol=1e-5)
+
+
+def test_fp16_range_overflow_is_flagged_not_silent(dev):
+    m, times, coeffs, y0 = make_problem(4, 17, 6, 64, 3, 1, 6, seed=2)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    with torch.no_grad():
+        snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=1, precision="tc")
+        plan = mg._snsde_plans[("euler", "tc", str(dev))]
+        assert plan.status() == 0
+        big = y0.clone()
+        big[2, 5] = 1.0e5                                   # beyond the split-fp16 operand range
+        z_tc = snsde_b200.sdeint(mg, big.to(dev), times.to(dev), dt=1.0, seed=1, precision="tc")
+        assert plan.status() == 1 and plan.status() == 0    # sticky until read, then cleared
+        z32 = snsde_b200.sdeint(mg, big.to(dev), times.to(dev), dt=1.0, seed=1, precision="fp32")
+    # the fp32 kernel has no such limit; unaffected rows of the tensor-core result are still right
+    ok = [0, 1, 3, 4, 5]
+    close(z_tc[:, ok], z32[:, ok])
