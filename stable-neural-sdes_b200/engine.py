@@ -301,7 +301,13 @@ def patch(model, fuse_final_index=True):
             z0, kwargs = rest
             ts = times
         kwargs = dict(kwargs)
-        kwargs.setdefault("method", getattr(self, "_snsde_default_method", "euler"))
+        if "method" not in kwargs:
+            if len(rest) == 2:
+                # torch-ists NeuralSDE defaults to 'srk' (nsde_model.py:67), which the engine does not implement:
+                # refuse rather than silently integrating with a different scheme
+                raise ValueError("snsde: this wrapper's default method is 'srk' (not implemented); pass method='euler' "
+                                 "or method='milstein' explicitly")
+            kwargs["method"] = "euler"                       # benchmark wrappers' default (neuralsde.py:75)
         if kwargs["method"] == "srk":
             raise ValueError("snsde: method 'srk' is not implemented (SURVEY 8f2); use 'euler' or 'milstein'")
         dt = stepplan.solver_dt(_host_array(times))

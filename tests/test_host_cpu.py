@@ -182,3 +182,54 @@ def test_two_rank_gloo_all_gather_of_latents(tmp_path):
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+# ---- drop-in boundary against the REAL reference classes (build container only: needs /root/reference) ----
+REF = pathlib.Path("/root/reference")
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("bench_dir,io,no", [("benchmark_classification", 4, 17), ("benchmark_classification", 1, 18),
+                                              ("benchmark_forecasting", 6, 17), ("benchmark_classification", 2, 5)])
+def test_packing_and_patch_accept_the_reference_own_modules(bench_dir, io, no):
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    try:
+        import make_golden
+    finally:
+        sys.path.pop(0)
+    make_golden.install_shims()
+    try:
+        ref, _ = make_golden.load_reference_module(REF / bench_dir, real_cde=(bench_dir == "benchmark_classification"))
+        torch.manual_seed(0)
+        func = ref.Diffusion_model(input_channels=5, hidden_channels=32, hidden_hidden_channels=32, num_hidden_layers=2,
+                                   input_option=io, noise_option=no)
+        desc = packing.describe(func)
+        assert (desc["input_option"], desc["noise_option"], desc["hidden"], desc["num_hidden_layers"]) == (io, no, 32, 2)
+        blob = packing.pack(func, desc)
+        own = vector_field.DiffusionModel(5, 32, 32, 2, input_option=io, noise_option=no)
+        own.load_state_dict(func.state_dict())
+        assert torch.equal(blob, packing.pack(own, packing.describe(own)))        # same bytes from either module
+        cd = _lib.ModelDesc(method=0, precision=0, **desc)
+        assert _lib.load().snsde_weight_count(ctypes.byref(cd)) == blob.numel()
+        model = ref.NeuralSDE(func, 5, 32, 3, initial=False)
+        assert snsde_b200.patch(model) is model and model._solve_sde_path.__func__.__name__ == "_solve"
+        times = torch.arange(6.0)
+        coeffs = torch.zeros(2, 5, 20)
+        if not torch.cuda.is_available():
+            with torch.no_grad(), pytest.raises(snsde_b200.EngineError):       # reaches the engine, which refuses without a GPU
+                model(times, [coeffs], torch.tensor([5, 3]), z0=torch.zeros(2, 32))
+    finally:
+        for name in ("torchcde", "torchsde", "torchdiffeq", "controldiffeq"):
+            sys.modules.pop(name, None)
+
+
+def test_torch_ists_style_wrapper_requires_an_explicit_method():
+    class IstsStyle(torch.nn.Module):                      # signature of torch-ists NeuralSDE._solve_sde_path (nsde_model.py:63)
+        def __init__(self):
+            super().__init__()
+            self.func = vector_field.DiffusionModel(3, 8, 8, 1, input_option=4, noise_option=17)
+    m = snsde_b200.patch(IstsStyle(), fuse_final_index=False)
+    with pytest.raises(ValueError, match="srk"):
+        m._solve_sde_path(torch.arange(4.0), torch.zeros(2, 8), {})
+    with pytest.raises(ValueError, match="srk"):
+        m._solve_sde_path(torch.arange(4.0), torch.zeros(2, 8), {"method": "srk"})
