@@ -10,7 +10,8 @@ import sys
 import numpy as np
 
 EV = ["EPI_ACC0", "EPI_LD0", "EPI_DONE0", "EPI_ACC1", "EPI_LD1", "EPI_DONE1", "EPI_SHADOW_END",
-      "MMA_WAKE0", "MMA_COMMIT0", "MMA_WAKE1", "MMA_COMMIT1", "MMA_X_DONE", "PREP_DONE", "PROD_DONE"]
+      "MMA_WAKE0", "MMA_COMMIT0", "MMA_WAKE1", "MMA_COMMIT1", "MMA_X_DONE", "PREP_DONE", "PROD_DONE",
+      "EPI_PFULL", "EPI_PREPARED"]
 t = np.loadtxt(sys.argv[1], dtype=np.int64)
 t = t[20:-5]                                  # steady state
 ix = {n: i for i, n in enumerate(EV)}
@@ -31,6 +32,13 @@ rows = [
     ("shadow: emits etc. after hand-over", g("EPI_SHADOW_END") - g("EPI_DONE1")),
     ("MMA warp: X(t) segment after L1 commit", g("MMA_X_DONE") - g("MMA_COMMIT1")),
 ]
+if t[:, ix["EPI_PFULL"]].any():
+    rows += [
+        ("shadow: step data visible after shadow end (pfull)", g("EPI_PFULL") - prev("EPI_SHADOW_END")),
+        ("shadow: diffusion of the new state (prepare)", g("EPI_PREPARED") - g("EPI_PFULL")),
+        ("shadow: prepared -> accumulators of L0 seen", g("EPI_ACC0") - g("EPI_PREPARED")),
+        ("prefetch warp: slot s ready before epilogue needs it by", g("EPI_PFULL") - g("PREP_DONE")),
+    ]
 for name, d in rows:
     d = d[1:]
     print(f"{name:55s} median {np.median(d):8.0f}  p10 {np.percentile(d, 10):8.0f}  p90 {np.percentile(d, 90):8.0f} cycles")

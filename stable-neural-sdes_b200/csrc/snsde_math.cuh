@@ -12,12 +12,11 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-__device__ __forceinline__ float nan_to_num_f(float v) {               // torch.nan_to_num defaults
-  if (v != v) return 0.f;
-  if (v == INFINITY) return 3.4028234663852886e38f;
-  if (v == -INFINITY) return -3.4028234663852886e38f;
-  return v;
+__device__ __forceinline__ float nan_to_num_f(float v) {               // torch.nan_to_num defaults, branch-free
+  v = (v == v) ? v : 0.f;                                              // NaN -> 0
+  return fminf(fmaxf(v, -3.4028234663852886e38f), 3.4028234663852886e38f);   // +-inf -> +-FLT_MAX
 }
+__device__ __forceinline__ bool is_finite_f(float v) { return fabsf(v) <= 3.4028234663852886e38f; }   // false for NaN, +-inf
 
 // tanh with ~4e-7 RELATIVE accuracy on the fast path: odd Taylor polynomial below 0.25 (the multiplicative
 // models - tanh(sigma a y), z*tanh(y) - live on the relative accuracy near 0: an absolute 1e-7 error there is
@@ -50,7 +49,7 @@ __device__ __forceinline__ void diffusion_eval(const TailOp& t, float coef, floa
   }
   const bool state_dep = (t.special >= SP_SQRT) || (t.special == SP_NONE && (t.mult == MU_Y || t.mult == MU_TY));
   if (t.bounded) {
-    const bool fin = (raw == raw) && (fabsf(raw) != INFINITY);
+    const bool fin = is_finite_f(raw);
     const float arg = t.s_theta * nan_to_num_f(raw);
     g = FAST ? tanh_fast(arg) : tanhf(arg);
     // autograd chain of tanh(s * nan_to_num(raw)): (1-g^2) * s * isfinite(raw) * raw'.

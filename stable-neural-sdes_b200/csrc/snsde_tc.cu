@@ -235,21 +235,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     hand_over();
 
     // diffusion of the CURRENT state for the coming step (needs only y and the step's coefficient)
-    auto state_terms = [&](float yr, float cf, float t0, float& g, float& dgy, float& th) {
+    // Row loops are kept branch-free (model flags are tested OUTSIDE the loops) so that the compiler interleaves
+    // the rows' dependent MUFU/FMA chains; with per-row branches each row's ~150-cycle chain ran back to back.
+    auto diffusion_rows = [&](const float (&yv)[RT], float cf, float t0, float (&g)[RT], float (&dgy)[RT]) {
       if (DIFF == 1) {
-        const float raw = cf * yr;
-        const bool fin = (raw == raw) && (fabsf(raw) != INFINITY);
-        g = tanh_fast(t.s_theta * nan_to_num_f(raw));
-        dgy = t.milstein ? ((1.f - g * g) * t.s_theta) * (fin ? 1.f : 0.f) * cf : 0.f;
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+          const float raw = cf * yv[i];
+          g[i] = tanh_fast(t.s_theta * nan_to_num_f(raw));
+          dgy[i] = ((1.f - g[i] * g[i]) * t.s_theta) * (is_finite_f(raw) ? cf : 0.f);
+        }
       } else {
-        diffusion_eval<true>(t, cf, yr, t0, g, dgy);
+#pragma unroll
+        for (int i = 0; i < RT; ++i) diffusion_eval<true>(t, cf, yv[i], t0, g[i], dgy[i]);
       }
-      th = t.geometric ? tanh_fast(yr) : 1.f;
     };
     auto prepare_state = [&](float cf, float t0) {
       if (!act || !PRE) return;
+      float g[RT], d[RT];
+      diffusion_rows(y, cf, t0, g, d);
 #pragma unroll
-      for (int i = 0; i < NP; ++i) state_terms(y[i], cf, t0, gv[i], dg[i], thy[i]);
+      for (int i = 0; i < NP; ++i) { gv[i] = g[i]; dg[i] = d[i]; }
+      if (t.geometric) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) thy[i] = tanh_fast(y[i]);
+      }
     };
 
     uint32_t pacc = 0;
@@ -258,10 +268,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       const uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
       const float* sdw = reinterpret_cast<const float*>(slot);
       mbar_wait(bar_pfull + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+      TC_TRACE(tid == 0, s, EV_EPI_PFULL);
       const StepInfo si = *reinterpret_cast<const StepInfo*>(slot + (NR + 2) * 512);
       const float add0 = sdw[NR * 128 + h];
       const float cf = sdw[(NR + 1) * 128 + h];
       prepare_state(cf, si.t0);                       // in the shadow of the layer-0 MMAs
+      TC_TRACE(tid == 0, s, EV_EPI_PREPARED);
       for (int l = 0; l < NL; ++l) {
         mbar_wait(bar_acc, pacc);
         pacc ^= 1;
@@ -299,23 +311,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
             }
           }
         } else if (act) {
+          float d[RT], g[RT], dgy[RT], dw[RT];
 #pragma unroll
           for (int i = 0; i < RT; ++i) {
-            float d = fmaf(vc[i], kLoInv, vm[i]) + bias_last;
-            float g, dgy, th;
-            if (PRE) { g = gv[i]; dgy = dg[i]; th = thy[i]; }
-            else state_terms(y[i], cf, si.t0, g, dgy, th);
-            if (t.geometric) d *= th;
-            if (t.clip_drift) d = tanh_fast(d);
-            const float dw = sdw[(rbase + i) * 128 + h];
-            float yn = __fadd_rn(__fadd_rn(y[i], __fmul_rn(d, si.h)), __fmul_rn(g, dw));
-            if (t.milstein) {
-              const float v2 = __fmul_rn(dw, dw) - si.h;
-              yn = __fadd_rn(yn, 0.5f * ((g * v2) * dgy));
+            d[i] = fmaf(vc[i], kLoInv, vm[i]) + bias_last;
+            dw[i] = sdw[(rbase + i) * 128 + h];
+          }
+          if (PRE) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) { g[i] = gv[i]; dgy[i] = dg[i]; }
+            if (t.geometric) {
+#pragma unroll
+              for (int i = 0; i < NP; ++i) d[i] *= thy[i];
             }
+          } else {
+            diffusion_rows(y, cf, si.t0, g, dgy);
+            if (t.geometric) {
+#pragma unroll
+              for (int i = 0; i < RT; ++i) d[i] *= tanh_fast(y[i]);
+            }
+          }
+          if (t.clip_drift) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i) d[i] = tanh_fast(d[i]);
+          }
+          float yn[RT];
+#pragma unroll
+          for (int i = 0; i < RT; ++i) yn[i] = __fadd_rn(__fadd_rn(y[i], __fmul_rn(d[i], si.h)), __fmul_rn(g[i], dw[i]));
+          if (t.milstein) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+              const float v2 = __fmul_rn(dw[i], dw[i]) - si.h;
+              yn[i] = __fadd_rn(yn[i], 0.5f * ((g[i] * v2) * dgy[i]));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < RT; ++i) {
             yprev[i] = y[i];
-            y[i] = yn;
-            write_operand(rbase + i, yn);
+            y[i] = yn[i];
+            write_operand(rbase + i, yn[i]);
           }
         }
         hand_over();
@@ -368,42 +402,64 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       const int ptid = tid - 32 * kProdWarp0;            // 0..95
       const int pwarp = warp - kProdWarp0;
       const uint32_t row_bytes = 16u * C;
-      auto fetch = [&](int s) {                         // spline rows of step s -> staging slot (warp 5 only)
+      // Step metadata is loaded one iteration ahead (an exposed L2 round trip per step made this role the
+      // bottleneck of the whole kernel), and each thread's (row, channel) items are tabulated once.
+      auto fetch = [&](int s, int interval) {           // spline rows of step s -> staging slot (first producer warp only)
         if (pwarp != 0 || s >= p.S) return;
         const int stg = s % p.nstg;
         const uint32_t bar = bar_cfull + 8 * stg;
         if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * NR);
         __syncwarp();
-        const int interval = p.steps[s].interval;
         for (int r = lane; r < NR; r += 32) {
           const int b = min(row0 + r, p.B - 1);
           const float* src = p.coeffs + (size_t)b * p.coeff_row_stride + (size_t)interval * 4 * C;
           bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
         }
       };
-      for (int s = 0; s < p.nstg - 1; ++s) fetch(s);
+      constexpr int kMaxItems = 12;
+      int item_src[kMaxItems], item_dst[kMaxItems];
+#pragma unroll
+      for (int k = 0; k < kMaxItems; ++k) {
+        const int i = ptid + k * kProdThreads;
+        const int r = i / C, c = i - r * C;
+        item_src[k] = (i < NR * C) ? r * 4 * C + c : -1;
+        item_dst[k] = (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+      }
+      auto eval_item = [&](const float* rows, uint8_t* xs, int src, int dst, float frac) {
+        const float* q0 = rows + src;
+        float inner = 0.5f * q0[2 * C] + __fdiv_rn(q0[3 * C] * frac, 3.0f);
+        inner = q0[C] + inner * frac;
+        const float x = q0[0] + inner * frac;
+        __half hi, lo;
+        split_f16(x, hi, lo);
+        if (fabsf(x) > 65504.f) *p.status = 1;
+        *reinterpret_cast<__half*>(xs + dst) = hi;
+        *reinterpret_cast<__half*>(xs + dst + (N / 8) * 128) = lo;
+      };
+      for (int s = 0; s < p.nstg - 1; ++s) fetch(s, s < p.S ? p.steps[s].interval : 0);
+      int interval_ahead = (p.nstg - 1 < p.S) ? p.steps[p.nstg - 1].interval : 0;
+      float frac_cur = p.S > 0 ? p.steps[0].frac : 0.f;
       for (int s = 0; s < p.S; ++s) {
         asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads));      // all producer warps are done with step s-1
-        fetch(s + p.nstg - 1);
+        fetch(s + p.nstg - 1, interval_ahead);
+        const int sa = s + p.nstg;
+        const int interval_next = sa < p.S ? p.steps[sa].interval : 0;       // consumed next iteration
+        const float frac_next = s + 1 < p.S ? p.steps[s + 1].frac : 0.f;
         const int stg = s % p.nstg, slot = s % p.nx;
-        const float frac = p.steps[s].frac;
+        const float frac = frac_cur;
         mbar_wait_relaxed(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
         if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
-        for (int i = ptid; i < NR * C; i += kProdThreads) {
+#pragma unroll
+        for (int k = 0; k < kMaxItems; ++k)
+          if (item_src[k] >= 0) eval_item(rows, xs, item_src[k], item_dst[k], frac);
+        for (int i = ptid + kMaxItems * kProdThreads; i < NR * C; i += kProdThreads) {     // wide inputs: generic tail
           const int r = i / C, c = i - r * C;
-          const float* row = rows + r * 4 * C;
-          float inner = 0.5f * row[2 * C + c] + __fdiv_rn(row[3 * C + c] * frac, 3.0f);
-          inner = row[C + c] + inner * frac;
-          const float x = row[c] + inner * frac;
-          __half hi, lo;
-          split_f16(x, hi, lo);
-          if (fabsf(x) > 65504.f) *p.status = 1;
-          uint8_t* q = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
-          *reinterpret_cast<__half*>(q) = hi;
-          *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
+          eval_item(rows, xs, r * 4 * C + c, (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16, frac);
         }
+        interval_ahead = interval_next;
+        frac_cur = frac_next;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);

@@ -13,7 +13,8 @@ constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 
 // clock64 trace (debug aid, enabled by the SNSDE_TC_TRACE environment variable): 16 events per step, CTA 0.
 enum TraceEv { EV_EPI_ACC0 = 0, EV_EPI_LD0, EV_EPI_DONE0, EV_EPI_ACC1, EV_EPI_LD1, EV_EPI_DONE1, EV_EPI_SHADOW_END,
-               EV_MMA_WAKE0, EV_MMA_COMMIT0, EV_MMA_WAKE1, EV_MMA_COMMIT1, EV_MMA_X_DONE, EV_PREP_DONE, EV_PROD_DONE };
+               EV_MMA_WAKE0, EV_MMA_COMMIT0, EV_MMA_WAKE1, EV_MMA_COMMIT1, EV_MMA_X_DONE, EV_PREP_DONE, EV_PROD_DONE,
+               EV_EPI_PFULL, EV_EPI_PREPARED };
 #define TC_TRACE(cond, step, ev) do { if (p.dbg != nullptr && blockIdx.x == 0 && (cond)) p.dbg[(size_t)(step) * 16 + (ev)] = clock64(); } while (0)
 
 // Per-step broadcast block written by the step-prefetch warps (ring of 2).

@@ -385,42 +385,64 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       const int ptid = tid - 32 * kGProdWarp0;
       const int pwarp = warp - kGProdWarp0;
       const uint32_t row_bytes = 16u * C;
-      auto fetch = [&](int s) {
+      // Step metadata is loaded one iteration ahead (an exposed L2 round trip per step made this role the
+      // bottleneck of the whole kernel), and each thread's (row, channel) items are tabulated once.
+      auto fetch = [&](int s, int interval) {           // spline rows of step s -> staging slot (first producer warp only)
         if (pwarp != 0 || s >= p.S) return;
         const int stg = s % p.nstg;
         const uint32_t bar = bar_cfull + 8 * stg;
         if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * NR);
         __syncwarp();
-        const int interval = p.steps[s].interval;
         for (int r = lane; r < NR; r += 32) {
           const int b = min(row0 + r, p.B - 1);
           const float* src = p.coeffs + (size_t)b * p.coeff_row_stride + (size_t)interval * 4 * C;
           bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
         }
       };
-      for (int s = 0; s < p.nstg - 1; ++s) fetch(s);
+      constexpr int kMaxItems = 12;
+      int item_src[kMaxItems], item_dst[kMaxItems];
+#pragma unroll
+      for (int k = 0; k < kMaxItems; ++k) {
+        const int i = ptid + k * kGProdThreads;
+        const int r = i / C, c = i - r * C;
+        item_src[k] = (i < NR * C) ? r * 4 * C + c : -1;
+        item_dst[k] = (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+      }
+      auto eval_item = [&](const float* rows, uint8_t* xs, int src, int dst, float frac) {
+        const float* q0 = rows + src;
+        float inner = 0.5f * q0[2 * C] + __fdiv_rn(q0[3 * C] * frac, 3.0f);
+        inner = q0[C] + inner * frac;
+        const float x = q0[0] + inner * frac;
+        __half hi, lo;
+        split_f16(x, hi, lo);
+        if (fabsf(x) > 65504.f) *p.status = 1;
+        *reinterpret_cast<__half*>(xs + dst) = hi;
+        *reinterpret_cast<__half*>(xs + dst + (N / 8) * 128) = lo;
+      };
+      for (int s = 0; s < p.nstg - 1; ++s) fetch(s, s < p.S ? p.steps[s].interval : 0);
+      int interval_ahead = (p.nstg - 1 < p.S) ? p.steps[p.nstg - 1].interval : 0;
+      float frac_cur = p.S > 0 ? p.steps[0].frac : 0.f;
       for (int s = 0; s < p.S; ++s) {
-        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads));
-        fetch(s + p.nstg - 1);
+        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads));      // all producer warps are done with step s-1
+        fetch(s + p.nstg - 1, interval_ahead);
+        const int sa = s + p.nstg;
+        const int interval_next = sa < p.S ? p.steps[sa].interval : 0;       // consumed next iteration
+        const float frac_next = s + 1 < p.S ? p.steps[s + 1].frac : 0.f;
         const int stg = s % p.nstg, slot = s % p.nx;
-        const float frac = p.steps[s].frac;
+        const float frac = frac_cur;
         mbar_wait_relaxed(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
         if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
-        for (int i = ptid; i < NR * C; i += kGProdThreads) {
+#pragma unroll
+        for (int k = 0; k < kMaxItems; ++k)
+          if (item_src[k] >= 0) eval_item(rows, xs, item_src[k], item_dst[k], frac);
+        for (int i = ptid + kMaxItems * kGProdThreads; i < NR * C; i += kGProdThreads) {     // wide inputs: generic tail
           const int r = i / C, c = i - r * C;
-          const float* row = rows + r * 4 * C;
-          float inner = 0.5f * row[2 * C + c] + __fdiv_rn(row[3 * C + c] * frac, 3.0f);
-          inner = row[C + c] + inner * frac;
-          const float x = row[c] + inner * frac;
-          __half hi, lo;
-          split_f16(x, hi, lo);
-          if (fabsf(x) > 65504.f) *p.status = 1;
-          uint8_t* q = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
-          *reinterpret_cast<__half*>(q) = hi;
-          *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
+          eval_item(rows, xs, r * 4 * C + c, (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16, frac);
         }
+        interval_ahead = interval_next;
+        frac_cur = frac_next;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);
