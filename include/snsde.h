@@ -146,6 +146,13 @@ int snsde_philox_fill(uint64_t seed, uint64_t row_offset, int32_t S, int32_t B, 
  * Returns the flags (>= 0) or a negative snsde_status. */
 int snsde_plan_status(snsde_plan* plan, void* stream);
 
+/* Control-path coefficients on device.  Replaces, for NaN-free inputs,
+ * torchcde.hermite_cubic_coefficients_with_backward_differences(x, t) as the reference calls it at
+ * benchmark_classification/datasets/common.py:82-84: x_dev [B,K,C], knots_dev [K] ->
+ * coeffs_dev [B,K-1,4C] = cat(a,b,two_c,three_d), the packing snsde_forward reads. */
+int snsde_hermite_coeffs(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
+                         float* coeffs_dev, int device, void* stream);
+
 /* Number of engine kernels launched by this plan so far (for bench.py's gpu_launches). */
 int64_t snsde_plan_launch_count(const snsde_plan* plan);
 

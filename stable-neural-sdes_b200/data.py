@@ -5,6 +5,8 @@ dataset (/root/reference/benchmark_classification/datasets/common.py:82-84 via t
 benchmark_forecasting/datasets/common.py:79-81 via the in-tree natural spline) and feeds the
 packed ``[B, K-1, 4C]`` tensor to ``set_X``.  Packing: ``cat(a, b, two_c, three_d)``.
 """
+import ctypes
+
 import torch
 
 
@@ -54,3 +56,23 @@ def natural_cubic_coeffs(x, t):
     two_c = (6 * dx * rr - 4 * k0 - 2 * k1) * rr
     three_d = (-6 * dx * rr + 3 * (k0 + k1)) * rr ** 2
     return torch.cat((x[..., :-1, :], k0, two_c, three_d), dim=-1)
+
+
+def hermite_coeffs_cuda(x, t, out=None):
+    """Fused CUDA version of :func:`hermite_backward_difference_coeffs` for a NaN-free CUDA tensor
+    ``x [B, K, C]`` (one HBM pass through the C ABI, ``snsde_hermite_coeffs``)."""
+    from . import _lib
+    if not x.is_cuda or x.dim() != 3:
+        raise ValueError("snsde: hermite_coeffs_cuda needs a CUDA tensor [B, K, C]")
+    x = x.detach().to(torch.float32).contiguous()
+    t = t.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    B, K, C = x.shape
+    if t.shape != (K,):
+        raise ValueError("snsde: knots must be [K]")
+    if out is None:
+        out = torch.empty((B, K - 1, 4 * C), device=x.device, dtype=torch.float32)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.load().snsde_hermite_coeffs(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(t.data_ptr()), B, K, C,
+                                                ctypes.c_void_p(out.data_ptr()), x.device.index or 0,
+                                                ctypes.c_void_p(stream)))
+    return out

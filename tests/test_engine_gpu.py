@@ -422,3 +422,24 @@ def test_fp16_range_overflow_is_flagged_not_silent(dev):
     # the fp32 kernel has no such limit; unaffected rows of the tensor-core result are still right
     ok = [0, 1, 3, 4, 5]
     close(z_tc[:, ok], z32[:, ok])
+
+
+def test_hermite_coefficients_on_device_match_the_oracle_builder(dev):
+    from snsde_b200 import data
+    g = torch.Generator().manual_seed(0)
+    for B, K, C in ((3, 2, 1), (5, 7, 3), (64, 201, 35)):
+        times = torch.cat([torch.zeros(1), torch.rand(K - 1, generator=g) + 0.3]).cumsum(0)
+        x = torch.randn(B, K, C, generator=g).cumsum(1)
+        want = spline.hermite_cubic_coefficients_with_backward_differences(x, times)
+        got = data.hermite_coeffs_cuda(x.to(dev), times.to(dev))
+        assert got.shape == want.shape
+        assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-6)
+        # and the solve accepts them directly
+    m, times, coeffs, y0 = make_problem(4, 17, 8, 32, 3, 1, 9, seed=5)
+    x = torch.cat([coeffs[:, :, :3], (coeffs[:, -1:, :3] + coeffs[:, -1:, 3:6] * 1.0)], dim=1)   # knot values back from a,b (h = 1)
+    with torch.no_grad():
+        mg = m.to(dev)
+        c_dev = data.hermite_coeffs_cuda(x.to(dev), times.to(dev))
+        mg.set_X(c_dev, times.to(dev))
+        z = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=3)
+    assert torch.isfinite(z).all()
