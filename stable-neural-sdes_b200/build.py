@@ -16,8 +16,12 @@ HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = HERE / "build"
 LIB = HERE / "libsnsde.so"
+import os
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
+if os.environ.get("SNSDE_TRACE_BUILD"):       # debug build: compiles the clock64 trace events into the tcgen05 kernels
+    NVCC_FLAGS.append("-DSNSDE_TC_TRACE_BUILD")
 
 
 def _headers_hash():

@@ -91,25 +91,47 @@ __host__ __device__ inline TcSmem tc_smem_layout(int wimg_bytes, int H, int C, i
 // All MMAs of one operand segment (executed warp-uniformly; `leader` is the one issuing lane).
 // nk (16-wide K chunks) is a multiple of CH; chunk j feeds chain j % CH, so the chain index is a compile-time
 // constant inside the unrolled body.  `fresh`: the region holds no partial sums yet (first segment of a layer).
+// TSH / TSL: the hi / lo weight image is resident in TMEM (a_hi / a_lo is then a TMEM address and the MMA takes
+// the TS form).  Measured on B200 (tests/cuda/umma_probe.cu, M=128 K=16): an SS-form MMA costs >= 39 cycles
+// whatever N <= 32 is (it re-reads the 4 KB A tile from shared memory), a TS-form one 11 (N=16) / 17 (N=32).
 template <int N, int CH>
-__device__ __forceinline__ void issue_segment(bool leader, uint32_t a_hi, uint32_t a_lo, uint32_t b_base, int nk,
+__device__ __forceinline__ void issue_segment(bool leader, int ts, uint32_t a_hi, uint32_t a_lo, uint32_t b_base, int nk,
                                               uint32_t lbo_b, uint32_t d_tmem, bool fresh) {
   constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * N), idesc1 = umma_idesc_f16(128, N);
-  uint64_t da_hi = umma_smem_desc(a_hi, kALbo, kASbo);
-  uint64_t da_lo = umma_smem_desc(a_lo, kALbo, kASbo);
   uint64_t db = umma_smem_desc(b_base, lbo_b, 128);
   const uint64_t a_step = (uint64_t)((2 * kALbo) >> 4), b_step = (uint64_t)((2 * lbo_b) >> 4);
   uint32_t acc = fresh ? 0u : 1u;
+  if (ts == 3) {                                       // both images in TMEM: the hot loop
 #pragma unroll 2
+    for (int kb = 0; kb < nk; kb += CH) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        if (leader) {
+          umma_f16_ts(d_tmem + AccRegion<N, CH>::a(c), a_hi, db, idesc2, acc);
+          umma_f16_ts(d_tmem + AccRegion<N, CH>::b(c), a_lo, db, idesc1, acc);
+        }
+        a_hi += 8; a_lo += 8;                          // 8 TMEM columns = 16 fp16 of K
+        db += b_step;
+      }
+      acc = 1u;
+    }
+    return;
+  }
+  uint64_t da_hi = umma_smem_desc(a_hi, kALbo, kASbo);  // only meaningful for an SS-form image
+  uint64_t da_lo = umma_smem_desc(a_lo, kALbo, kASbo);
+  const bool tsh = (ts & 1) != 0, tsl = (ts & 2) != 0;  // warp-uniform
+#pragma unroll 1
   for (int kb = 0; kb < nk; kb += CH) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       if (leader) {
-        umma_f16(d_tmem + AccRegion<N, CH>::a(c), da_hi, db, idesc2, acc);
-        umma_f16(d_tmem + AccRegion<N, CH>::b(c), da_lo, db, idesc1, acc);
+        if (tsh) umma_f16_ts(d_tmem + AccRegion<N, CH>::a(c), a_hi, db, idesc2, acc);
+        else umma_f16(d_tmem + AccRegion<N, CH>::a(c), da_hi, db, idesc2, acc);
+        if (tsl) umma_f16_ts(d_tmem + AccRegion<N, CH>::b(c), a_lo, db, idesc1, acc);
+        else umma_f16(d_tmem + AccRegion<N, CH>::b(c), da_lo, db, idesc1, acc);
       }
-      da_hi += a_step;
-      da_lo += a_step;
+      a_hi += 8; a_lo += 8;
+      da_hi += a_step; da_lo += a_step;
       db += b_step;
     }
     acc = 1u;
@@ -125,7 +147,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, C = p.C, Cpad = p.Cpad, NL = p.NL;
-  const TcSmem L = tc_smem_layout(p.wimg_bytes, H, C, Cpad, N, NR, p.nx, p.nstg, p.uses_control);
+  const TcSmem L = tc_smem_layout(p.w_smem_bytes, H, C, Cpad, N, NR, p.nx, p.nstg, p.uses_control);
   const int row0 = blockIdx.x * NR;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -137,14 +159,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   // Two accumulator regions suffice: layer 0 owns region 0 (the X(t) segment of the NEXT step is issued into it
   // while the last layer's epilogue still reads), every later layer reuses region 1 (its MMAs are only issued
   // after the previous layer's epilogue has drained that region).
-  constexpr uint32_t kTmemCols = (2 * Acc::kCols <= 128) ? 128 : (2 * Acc::kCols <= 256 ? 256 : 512);
+  // The weight images that fit are kept in the TMEM columns behind the accumulators (p.img[].tmem_col).
   static_assert(2 * Acc::kCols <= 512, "TMEM budget");
+  const uint32_t kTmemCols = (uint32_t)p.tmem_cols;
 
   // ---- one-time setup: weights -> smem, zero the operand buffers, barriers, TMEM ----
   {
-    const uint4* src = reinterpret_cast<const uint4*>(p.wimg);
-    uint4* dst = reinterpret_cast<uint4*>(smem + L.w);
-    for (int i = tid; i < p.wimg_bytes / 16; i += kTcThreads) dst[i] = src[i];
+    for (int k = 0; k < p.n_img; ++k) {                 // SS-form images -> shared memory
+      if (p.img[k].tmem_col >= 0) continue;
+      const uint4* src = reinterpret_cast<const uint4*>(p.wimg + p.img[k].g_off);
+      uint4* dst = reinterpret_cast<uint4*>(smem + L.w + p.img[k].s_off);
+      for (int i = tid; i < p.img[k].bytes / 16; i += kTcThreads) dst[i] = src[i];
+    }
     uint4* z = reinterpret_cast<uint4*>(smem + L.b);
     const int zn = (L.stg - L.b) / 16;
     for (int i = tid; i < zn; i += kTcThreads) z[i] = make_uint4(0, 0, 0, 0);
@@ -169,6 +195,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   auto dcol = [&](int l) -> uint32_t { return (uint32_t)((l == 0 ? 0 : 1) * Acc::kCols); };
+  // TS-form images -> TMEM: lane m = weight row m, each 32-bit column packs two consecutive K elements, i.e. one
+  // 16-byte core-matrix row of the canonical image is 4 columns.  Warp w may only touch lane quadrant w % 4.
+  if (warp < kEpiWarps) {
+    const int m = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int k = 0; k < p.n_img; ++k) {
+      const TcImg im = p.img[k];
+      if (im.tmem_col < 0) continue;
+      const uint8_t* src = p.wimg + im.g_off + (m >> 3) * kASbo + (m & 7) * 16;
+      const int nkc = im.bytes / (2 * (int)kALbo);
+      for (int kc = (warp >> 2); kc < nkc; kc += kEpiPerQuad) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(src + (size_t)(2 * kc) * kALbo);
+        const uint4 hi = *reinterpret_cast<const uint4*>(src + (size_t)(2 * kc + 1) * kALbo);
+        const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tmem_st8(tmem + lane_base + (uint32_t)(im.tmem_col + kc * 8), r);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp < kEpiWarps) {
     // =========================== EPILOGUE / SDE STATE ===========================
@@ -365,36 +413,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
     // The whole warp runs this code (descriptor arithmetic stays on the uniform datapath); one elected
-    // lane issues the tcgen05 instructions.
+    // lane issues the tcgen05 instructions.  A step is NL layer segments plus the X(t) segment of the NEXT
+    // step's layer 0 (issued a layer early, into accumulator region 0); all of them go through ONE copy of
+    // the issue loop - the kernel's hot code has to stay inside the 32 KB instruction cache.
     const bool leader = elect_one();
     const uint32_t w_base = smem_u32(smem + L.w), b_base = smem_u32(smem + L.b), x_base = smem_u32(smem + L.x);
-    uint32_t pin = 0;
+    const bool has_x = p.uses_control != 0;
+    uint32_t pin = 0, xphase = 0;
     int xslot = 0;
-    uint32_t xphase = 0;
-    auto issue_x = [&]() {                 // X(t) segment of the NEXT step's layer 0, issued a layer early
-      mbar_wait(bar_xfull + 8 * xslot, xphase);
-      tc_fence_after();
-      issue_segment<N, CH>(leader, w_base + p.ax_hi, w_base + p.ax_lo, x_base + xslot * L.x_slot_bytes, Cpad / 16, L.lbo_b,
-                           tmem + dcol(0), true);
-      if (leader) umma_commit(bar_xempty + 8 * xslot);
-      __syncwarp();
-      if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
-    };
-    if (p.uses_control && p.S > 0) issue_x();
-    for (int s = 0; s < p.S; ++s) {
-      for (int l = 0; l < NL; ++l) {
-        mbar_wait(bar_in, pin);
-        pin ^= 1;
+    for (int s = -1; s < p.S; ++s) {
+      for (int seg = (s < 0 ? NL : 0); seg <= NL; ++seg) {
+        const bool isx = seg == NL;
+        if (isx && !(has_x && s + 1 < p.S)) continue;
+        int ts, nk;
+        uint32_t h_hi, h_lo, b_addr, d, commit_bar;
+        bool fresh;
+        if (isx) {
+          mbar_wait(bar_xfull + 8 * xslot, xphase);
+          ts = p.x_ts; h_hi = p.hx_hi; h_lo = p.hx_lo; nk = Cpad / 16;
+          b_addr = x_base + xslot * L.x_slot_bytes; d = tmem + dcol(0); fresh = true;
+          commit_bar = bar_xempty + 8 * xslot;
+          if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
+        } else {
+          mbar_wait(bar_in, pin);
+          pin ^= 1;
+          ts = p.layer[seg].ts; h_hi = p.layer[seg].h_hi; h_lo = p.layer[seg].h_lo; nk = p.layer[seg].K / 16;
+          b_addr = b_base; d = tmem + dcol(seg); fresh = !(seg == 0 && has_x);
+          commit_bar = bar_acc;
+        }
         tc_fence_after();
-        TC_TRACE(lane == 0 && l < 2, s, l == 0 ? EV_MMA_WAKE0 : EV_MMA_WAKE1);
-        issue_segment<N, CH>(leader, w_base + p.layer[l].a_hi, w_base + p.layer[l].a_lo, b_base, p.layer[l].K / 16, L.lbo_b,
-                             tmem + dcol(l), !(l == 0 && p.uses_control));
-        if (leader) umma_commit(bar_acc);
+        TC_TRACE(lane == 0 && seg < 2, s, seg == 0 ? EV_MMA_WAKE0 : EV_MMA_WAKE1);
+        issue_segment<N, CH>(leader, ts, ((ts & 1) ? tmem : w_base) + h_hi, ((ts & 2) ? tmem : w_base) + h_lo, b_addr, nk,
+                             L.lbo_b, d, fresh);
+        if (leader) umma_commit(commit_bar);
         __syncwarp();
-        TC_TRACE(lane == 0 && l < 2, s, l == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1);
+        TC_TRACE(lane == 0 && (seg < 2 || isx), s, isx ? EV_MMA_X_DONE : (seg == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1));
       }
-      if (p.uses_control && s + 1 < p.S) issue_x();
-      TC_TRACE(lane == 0, s, EV_MMA_X_DONE);
     }
   } else if (warp < kPrepWarp0) {
     // =========================== CONTROL PRODUCER ===========================
@@ -416,26 +470,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
           bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
         }
       };
-      constexpr int kMaxItems = 12;
-      int item_src[kMaxItems], item_dst[kMaxItems];
-#pragma unroll
-      for (int k = 0; k < kMaxItems; ++k) {
-        const int i = ptid + k * kProdThreads;
-        const int r = i / C, c = i - r * C;
-        item_src[k] = (i < NR * C) ? r * 4 * C + c : -1;
-        item_dst[k] = (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
-      }
-      auto eval_item = [&](const float* rows, uint8_t* xs, int src, int dst, float frac) {
-        const float* q0 = rows + src;
-        float inner = 0.5f * q0[2 * C] + __fdiv_rn(q0[3 * C] * frac, 3.0f);
-        inner = q0[C] + inner * frac;
-        const float x = q0[0] + inner * frac;
-        __half hi, lo;
-        split_f16(x, hi, lo);
-        if (fabsf(x) > 65504.f) *p.status = 1;
-        *reinterpret_cast<__half*>(xs + dst) = hi;
-        *reinterpret_cast<__half*>(xs + dst + (N / 8) * 128) = lo;
-      };
+      // (row, channel) items of this thread: i = ptid, ptid + 96, ...; the pair is advanced incrementally
+      // (no division in the loop) and the loop is NOT unrolled - compact code beats ILP here (I-cache).
+      const int r_first = ptid / C, c_first = ptid - r_first * C;
+      const int r_inc = kProdThreads / C, c_inc = kProdThreads - r_inc * C;
+#pragma unroll 1
       for (int s = 0; s < p.nstg - 1; ++s) fetch(s, s < p.S ? p.steps[s].interval : 0);
       int interval_ahead = (p.nstg - 1 < p.S) ? p.steps[p.nstg - 1].interval : 0;
       float frac_cur = p.S > 0 ? p.steps[0].frac : 0.f;
@@ -451,12 +490,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
-#pragma unroll
-        for (int k = 0; k < kMaxItems; ++k)
-          if (item_src[k] >= 0) eval_item(rows, xs, item_src[k], item_dst[k], frac);
-        for (int i = ptid + kMaxItems * kProdThreads; i < NR * C; i += kProdThreads) {     // wide inputs: generic tail
-          const int r = i / C, c = i - r * C;
-          eval_item(rows, xs, r * 4 * C + c, (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16, frac);
+        int r = r_first, c = c_first;
+#pragma unroll 1
+        while (r < NR) {
+          const float* q0 = rows + r * 4 * C + c;
+          float inner = 0.5f * q0[2 * C] + __fdiv_rn(q0[3 * C] * frac, 3.0f);
+          inner = q0[C] + inner * frac;
+          const float x = q0[0] + inner * frac;
+          __half hi, lo;
+          split_f16(x, hi, lo);
+          if (fabsf(x) > 65504.f) *p.status = 1;
+          uint8_t* dst = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+          *reinterpret_cast<__half*>(dst) = hi;
+          *reinterpret_cast<__half*>(dst + (N / 8) * 128) = lo;
+          r += r_inc; c += c_inc;
+          if (c >= C) { c -= C; ++r; }
         }
         interval_ahead = interval_next;
         frac_cur = frac_next;
@@ -478,35 +526,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     const float ccos = (p.c_cos >= 0 && act) ? p.vec[p.c_cos + h] : 0.f;
     float coef = t.coef_scalar;
     if (t.coef_src == CO_IMG && act) coef = p.vec[p.coef_vec + h];
+    // Global rows of this CTA start at gb0; Philox yields 4 normals for the aligned row quad gb >> 2, so the NR
+    // rows span nq = (gb0 % 4 + NR + 3) / 4 quads.  One quad per iteration of a NOT unrolled loop (I-cache).
+    const unsigned long long gb0 = p.row_offset + (unsigned long long)row0;
+    const int lane0 = (int)(gb0 & 3ull);
+    const int nq = (lane0 + NR + 3) >> 2;
     for (int s = 0; s < p.S; ++s) {
       const snsde_step st = p.steps[s];
       uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
       float* sdw = reinterpret_cast<float*>(slot);
       float cf = coef;
       if (t.coef_src == CO_VBUF && act) cf = p.a_tab[(size_t)s * H + h];
-      float dwv[NR];
-      if (act) {
-        if (p.dW != nullptr) {
-#pragma unroll
-          for (int r = 0; r < NR; ++r) dwv[r] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + h];
-        } else {
-          float nrm[4];
-#pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            const unsigned long long gb = p.row_offset + (unsigned long long)(row0 + r);
-            if (r == 0 || (gb & 3ull) == 0ull) philox_normals4(p.seed, (uint32_t)h, (uint32_t)(gb >> 2), (uint32_t)s, nrm);
-            dwv[r] = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), st.sqrt_h);
-          }
-        }
-      }
       StepInfo si;
       si.h = st.h; si.t0 = st.t0; si.n_emits = st.emit_end - st.emit_begin; si.emit_begin = st.emit_begin;
       si.first.slot = 0; si.first.w_prev = 0.f; si.first.w_curr = 0.f;
       if (h == 0 && si.n_emits > 0) si.first = p.emits[st.emit_begin];
       if (s >= 2) mbar_wait_relaxed(bar_pempty + 8 * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
       if (act) {
+        if (p.dW != nullptr) {
+#pragma unroll 4
+          for (int r = 0; r < NR; ++r) sdw[r * 128 + h] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + h];
+        } else {
+#pragma unroll 1
+          for (int q = 0; q < nq; ++q) {
+            float nrm[4];
+            philox_normals4(p.seed, (uint32_t)h, (uint32_t)((gb0 >> 2) + (unsigned long long)q), (uint32_t)s, nrm);
+            const int rq = q * 4 - lane0;               // CTA-local row of the quad's first normal
 #pragma unroll
-        for (int r = 0; r < NR; ++r) sdw[r * 128 + h] = dwv[r];
+            for (int k = 0; k < 4; ++k)
+              if ((unsigned)(rq + k) < (unsigned)NR) sdw[(rq + k) * 128 + h] = __fmul_rn(nrm[k], st.sqrt_h);
+          }
+        }
         sdw[NR * 128 + h] = fmaf(st.cos_t0, ccos, fmaf(st.sin_t0, csin, c0));
         sdw[(NR + 1) * 128 + h] = cf;
       }
@@ -553,12 +603,36 @@ const char* tc_unsupported_reason() { return g_reason.c_str(); }
 static bool is_time_opt(int io) { return io >= 3 && io <= 6; }
 static bool is_emb_opt(int io) { return io == 2 || io == 4 || io == 6; }
 
-static size_t tc_weight_bytes(const snsde_model_desc& d) {
-  const int H = d.hidden, L = d.num_hidden_layers;
-  const int Cpad = (d.input_channels + 31) & ~31;
-  size_t k_total = (size_t)H * (L + 1) + (is_emb_opt(d.input_option) ? Cpad : 0);
-  return k_total * 128 * 2 * 2;
+// Where each operand image lives for one launch shape: TMEM columns behind the two accumulator regions while
+// they last (layers first - they are on the critical path - then the control segment), shared memory otherwise.
+// Fills p.img / the layers' handles / p.tmem_cols and returns the bytes of the shared-memory weight area.
+static int tc_place(TcParams& p, int N, int CH, bool use_tmem) {
+  int col = 2 * CH * 3 * N, soff = 0;
+  p.n_img = 0;
+  auto place = [&](int g_off, int K, int& handle, int& ts, int bit) {
+    TcImg im;
+    im.g_off = g_off; im.bytes = (K / 8) * (int)kALbo;
+    const int need = K / 2;
+    if (use_tmem && col + need <= 512) { im.tmem_col = col; im.s_off = -1; handle = col; ts |= bit; col += need; }
+    else { im.tmem_col = -1; im.s_off = soff; handle = soff; soff += im.bytes; }
+    p.img[p.n_img++] = im;
+  };
+  for (int l = 0; l < p.NL; ++l) {
+    p.layer[l].ts = 0;
+    place(p.layer[l].a_hi, p.layer[l].K, p.layer[l].h_hi, p.layer[l].ts, 1);
+    place(p.layer[l].a_lo, p.layer[l].K, p.layer[l].h_lo, p.layer[l].ts, 2);
+  }
+  p.x_ts = 0; p.hx_hi = p.hx_lo = 0;
+  if (p.uses_control) {
+    place(p.ax_hi, p.Cpad, p.hx_hi, p.x_ts, 1);
+    place(p.ax_lo, p.Cpad, p.hx_lo, p.x_ts, 2);
+  }
+  p.tmem_cols = col <= 128 ? 128 : (col <= 256 ? 256 : 512);
+  p.w_smem_bytes = soff;
+  return soff;
 }
+static bool tc_env_no_tmem() { return getenv("SNSDE_TC_NO_TMEM") != nullptr; }     // testing aid: every image SS-form
+static int tc_env_chains() { const char* e = getenv("SNSDE_TC_CH"); return (e && atoi(e) == 2) ? 2 : 1; }
 
 bool tc_supported(const snsde_model_desc& d, int cc_major, int smem_optin) {
   const int no = d.noise_option, io = d.input_option;
@@ -571,7 +645,13 @@ bool tc_supported(const snsde_model_desc& d, int cc_major, int smem_optin) {
   if (d.hidden % 32 || d.hidden < 32 || d.hidden > 128) { g_reason = "needs hidden in {32,64,96,128}"; return false; }
   if (d.num_hidden_layers + 1 > kTcMaxLayers) { g_reason = "too many hidden layers"; return false; }
   const int Cpad = (d.input_channels + 31) & ~31;
-  const TcSmem L = tc_smem_layout((int)tc_weight_bytes(d), d.hidden, d.input_channels, Cpad, 16, 8, 2, 2, is_emb_opt(io));
+  if (Cpad > 256) { g_reason = "too many input channels for the resident kernel"; return false; }
+  TcParams q;                                         // smallest launch shape: 8 rows per CTA, one accumulator chain
+  memset(&q, 0, sizeof(q));
+  q.NL = d.num_hidden_layers + 1; q.uses_control = is_emb_opt(io); q.Cpad = Cpad;
+  for (int l = 0; l < q.NL; ++l) q.layer[l].K = d.hidden;
+  const int wsm = tc_place(q, 16, 1, !tc_env_no_tmem());
+  const TcSmem L = tc_smem_layout(wsm, d.hidden, d.input_channels, Cpad, 16, 8, 2, 2, is_emb_opt(io));
   if (L.total > smem_optin) { g_reason = "weights + operand buffers exceed shared memory"; return false; }
   return true;
 }
@@ -751,14 +831,17 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
   // rows per CTA: the fewest that still covers the batch in one wave; then whatever shared memory allows
   int NR = 8;
   while (NR < 32 && (a.B + NR - 1) / NR > tc.num_sms) NR *= 2;
+  const int CH = tc_env_chains();
+  const bool use_tmem = !tc_env_no_tmem();
   TcSmem L;
   for (;;) {
     const int N = NR < 16 ? 16 : NR;
+    const int wsm = tc_place(p, N, CH, use_tmem);
     bool ok = false;
     for (int cfg = 0; cfg < 3 && !ok; ++cfg) {
       p.nx = cfg == 0 ? 4 : 2;
       p.nstg = cfg == 2 ? 2 : 4;
-      L = tc_smem_layout(p.wimg_bytes, p.H, p.C, p.Cpad, N, NR, p.nx, p.nstg, p.uses_control);
+      L = tc_smem_layout(wsm, p.H, p.C, p.Cpad, N, NR, p.nx, p.nstg, p.uses_control);
       ok = L.total <= tc.smem_optin;
     }
     if (ok) break;
@@ -768,14 +851,20 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
   const int grid = (a.B + NR - 1) / NR;
   cudaError_t e;
   const bool fast_diff = p.tail.bounded && p.tail.special == SP_NONE && p.tail.mult == MU_Y;
-  // Two accumulator chains per product.  (Four chains were measured on c2/c3: the MMA phase gets shorter but
-  // the extra TMEM loads/adds in the epilogue cost more - the template parameter is kept for experiments.)
-  switch (NR * 2 + (fast_diff ? 1 : 0)) {
-    case 16: e = tc_launch_one<8, 0, 2>(p, grid, L.total, stream); break;
-    case 17: e = tc_launch_one<8, 1, 2>(p, grid, L.total, stream); break;
-    case 32: e = tc_launch_one<16, 0, 2>(p, grid, L.total, stream); break;
-    case 33: e = tc_launch_one<16, 1, 2>(p, grid, L.total, stream); break;
-    case 64: e = tc_launch_one<32, 0, 2>(p, grid, L.total, stream); break;
+  // Accumulator chains per product: with the weights in TMEM the MMA phase is short and one chain is best (fewer
+  // TMEM loads/adds in the epilogue); two chains stay selectable (SNSDE_TC_CH=2) for experiments.
+  switch ((CH == 2 ? 128 : 0) + NR * 2 + (fast_diff ? 1 : 0)) {
+    case 16: e = tc_launch_one<8, 0, 1>(p, grid, L.total, stream); break;
+    case 17: e = tc_launch_one<8, 1, 1>(p, grid, L.total, stream); break;
+    case 32: e = tc_launch_one<16, 0, 1>(p, grid, L.total, stream); break;
+    case 33: e = tc_launch_one<16, 1, 1>(p, grid, L.total, stream); break;
+    case 64: e = tc_launch_one<32, 0, 1>(p, grid, L.total, stream); break;
+    case 65: e = tc_launch_one<32, 1, 1>(p, grid, L.total, stream); break;
+    case 128 + 16: e = tc_launch_one<8, 0, 2>(p, grid, L.total, stream); break;
+    case 128 + 17: e = tc_launch_one<8, 1, 2>(p, grid, L.total, stream); break;
+    case 128 + 32: e = tc_launch_one<16, 0, 2>(p, grid, L.total, stream); break;
+    case 128 + 33: e = tc_launch_one<16, 1, 2>(p, grid, L.total, stream); break;
+    case 128 + 64: e = tc_launch_one<32, 0, 2>(p, grid, L.total, stream); break;
     default: e = tc_launch_one<32, 1, 2>(p, grid, L.total, stream); break;
   }
   if (e == cudaSuccess) *n_launches += 1;

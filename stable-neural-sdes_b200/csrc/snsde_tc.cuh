@@ -9,20 +9,35 @@ namespace snsde {
 constexpr int kTcMaxLayers = 6;
 
 struct TcLayer {
-  int a_hi, a_lo;   // byte offsets of the fp16 hi / scaled-lo operand images inside the weight image
+  int a_hi, a_lo;   // byte offsets of the fp16 hi / scaled-lo operand images inside the (global) weight image
   int K;            // contraction length (multiple of 16)
   int bias;         // float offset into the vector region
+  // per-launch placement of the two operand images: a TMEM column offset (TS-form MMA, bit set in `ts`) or a
+  // byte offset into the shared-memory weight area (SS-form MMA)
+  int h_hi, h_lo, ts;   // ts bit 0: hi image in TMEM, bit 1: lo image in TMEM
 };
+
+// One operand image (hi or lo part of one weight matrix) and where this launch keeps it.
+struct TcImg {
+  int g_off, bytes;     // location inside the global weight image
+  int tmem_col;         // >= 0: resident in TMEM from this column on (K/2 columns); -1: shared memory
+  int s_off;            // byte offset inside the shared-memory weight area (when tmem_col < 0)
+};
+constexpr int kTcMaxImgs = 2 * (kTcMaxLayers + 1);
 
 // Everything the tcgen05 kernel needs; built by tc_set_weights (model part) and tc_forward (call part).
 struct TcParams {
   int H, C, Cpad, NL, uses_control;
   TcLayer layer[kTcMaxLayers];
-  int ax_hi, ax_lo;          // control segment of layer 0 (K = Cpad), byte offsets
+  int ax_hi, ax_lo;          // control segment of layer 0 (K = Cpad), byte offsets in the global image
+  int hx_hi, hx_lo, x_ts;    // its per-launch placement (see TcLayer)
+  TcImg img[kTcMaxImgs]; int n_img;
+  int tmem_cols;             // TMEM columns to allocate (power of two)
   int c_sin, c_cos;          // float offsets of the folded time-feature vectors of layer 0 (-1: none)
   int coef_vec;              // float offset of a per-feature diffusion coefficient vector (-1: none)
   TailOp tail;
-  const uint8_t* wimg; int wimg_bytes;
+  const uint8_t* wimg; int wimg_bytes;   // global weight image
+  int w_smem_bytes;          // bytes of the shared-memory weight area (SS-form images of this launch)
   const float* vec;
   const float* a_tab;        // [S][H] per-step diffusion coefficient (noise_t networks), or null
   // per call

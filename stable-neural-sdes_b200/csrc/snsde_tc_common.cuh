@@ -15,7 +15,13 @@ constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 enum TraceEv { EV_EPI_ACC0 = 0, EV_EPI_LD0, EV_EPI_DONE0, EV_EPI_ACC1, EV_EPI_LD1, EV_EPI_DONE1, EV_EPI_SHADOW_END,
                EV_MMA_WAKE0, EV_MMA_COMMIT0, EV_MMA_WAKE1, EV_MMA_COMMIT1, EV_MMA_X_DONE, EV_PREP_DONE, EV_PROD_DONE,
                EV_EPI_PFULL, EV_EPI_PREPARED };
-#define TC_TRACE(cond, step, ev) do { if (p.dbg != nullptr && blockIdx.x == 0 && (cond)) p.dbg[(size_t)(step) * 16 + (ev)] = clock64(); } while (0)
+// The trace code is compiled in only with -DSNSDE_TC_TRACE_BUILD (SNSDE_TRACE_BUILD=1 python .../build.py): the hot code of
+// the persistent kernels has to fit the 32 KB instruction cache and every event costs ~10 instructions.
+#ifdef SNSDE_TC_TRACE_BUILD
+#define TC_TRACE(cond, step, ev) do { if (p.dbg != nullptr && blockIdx.x == 0 && (step) >= 0 && (cond)) p.dbg[(size_t)(step) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TC_TRACE(cond, step, ev) do { } while (0)
+#endif
 
 // Per-step broadcast block written by the step-prefetch warps (ring of 2).
 struct StepInfo {

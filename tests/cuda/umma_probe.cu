@@ -15,6 +15,7 @@
 using namespace snsde::ptx;
 
 constexpr int M = 128;
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 struct Args {
   const __half* A; const __half* B; float* D;
@@ -131,6 +132,192 @@ __global__ void __launch_bounds__(192) probe_kernel(Args p) {
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+
+// Pure issue-rate probe: `n` MMAs (M=128, N, K=16 each) round-robin over NACC independent accumulators and 4 K chunks,
+// one commit at the end; cycles measured by the issuing warp from the first issue to the commit's arrival.
+// Everything is compile-time so the loop body is just the MMA instructions (warp-uniform code, one elected lane).
+template <int N, int NACC, int ATMEM, int PADB = 0, int ALT = 0, int POLL = 0, int INIT = 0, int SAMEB = 0>
+__global__ void __launch_bounds__(384) rate_kernel(int n, int two_issuers, long long* cycles, int reps = 1, int gap = 0) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t lbo_b = (N / 8) * 128 + PADB;     // PADB: the kernel's de-conflicting pad between K groups
+  constexpr int kA = 8 * 2048, kB = 8 * lbo_b;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kA + kB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (kA + kB) / 4; i += blockDim.x) {
+    uint32_t v = 0;
+    if (INIT) {                       // non-zero fp16 pairs in [-1, 1): is the MMA rate data dependent?
+      const uint32_t hsh = (uint32_t)i * 2654435761u;
+      const __half2 h2 = __floats2half2_rn(((int)(hsh >> 8 & 2047) - 1024) / 1024.f, ((int)(hsh >> 20 & 2047) - 1024) / 1024.f);
+      v = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    ((uint32_t*)smem)[i] = v;
+  }
+  if (tid == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (INIT && warp < 4) {             // A tiles in TMEM: same kind of data
+    uint32_t r[8];
+    for (int c = 0; c < 32; c += 8) {
+      for (int i = 0; i < 8; ++i) r[i] = ((const uint32_t*)smem)[(tid * 32 + c + i) & 1023];
+      tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + 480 + c, r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  if (INIT) { __syncthreads(); tc_fence_after(); }
+  constexpr uint32_t idesc = umma_idesc_f16(M, N), idesc_h = umma_idesc_f16(M, N / 2);   // ALT: alternate N and N/2 (hi / lo products)
+  if (warp == 0 || (two_issuers && warp == 1)) {
+    const bool leader = elect_one();
+    const uint64_t da0 = umma_smem_desc(smem_u32(smem), 2048, 128);
+    const uint64_t db0 = umma_smem_desc(smem_u32(smem + kA), lbo_b, 128);
+    const uint32_t acc0 = tmem + (warp == 1 ? 256u : 0u);
+    const uint32_t at0 = tmem + 480;
+    const long long t0 = clock64();
+    long long t1 = t0, t2 = t0, issue = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+      const long long ta = clock64();
+      uint32_t accf = 0;
+      for (int i = 0; i < n; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (leader) {
+            if (ATMEM) umma_f16_ts(acc0 + (j % NACC) * N, at0 + (j & 3) * 8, db0 + (uint64_t)((((SAMEB ? j >> 1 : j) & 3) * 2 * lbo_b) >> 4), (ALT == 1 && (j & 1)) || (ALT == 2 && (j & 4)) ? idesc_h : idesc, accf);
+            else umma_f16(acc0 + (j % NACC) * N, da0 + (uint64_t)(((j & 3) * 2 * 2048) >> 4), db0 + (uint64_t)((((SAMEB ? j >> 1 : j) & 3) * 2 * lbo_b) >> 4), (ALT == 1 && (j & 1)) || (ALT == 2 && (j & 4)) ? idesc_h : idesc, accf);
+          }
+        }
+        accf = 1;
+      }
+      if (leader) umma_commit(smem_u32(&bars[warp]));
+      __syncwarp();
+      t1 = clock64();
+      issue += t1 - ta;
+      mbar_wait(smem_u32(&bars[warp]), rep & 1);
+      t2 = clock64();
+      if (gap) __nanosleep(gap);
+    }
+    if (reps > 1) { t1 = t0 + issue / reps; t2 = t0 + (t2 - t0) / reps; }
+    if (lane_id() == 0 && warp == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t0; }
+    if (POLL && lane_id() == 0 && warp == 0) mbar_arrive(smem_u32(&bars[1]));
+  } else if (POLL && warp >= 4) {
+    // bystanders polling an mbarrier in shared memory the way the kernel's waiting roles do:
+    // POLL 1: every lane spins on try_wait; POLL 2: one lane spins, the rest park at __syncwarp; POLL 3: all lanes, nanosleep back-off
+    const uint32_t bar = smem_u32(&bars[1]);
+    if (POLL == 1) { while (!mbar_try_wait(bar, 0)) {} }
+    else if (POLL == 2) { if (lane_id() == 0) { while (!mbar_try_wait(bar, 0)) {} } __syncwarp(); }
+    else { while (!mbar_try_wait(bar, 0)) __nanosleep(64); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int N, int NACC, int ATMEM, int PADB = 0, int ALT = 0, int POLL = 0, int INIT = 0, int SAMEB = 0>
+static void rate(int n, int two, int reps = 1, int gap = 0) {
+  long long* dC; cudaMalloc(&dC, 16);
+  const size_t smem = 8 * 2048 + 8 * ((N / 8) * 128 + PADB) + 64;
+  auto k = rate_kernel<N, NACC, ATMEM, PADB, ALT, POLL, INIT, SAMEB>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<1, POLL ? 384 : 128, smem>>>(n, two, dC, reps, gap);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  CUDA error: %s\n", cudaGetErrorString(e)); exit(2); }
+  long long c[2]; cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost);
+  printf("rate N=%3d nacc=%d A=%s padB=%d alt=%d poll=%d init=%d sameB=%d issuers=%d reps=%d gap=%d: %d MMAs  issue %.1f cyc/MMA, complete %.1f cyc/MMA\n", N, NACC, ATMEM ? "tmem" : "smem", PADB, ALT, POLL, INIT, SAMEB,
+         two ? 2 : 1, reps, gap, n, (double)c[0] / n, (double)c[1] / n);
+  cudaFree(dC);
+}
+
+
+// Kernel-like burst: exactly the operand/accumulator geometry of snsde_tc_kernel<8,.,1> at c2 (N=16): per K chunk a
+// hi MMA (N'=32, D at column DH) and a lo MMA (N=16, D at column DL), A-hi at AH + 8k, A-lo at AL + 8k, B chunk k.
+__global__ void __launch_bounds__(512) klike_kernel(int nk, int DH, int DL, int AH, int AL, int reps, long long* cycles, int nwait, int mode) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t lbo_b = 4 * 128 + 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16 * lbo_b);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16 * lbo_b / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003800u + i;
+  if (tid == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), nwait > 0 ? nwait : 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp < 4) {
+    uint32_t r[8];
+    for (int c = 96; c < 512; c += 8) {
+      for (int i = 0; i < 8; ++i) r[i] = 0x38003c00u + (uint32_t)(tid * 7 + c + i);
+      tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + c, r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  constexpr uint32_t idesc2 = umma_idesc_f16(M, 32), idesc1 = umma_idesc_f16(M, 16);
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const uint64_t db0 = umma_smem_desc(smem_u32(smem), lbo_b, 128);
+    const uint64_t b_step = (uint64_t)((2 * lbo_b) >> 4);
+    long long issue = 0, total = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+      if (nwait > 0 && rep > 0) { mbar_wait(smem_u32(&bars[1]), (rep - 1) & 1); tc_fence_after(); }
+      const long long ta = clock64();
+      uint64_t db = db0;
+      uint32_t ah = tmem + AH, al = tmem + AL, acc = 0;
+#pragma unroll 4
+      for (int k = 0; k < nk; ++k) {
+        if (leader) {
+          umma_f16_ts(tmem + DH, ah, db, idesc2, acc);
+          umma_f16_ts(tmem + DL, al, db, idesc1, acc);
+        }
+        ah += 8; al += 8; db += b_step; acc = 1;
+      }
+      const long long tb = clock64();
+      if (leader) umma_commit(smem_u32(&bars[0]));
+      __syncwarp();
+      mbar_wait(smem_u32(&bars[0]), rep & 1);
+      const long long tc = clock64();
+      issue += tb - ta; total += tc - ta;
+    }
+    if (lane_id() == 0) { cycles[0] = issue / reps; cycles[1] = total / reps; }
+  } else if (warp >= 4 && warp < 4 + nwait) {
+    // bystander "epilogue" warps: wait for the commit, (mode 1: read 8 accumulator columns, rewrite a B element), hand over
+    for (int rep = 0; rep < reps; ++rep) {
+      mbar_wait(smem_u32(&bars[0]), rep & 1);
+      tc_fence_after();
+      if (mode == 1) {
+        float v[8];
+        tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + DH, v);
+        tmem_ld_wait();
+        ((__half*)smem)[tid] = __float2half(v[0] * 1e-9f + 1.f);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(smem_u32(&bars[1]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+static void klike(int nk, int DH, int DL, int AH, int AL, int nwait = 0, int mode = 0) {
+  long long* dC; cudaMalloc(&dC, 16);
+  const size_t smem = 16 * (4 * 128 + 16) + 64;
+  klike_kernel<<<1, 128 + 32 * nwait, smem>>>(nk, DH, DL, AH, AL, 200, dC, nwait, mode);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  CUDA error: %s\n", cudaGetErrorString(e)); exit(2); }
+  long long c[2]; cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost);
+  printf("klike nk=%d D(hi)=%d D(lo)=%d A(hi)=%d A(lo)=%d waiters=%d mode=%d: issue %lld, issue->complete %lld cycles per phase of %d MMAs\n", nk, DH, DL, AH, AL, nwait, mode, c[0], c[1], 2 * nk);
+  cudaFree(dC);
+}
+
 // canonical K-major no-swizzle image of X[rows][K] (fp16): 8x(16 byte) core matrices
 static void pack(const std::vector<float>& X, int rows, int K, uint32_t lbo, uint32_t sbo, std::vector<__half>& img, size_t bytes) {
   img.assign(bytes / 2, __float2half(0.f));
@@ -181,8 +368,14 @@ static double run(int N, int K, bool swap_desc, uint32_t b_pad, int iters, doubl
   return err;
 }
 
-int main() {
+int main(int argc, char** argv) {
   srand(1);
+  if (argc > 1) {
+    klike(8, 48, 80, 96, 160);
+    klike(8, 48, 80, 96, 160, 1, 0); klike(8, 48, 80, 96, 160, 4, 0); klike(8, 48, 80, 96, 160, 8, 0); klike(8, 48, 80, 96, 160, 12, 0);
+    klike(8, 48, 80, 96, 160, 4, 1); klike(8, 48, 80, 96, 160, 8, 1); klike(8, 48, 80, 96, 160, 12, 1);
+    return 0;
+  }
   for (g_a_tmem = 0; g_a_tmem < 2; ++g_a_tmem) {
   printf("==== A operand from %s ====\n", g_a_tmem ? "TMEM (tcgen05.st + TS-form MMA)" : "shared memory");
   for (int N : {16, 32, 64}) {

@@ -314,6 +314,9 @@ TC_CASES = [
     (5, 13, 96, 7, 2, 27, "euler"),          # geometric drift, Linear(2,H) noise * y
     (2, 0, 32, 2, 1, 5, "euler"),
     (6, 9, 64, 6, 1, 300, "euler"),          # B > 148*... multiple rows per CTA (NR=16)
+    (4, 17, 128, 35, 2, 30, "euler"),        # H=128 with a hidden layer: 448 TMEM columns of weights -> last images SS-form from smem
+    (2, 16, 128, 9, 4, 8, "euler"),          # 5 drift layers: most images stay in shared memory
+    (4, 17, 128, 35, 1, 600, "euler"),       # NR=32 rows per CTA: wider accumulators leave 320 TMEM columns for weights
 ]
 
 
@@ -371,14 +374,15 @@ TCG_CASES = [
     (4, 18, 96, 5, 3, 11, "euler"),        # noise net finishes two phases before the drift
     (4, 17, 256, 14, 1, 20, "euler"),      # c5 model: two M tiles, weights (557 KB) streamed through the ring
     (6, 17, 192, 7, 1, 13, "milstein"),    # two M tiles with a partial second tile
-    (4, 17, 128, 35, 2, 30, "euler"),      # H=128 with a hidden layer: exceeds smem -> partly streamed
+    (4, 17, 128, 35, 2, 30, "euler"),      # H=128 with a hidden layer: partly streamed
     (2, 16, 128, 9, 4, 8, "euler"),        # 5 drift phases
     (3, 13, 256, 3, 2, 150, "euler"),      # H=256, no control, NR=8 with >148... single wave, Linear(2,H) noise table
 ]
 
 
 @pytest.mark.parametrize("io,no,H,C,L,B,method", TCG_CASES)
-def test_general_tc_kernel_matches_oracle(io, no, H, C, L, B, method, dev):
+def test_general_tc_kernel_matches_oracle(io, no, H, C, L, B, method, dev, monkeypatch):
+    monkeypatch.setenv("SNSDE_FORCE_TCG", "1")       # some of these shapes also fit the resident kernel (weights in TMEM)
     K = 21
     m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, K, seed=3 * H + io + no)
     dt = solver.solver_dt(times)
@@ -404,6 +408,25 @@ def test_general_kernel_agrees_with_resident_kernel(dev, monkeypatch):
         b = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
         assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05_general"
     close(b, a, rtol=1e-5)
+
+
+def test_weights_in_tmem_agree_with_weights_in_smem(dev, monkeypatch):
+    """TS-form MMAs (weight images resident in TMEM) against the SS-form path (SNSDE_TC_NO_TMEM) and two chains."""
+    B, H, C, L, K = 70, 128, 35, 1, 41
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=9)
+    fi = torch.randint(1, K, (B,), generator=torch.Generator().manual_seed(3))
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    with torch.no_grad():
+        a = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
+        assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05"
+        monkeypatch.setenv("SNSDE_TC_NO_TMEM", "1")
+        b = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
+        monkeypatch.delenv("SNSDE_TC_NO_TMEM")
+        monkeypatch.setenv("SNSDE_TC_CH", "2")
+        c = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
+    assert torch.equal(a, b)               # same products, same accumulation order: only the operand source differs
+    close(c, a, rtol=1e-5)
 
 
 def test_fp16_range_overflow_is_flagged_not_silent(dev):
