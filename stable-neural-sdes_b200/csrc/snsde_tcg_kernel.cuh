@@ -194,12 +194,13 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         }
       }
     };
-    for (int e = 0; e < p.n_init_emits; ++e) {
-      snsde_emit em = p.emits[e];
-      em.w_prev = 0.f; em.w_curr = 1.f;
-      emit(em);
-    }
     hand_over();
+    // Outputs are written at ONE place in the code (top of the loop: the emits the previous step left pending,
+    // initially the outputs at ts[0] with weights (0, 1)): the hot code has to fit the 32 KB instruction cache.
+    int pend_n = p.n_init_emits, pend_begin = 0;
+    snsde_emit pend_first;
+    pend_first.slot = 0; pend_first.w_prev = 0.f; pend_first.w_curr = 1.f;
+    if (pend_n > 0) { pend_first = p.emits[0]; pend_first.w_prev = 0.f; pend_first.w_curr = 1.f; }
 
     auto state_terms = [&](float yr, float cf, float t0, float& g, float& dgy, float& th) {
       if (DIFF == 1) {
@@ -214,7 +215,17 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     };
 
     uint32_t pacc = 0;
-    for (int s = 0; s < p.S; ++s) {
+    for (int s = 0; s <= p.S; ++s) {
+#pragma unroll 1
+      for (int e = 0; e < pend_n; ++e) {
+        snsde_emit em = pend_first;
+        if (e > 0) {
+          em = p.emits[pend_begin + e];
+          if (s == 0) { em.w_prev = 0.f; em.w_curr = 1.f; }
+        }
+        emit(em);
+      }
+      if (s == p.S) break;
       const uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
       const float* sdw = reinterpret_cast<const float*>(slot);
       mbar_wait(bar_pfull + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
@@ -298,8 +309,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pempty + 8 * (s & 1));
-      if (si.n_emits > 0) emit(si.first);
-      for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);
+      pend_n = si.n_emits; pend_begin = si.emit_begin; pend_first = si.first;
       TC_TRACE(tid == 0, s, EV_EPI_SHADOW_END);
     }
   } else if (warp == kGMmaWarp) {
@@ -355,29 +365,37 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         }
       }
     };
-    auto issue_x = [&]() {
-      mbar_wait(bar_xfull + 8 * xslot, xphase);
-      tc_fence_after();
-      for (int j = p.n_jobs - p.n_xjobs; j < p.n_jobs; ++j) issue_job(j, x_base + xslot * L.x_slot_bytes);
-      if (leader) umma_commit(bar_xempty + 8 * xslot);
-      __syncwarp();
-      if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
-    };
-    if (p.n_xjobs > 0 && p.S > 0) issue_x();
-    for (int s = 0; s < p.S; ++s) {
+    // One step = NP phases of drift/noise jobs + the X(t) jobs of the NEXT step's phase 0 (issued a phase early);
+    // every job goes through ONE inlined copy of issue_job (instruction cache).
+    const int n_main = p.n_jobs - p.n_xjobs;
+    for (int s = -1; s < p.S; ++s) {
       int j = 0;
-      for (int ph = 0; ph < NP; ++ph) {
-        mbar_wait(bar_in, pin);
-        pin ^= 1;
+      for (int ph = (s < 0 ? NP : 0); ph <= NP; ++ph) {
+        const bool isx = ph == NP;
+        if (isx && !(p.n_xjobs > 0 && s + 1 < p.S)) continue;
+        int j_end;
+        uint32_t commit_bar, xb = 0;
+        if (isx) {
+          mbar_wait(bar_xfull + 8 * xslot, xphase);
+          j = n_main; j_end = p.n_jobs;
+          xb = x_base + xslot * L.x_slot_bytes;
+          commit_bar = bar_xempty + 8 * xslot;
+          if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
+        } else {
+          mbar_wait(bar_in, pin);
+          pin ^= 1;
+          j_end = j;
+          while (j_end < n_main && p.jobs[j_end].phase == ph) ++j_end;
+          commit_bar = bar_acc;
+        }
         tc_fence_after();
         TC_TRACE(lane == 0 && ph < 2, s, ph == 0 ? EV_MMA_WAKE0 : EV_MMA_WAKE1);
-        for (; j < p.n_jobs - p.n_xjobs && p.jobs[j].phase == ph; ++j) issue_job(j, p.jobs[j].b_src ? b_base1 : b_base0);
-        if (leader) umma_commit(bar_acc);
+#pragma unroll 1
+        for (; j < j_end; ++j) issue_job(j, isx ? xb : (p.jobs[j].b_src ? b_base1 : b_base0));
+        if (leader) umma_commit(commit_bar);
         __syncwarp();
-        TC_TRACE(lane == 0 && ph < 2, s, ph == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1);
+        TC_TRACE(lane == 0 && (ph < 2 || isx), s, isx ? EV_MMA_X_DONE : (ph == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1));
       }
-      if (p.n_xjobs > 0 && s + 1 < p.S) issue_x();
-      TC_TRACE(lane == 0, s, EV_MMA_X_DONE);
     }
   } else if (warp < kGStreamWarp) {
     // =========================== CONTROL PRODUCER ===========================
@@ -399,26 +417,11 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
           bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
         }
       };
-      constexpr int kMaxItems = 12;
-      int item_src[kMaxItems], item_dst[kMaxItems];
-#pragma unroll
-      for (int k = 0; k < kMaxItems; ++k) {
-        const int i = ptid + k * kGProdThreads;
-        const int r = i / C, c = i - r * C;
-        item_src[k] = (i < NR * C) ? r * 4 * C + c : -1;
-        item_dst[k] = (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
-      }
-      auto eval_item = [&](const float* rows, uint8_t* xs, int src, int dst, float frac) {
-        const float* q0 = rows + src;
-        float inner = 0.5f * q0[2 * C] + __fdiv_rn(q0[3 * C] * frac, 3.0f);
-        inner = q0[C] + inner * frac;
-        const float x = q0[0] + inner * frac;
-        __half hi, lo;
-        split_f16(x, hi, lo);
-        if (fabsf(x) > 65504.f) *p.status = 1;
-        *reinterpret_cast<__half*>(xs + dst) = hi;
-        *reinterpret_cast<__half*>(xs + dst + (N / 8) * 128) = lo;
-      };
+      // (row, channel) items of this thread: i = ptid, ptid + 64, ...; the pair is advanced incrementally
+      // (no division in the loop) and the loop is NOT unrolled - compact code beats ILP here (I-cache).
+      const int r_first = ptid / C, c_first = ptid - r_first * C;
+      const int r_inc = kGProdThreads / C, c_inc = kGProdThreads - r_inc * C;
+#pragma unroll 1
       for (int s = 0; s < p.nstg - 1; ++s) fetch(s, s < p.S ? p.steps[s].interval : 0);
       int interval_ahead = (p.nstg - 1 < p.S) ? p.steps[p.nstg - 1].interval : 0;
       float frac_cur = p.S > 0 ? p.steps[0].frac : 0.f;
@@ -434,12 +437,21 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
-#pragma unroll
-        for (int k = 0; k < kMaxItems; ++k)
-          if (item_src[k] >= 0) eval_item(rows, xs, item_src[k], item_dst[k], frac);
-        for (int i = ptid + kMaxItems * kGProdThreads; i < NR * C; i += kGProdThreads) {     // wide inputs: generic tail
-          const int r = i / C, c = i - r * C;
-          eval_item(rows, xs, r * 4 * C + c, (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16, frac);
+        int r = r_first, c = c_first;
+#pragma unroll 1
+        while (r < NR) {
+          const float* q0 = rows + r * 4 * C + c;
+          float inner = 0.5f * q0[2 * C] + __fdiv_rn(q0[3 * C] * frac, 3.0f);
+          inner = q0[C] + inner * frac;
+          const float x = q0[0] + inner * frac;
+          __half hi, lo;
+          split_f16(x, hi, lo);
+          if (fabsf(x) > 65504.f) *p.status = 1;
+          uint8_t* dst = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+          *reinterpret_cast<__half*>(dst) = hi;
+          *reinterpret_cast<__half*>(dst + (N / 8) * 128) = lo;
+          r += r_inc; c += c_inc;
+          if (c >= C) { c -= C; ++r; }
         }
         interval_ahead = interval_next;
         frac_cur = frac_next;
@@ -466,42 +478,52 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       coef[mt] = t.coef_scalar;
       if (t.coef_src == CO_IMG && a) coef[mt] = p.vec[p.coef_vec + f];
     }
+    // Global rows of this CTA start at gb0; Philox yields 4 normals for the aligned row quad gb >> 2, so the NR
+    // rows span nq quads.  One quad per iteration of a NOT unrolled loop (I-cache).
+    const unsigned long long gb0 = p.row_offset + (unsigned long long)row0;
+    const int lane0 = (int)(gb0 & 3ull);
+    const int nq = (lane0 + NR + 3) >> 2;
     for (int s = 0; s < p.S; ++s) {
       const snsde_step st = p.steps[s];
       uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
       float* sdw = reinterpret_cast<float*>(slot);
-      float dwv[MT][NR], v1[MT];
+      float v1[MT];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const int f = h + 128 * mt;
-        if (f >= H) continue;
         v1[mt] = coef[mt];
+        if (f >= H) continue;
         if (nets > 1) v1[mt] = fmaf(st.cos_t0, ncos[mt], fmaf(st.sin_t0, nsin[mt], n0[mt]));
         else if (t.coef_src == CO_VBUF) v1[mt] = p.a_tab[(size_t)s * H + f];
-        if (p.dW != nullptr) {
-#pragma unroll
-          for (int r = 0; r < NR; ++r) dwv[mt][r] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + f];
-        } else {
-          float nrm[4];
-#pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            const unsigned long long gb = p.row_offset + (unsigned long long)(row0 + r);
-            if (r == 0 || (gb & 3ull) == 0ull) philox_normals4(p.seed, (uint32_t)f, (uint32_t)(gb >> 2), (uint32_t)s, nrm);
-            dwv[mt][r] = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), st.sqrt_h);
-          }
-        }
       }
       StepInfo si;
       si.h = st.h; si.t0 = st.t0; si.n_emits = st.emit_end - st.emit_begin; si.emit_begin = st.emit_begin;
       si.first.slot = 0; si.first.w_prev = 0.f; si.first.w_curr = 0.f;
       if (h == 0 && si.n_emits > 0) si.first = p.emits[st.emit_begin];
       if (s >= 2) mbar_wait_relaxed(bar_pempty + 8 * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int f = h + 128 * mt;
+        if (f >= H) continue;
+        if (p.dW != nullptr) {
+#pragma unroll 4
+          for (int r = 0; r < NR; ++r) sdw[r * HP + f] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + f];
+        } else {
+#pragma unroll 1
+          for (int q = 0; q < nq; ++q) {
+            float nrm[4];
+            philox_normals4(p.seed, (uint32_t)f, (uint32_t)((gb0 >> 2) + (unsigned long long)q), (uint32_t)s, nrm);
+            const int rq = q * 4 - lane0;               // CTA-local row of the quad's first normal
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if ((unsigned)(rq + k) < (unsigned)NR) sdw[(rq + k) * HP + f] = __fmul_rn(nrm[k], st.sqrt_h);
+          }
+        }
+      }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const int f = h + 128 * mt;
         if (f >= H) continue;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) sdw[r * HP + f] = dwv[mt][r];
         sdw[NR * HP + f] = fmaf(st.cos_t0, ccos[mt], fmaf(st.sin_t0, csin[mt], c0[mt]));
         sdw[(NR + 1) * HP + f] = v1[mt];
       }

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(512) klike_kernel(int nk, int DH, int DL, int 
       const long long tc = clock64();
       issue += tb - ta; total += tc - ta;
     }
-    if (lane_id() == 0) { cycles[0] = issue / reps; cycles[1] = total / reps; }
+    if (lane_id() == 0 && blockIdx.x == 0) { cycles[0] = issue / reps; cycles[1] = total / reps; }
   } else if (warp >= 4 && warp < 4 + nwait) {
     // bystander "epilogue" warps: wait for the commit, (mode 1: read 8 accumulator columns, rewrite a B element), hand over
     for (int rep = 0; rep < reps; ++rep) {
@@ -307,14 +307,14 @@ __global__ void __launch_bounds__(512) klike_kernel(int nk, int DH, int DL, int 
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
-static void klike(int nk, int DH, int DL, int AH, int AL, int nwait = 0, int mode = 0) {
+static void klike(int nk, int DH, int DL, int AH, int AL, int nwait = 0, int mode = 0, int grid = 1) {
   long long* dC; cudaMalloc(&dC, 16);
   const size_t smem = 16 * (4 * 128 + 16) + 64;
-  klike_kernel<<<1, 128 + 32 * nwait, smem>>>(nk, DH, DL, AH, AL, 200, dC, nwait, mode);
+  klike_kernel<<<grid, 128 + 32 * nwait, smem>>>(nk, DH, DL, AH, AL, 2000, dC, nwait, mode);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("  CUDA error: %s\n", cudaGetErrorString(e)); exit(2); }
   long long c[2]; cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost);
-  printf("klike nk=%d D(hi)=%d D(lo)=%d A(hi)=%d A(lo)=%d waiters=%d mode=%d: issue %lld, issue->complete %lld cycles per phase of %d MMAs\n", nk, DH, DL, AH, AL, nwait, mode, c[0], c[1], 2 * nk);
+  printf("klike grid=%d nk=%d D(hi)=%d D(lo)=%d A(hi)=%d A(lo)=%d waiters=%d mode=%d: issue %lld, issue->complete %lld cycles per phase of %d MMAs\n", grid, nk, DH, DL, AH, AL, nwait, mode, c[0], c[1], 2 * nk);
   cudaFree(dC);
 }
 
@@ -371,9 +371,8 @@ static double run(int N, int K, bool swap_desc, uint32_t b_pad, int iters, doubl
 int main(int argc, char** argv) {
   srand(1);
   if (argc > 1) {
-    klike(8, 48, 80, 96, 160);
-    klike(8, 48, 80, 96, 160, 1, 0); klike(8, 48, 80, 96, 160, 4, 0); klike(8, 48, 80, 96, 160, 8, 0); klike(8, 48, 80, 96, 160, 12, 0);
-    klike(8, 48, 80, 96, 160, 4, 1); klike(8, 48, 80, 96, 160, 8, 1); klike(8, 48, 80, 96, 160, 12, 1);
+    for (int g : {1, 2, 4, 37, 74, 128, 148, 296}) klike(8, 48, 80, 96, 160, 8, 1, g);
+    for (int g : {1, 148}) klike(8, 48, 80, 96, 160, 0, 0, g);
     return 0;
   }
   for (g_a_tmem = 0; g_a_tmem < 2; ++g_a_tmem) {
