@@ -244,10 +244,13 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--rows", type=int, default=None, help="rows per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver-steps", type=int, default=None, help="override the workload's S (launch-overhead sweeps)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.rows:
         w["B"] = args.rows
+    if args.solver_steps:
+        w["S"] = args.solver_steps
     if args.impl == "reference":
         return run_reference_arm(args, w)
     args.warmup = max(args.warmup, 3)

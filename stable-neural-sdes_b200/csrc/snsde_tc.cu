@@ -94,43 +94,65 @@ __host__ __device__ inline TcSmem tc_smem_layout(int wimg_bytes, int H, int C, i
 // TSH / TSL: the hi / lo weight image is resident in TMEM (a_hi / a_lo is then a TMEM address and the MMA takes
 // the TS form).  Measured on B200 (tests/cuda/umma_probe.cu, M=128 K=16): an SS-form MMA costs >= 39 cycles
 // whatever N <= 32 is (it re-reads the 4 KB A tile from shared memory), a TS-form one 11 (N=16) / 17 (N=32).
-template <int N, int CH>
-__device__ __forceinline__ void issue_segment(bool leader, int ts, uint32_t a_hi, uint32_t a_lo, uint32_t b_base, int nk,
-                                              uint32_t lbo_b, uint32_t d_tmem, bool fresh) {
+// The operands of one segment, computed BEFORE the issuer waits for the segment's inputs: the descriptor and
+// address arithmetic (~25 dependent uniform-datapath instructions plus indexed constant loads) used to sit between
+// the wake-up and the first MMA, i.e. on the critical path of every layer.
+struct SegOps {
+  int ts, nk;
+  uint32_t a_hi, a_lo, d;
+  uint64_t db, da_hi, da_lo;
+  uint32_t acc0;
+};
+__device__ __forceinline__ SegOps seg_ops(int ts, uint32_t a_hi, uint32_t a_lo, uint32_t b_base, int nk, uint32_t lbo_b,
+                                          uint32_t d_tmem, bool fresh) {
+  SegOps o;
+  o.ts = ts; o.nk = nk; o.a_hi = a_hi; o.a_lo = a_lo; o.d = d_tmem;
+  o.db = umma_smem_desc(b_base, lbo_b, 128);
+  o.da_hi = umma_smem_desc(a_hi, kALbo, kASbo);        // only meaningful for an SS-form image
+  o.da_lo = umma_smem_desc(a_lo, kALbo, kASbo);
+  o.acc0 = fresh ? 0u : 1u;
+  return o;
+}
+
+// All MMAs of one operand segment (executed warp-uniformly; `leader` is the one issuing lane).
+// nk (16-wide K chunks) is a multiple of CH; chunk j feeds chain j % CH, so the chain index is a compile-time
+// constant inside the unrolled body.  acc0 = 0: the region holds no partial sums yet (first segment of a layer).
+// ts bit 0 / 1: the hi / lo weight image is resident in TMEM (a_hi / a_lo is then a TMEM address and the MMA takes
+// the TS form).  Measured on B200 (tests/cuda/umma_probe.cu, M=128 K=16): an SS-form MMA costs >= 39 cycles
+// whatever N <= 32 is (it re-reads the 4 KB A tile from shared memory), a TS-form one 11 (N=16) / 17 (N=32).
+template <int N, int CH, int NK>
+__device__ __forceinline__ void issue_ts_unrolled(bool leader, const SegOps& o, uint32_t lbo_b) {
   constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * N), idesc1 = umma_idesc_f16(128, N);
-  uint64_t db = umma_smem_desc(b_base, lbo_b, 128);
-  const uint64_t a_step = (uint64_t)((2 * kALbo) >> 4), b_step = (uint64_t)((2 * lbo_b) >> 4);
-  uint32_t acc = fresh ? 0u : 1u;
-  if (ts == 3) {                                       // both images in TMEM: the hot loop
-#pragma unroll 2
-    for (int kb = 0; kb < nk; kb += CH) {
+  const uint64_t b_step = (uint64_t)((2 * lbo_b) >> 4);
+  if (leader) {
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        if (leader) {
-          umma_f16_ts(d_tmem + AccRegion<N, CH>::a(c), a_hi, db, idesc2, acc);
-          umma_f16_ts(d_tmem + AccRegion<N, CH>::b(c), a_lo, db, idesc1, acc);
-        }
-        a_hi += 8; a_lo += 8;                          // 8 TMEM columns = 16 fp16 of K
-        db += b_step;
-      }
-      acc = 1u;
+    for (int kb = 0; kb < NK; ++kb) {
+      const uint32_t acc = kb < CH ? o.acc0 : 1u;
+      umma_f16_ts(o.d + AccRegion<N, CH>::a(kb % CH), o.a_hi + 8 * kb, o.db + b_step * kb, idesc2, acc);
+      umma_f16_ts(o.d + AccRegion<N, CH>::b(kb % CH), o.a_lo + 8 * kb, o.db + b_step * kb, idesc1, acc);
     }
-    return;
   }
-  uint64_t da_hi = umma_smem_desc(a_hi, kALbo, kASbo);  // only meaningful for an SS-form image
-  uint64_t da_lo = umma_smem_desc(a_lo, kALbo, kASbo);
-  const bool tsh = (ts & 1) != 0, tsl = (ts & 2) != 0;  // warp-uniform
+}
+template <int N, int CH>
+__device__ __forceinline__ void issue_segment(bool leader, const SegOps& o, uint32_t lbo_b) {
+  constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * N), idesc1 = umma_idesc_f16(128, N);
+  const uint64_t a_step = (uint64_t)((2 * kALbo) >> 4), b_step = (uint64_t)((2 * lbo_b) >> 4);
+  if (o.ts == 3 && o.nk == 8) { issue_ts_unrolled<N, CH, 8>(leader, o, lbo_b); return; }     // H = 128
+  if (o.ts == 3 && o.nk == 4) { issue_ts_unrolled<N, CH, 4>(leader, o, lbo_b); return; }     // H = 64, C <= 64
+  uint32_t a_hi = o.a_hi, a_lo = o.a_lo, acc = o.acc0;
+  uint64_t db = o.db, da_hi = o.da_hi, da_lo = o.da_lo;
+  const bool tsh = (o.ts & 1) != 0, tsl = (o.ts & 2) != 0;  // warp-uniform
 #pragma unroll 1
-  for (int kb = 0; kb < nk; kb += CH) {
+  for (int kb = 0; kb < o.nk; kb += CH) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       if (leader) {
-        if (tsh) umma_f16_ts(d_tmem + AccRegion<N, CH>::a(c), a_hi, db, idesc2, acc);
-        else umma_f16(d_tmem + AccRegion<N, CH>::a(c), da_hi, db, idesc2, acc);
-        if (tsl) umma_f16_ts(d_tmem + AccRegion<N, CH>::b(c), a_lo, db, idesc1, acc);
-        else umma_f16(d_tmem + AccRegion<N, CH>::b(c), da_lo, db, idesc1, acc);
+        if (tsh) umma_f16_ts(o.d + AccRegion<N, CH>::a(c), a_hi, db, idesc2, acc);
+        else umma_f16(o.d + AccRegion<N, CH>::a(c), da_hi, db, idesc2, acc);
+        if (tsl) umma_f16_ts(o.d + AccRegion<N, CH>::b(c), a_lo, db, idesc1, acc);
+        else umma_f16(o.d + AccRegion<N, CH>::b(c), da_lo, db, idesc1, acc);
       }
-      a_hi += 8; a_lo += 8;
+      a_hi += 8; a_lo += 8;                              // 8 TMEM columns = 16 fp16 of K
       da_hi += a_step; da_lo += a_step;
       db += b_step;
     }
@@ -320,7 +342,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       const StepInfo si = *reinterpret_cast<const StepInfo*>(slot + (NR + 2) * 512);
       const float add0 = sdw[NR * 128 + h];
       const float cf = sdw[(NR + 1) * 128 + h];
-      prepare_state(cf, si.t0);                       // in the shadow of the layer-0 MMAs
       TC_TRACE(tid == 0, s, EV_EPI_PREPARED);
       for (int l = 0; l < NL; ++l) {
         mbar_wait(bar_acc, pacc);
@@ -402,6 +423,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         }
         hand_over();
         TC_TRACE(tid == 0 && l < 2, s, l == 0 ? EV_EPI_DONE0 : EV_EPI_DONE1);
+        // diffusion / tanh of the current state for this step's update: in the shadow of the layer-1 MMAs (the
+        // layer-0 window is already filled by the outputs of the previous step)
+        if (l == 0) prepare_state(cf, si.t0);
       }
       // ---- in the shadow of the next step's layer-0 MMAs ----
       __syncwarp();
@@ -421,65 +445,128 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     const bool has_x = p.uses_control != 0;
     uint32_t pin = 0, xphase = 0;
     int xslot = 0;
-    for (int s = -1; s < p.S; ++s) {
-      for (int seg = (s < 0 ? NL : 0); seg <= NL; ++seg) {
-        const bool isx = seg == NL;
-        if (isx && !(has_x && s + 1 < p.S)) continue;
-        int ts, nk;
-        uint32_t h_hi, h_lo, b_addr, d, commit_bar;
-        bool fresh;
-        if (isx) {
-          mbar_wait(bar_xfull + 8 * xslot, xphase);
-          ts = p.x_ts; h_hi = p.hx_hi; h_lo = p.hx_lo; nk = Cpad / 16;
-          b_addr = x_base + xslot * L.x_slot_bytes; d = tmem + dcol(0); fresh = true;
-          commit_bar = bar_xempty + 8 * xslot;
-          if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
-        } else {
-          mbar_wait(bar_in, pin);
-          pin ^= 1;
-          ts = p.layer[seg].ts; h_hi = p.layer[seg].h_hi; h_lo = p.layer[seg].h_lo; nk = p.layer[seg].K / 16;
-          b_addr = b_base; d = tmem + dcol(seg); fresh = !(seg == 0 && has_x);
-          commit_bar = bar_acc;
+    auto layer_ops = [&](int l) {
+      const int ts = p.layer[l].ts;
+      return seg_ops(ts, ((ts & 1) ? tmem : w_base) + p.layer[l].h_hi, ((ts & 2) ? tmem : w_base) + p.layer[l].h_lo,
+                     b_base, p.layer[l].K / 16, L.lbo_b, tmem + dcol(l), !(l == 0 && has_x));
+    };
+    auto x_ops = [&](int slot) {
+      const int ts = p.x_ts;
+      return seg_ops(ts, ((ts & 1) ? tmem : w_base) + p.hx_hi, ((ts & 2) ? tmem : w_base) + p.hx_lo,
+                     x_base + slot * L.x_slot_bytes, Cpad / 16, L.lbo_b, tmem + dcol(0), true);
+    };
+    auto run_segment = [&](const SegOps& o, uint32_t wait_bar, uint32_t wait_par, uint32_t commit_bar, int s = -1, int ev = -1) {
+      mbar_wait(wait_bar, wait_par);
+      tc_fence_after();
+      TC_TRACE(lane == 0 && ev >= 0, s, ev);
+      issue_segment<N, CH>(leader, o, L.lbo_b);
+      if (leader) umma_commit(commit_bar);
+      __syncwarp();
+    };
+    if (NL == 2) {
+      // One hidden layer (every named model at its headline configuration): the operands of the three segments of a
+      // step live in uniform registers for the whole kernel, so nothing but the MMAs follows a wake-up.  (Computing
+      // them per segment - indexed constant loads plus ~25 dependent uniform-datapath instructions - cost ~350
+      // cycles per segment on the critical path.)
+      const SegOps o0 = layer_ops(0), o1 = layer_ops(1);
+      const SegOps ox = x_ops(0);
+      const uint64_t x_slot_desc = (uint64_t)(L.x_slot_bytes >> 4);
+      for (int s = -1; s < p.S; ++s) {
+        if (s >= 0) {
+          run_segment(o0, bar_in, pin, bar_acc, s, EV_MMA_WAKE0);
+          TC_TRACE(lane == 0, s, EV_MMA_COMMIT0);
+          run_segment(o1, bar_in, pin ^ 1, bar_acc, s, EV_MMA_WAKE1);
+          TC_TRACE(lane == 0, s, EV_MMA_COMMIT1);
         }
-        tc_fence_after();
-        TC_TRACE(lane == 0 && seg < 2, s, seg == 0 ? EV_MMA_WAKE0 : EV_MMA_WAKE1);
-        issue_segment<N, CH>(leader, ts, ((ts & 1) ? tmem : w_base) + h_hi, ((ts & 2) ? tmem : w_base) + h_lo, b_addr, nk,
-                             L.lbo_b, d, fresh);
-        if (leader) umma_commit(commit_bar);
-        __syncwarp();
-        TC_TRACE(lane == 0 && (seg < 2 || isx), s, isx ? EV_MMA_X_DONE : (seg == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1));
+        if (has_x && s + 1 < p.S) {
+          SegOps o = ox;
+          o.db += x_slot_desc * (uint64_t)xslot;
+          run_segment(o, bar_xfull + 8 * xslot, xphase, bar_xempty + 8 * xslot);
+          if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
+          TC_TRACE(lane == 0 && s >= 0, s, EV_MMA_X_DONE);
+        }
+      }
+    } else {
+      for (int s = -1; s < p.S; ++s) {
+        for (int seg = (s < 0 ? NL : 0); seg <= NL; ++seg) {
+          const bool isx = seg == NL;
+          if (isx && !(has_x && s + 1 < p.S)) continue;
+          // operands first (independent of the data we are about to wait for), then the wait
+          if (isx) {
+            const SegOps o = x_ops(xslot);
+            asm volatile("" ::"r"(o.ts), "r"(o.nk), "r"(o.a_hi), "r"(o.a_lo), "r"(o.d), "l"(o.db), "r"(o.acc0));
+            run_segment(o, bar_xfull + 8 * xslot, xphase, bar_xempty + 8 * xslot);
+            if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
+          } else {
+            const SegOps o = layer_ops(seg);
+            asm volatile("" ::"r"(o.ts), "r"(o.nk), "r"(o.a_hi), "r"(o.a_lo), "r"(o.d), "l"(o.db), "r"(o.acc0));
+            run_segment(o, bar_in, pin, bar_acc);
+            pin ^= 1;
+          }
+        }
       }
     }
   } else if (warp < kPrepWarp0) {
     // =========================== CONTROL PRODUCER ===========================
+    // This role has to deliver one X(t) operand per solver step; measured (clock64 trace) at 3500 cycles per
+    // iteration it was THE bottleneck of the kernel once the MMA phases got short: 840 cycles for 8 serialized
+    // bulk-copy issues from one warp, 2 x 320 for the barrier tests, 1760 for three dependent evaluate chains.
+    // Now: the copies are spread over the three warps, the items of a thread are tabulated once and evaluated
+    // interleaved (ILP across up to 4 items, one shared body), and x/3 uses the FMA-corrected reciprocal product
+    // (correctly rounded like the division it replaces, no subroutine call).
     if (p.uses_control) {
       const int ptid = tid - 32 * kProdWarp0;            // 0..95
       const int pwarp = warp - kProdWarp0;
       const uint32_t row_bytes = 16u * C;
-      // Step metadata is loaded one iteration ahead (an exposed L2 round trip per step made this role the
-      // bottleneck of the whole kernel), and each thread's (row, channel) items are tabulated once.
-      auto fetch = [&](int s, int interval) {           // spline rows of step s -> staging slot (first producer warp only)
-        if (pwarp != 0 || s >= p.S) return;
+      const int rows_per_warp = (NR + kProdWarps - 1) / kProdWarps;
+      auto fetch = [&](int s, int interval) {           // spline rows of step s -> staging slot
+        if (s >= p.S) return;
         const int stg = s % p.nstg;
         const uint32_t bar = bar_cfull + 8 * stg;
-        if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * NR);
-        __syncwarp();
-        for (int r = lane; r < NR; r += 32) {
+        const int r = pwarp * rows_per_warp + lane;
+        if (lane < rows_per_warp && r < NR) {
           const int b = min(row0 + r, p.B - 1);
           const float* src = p.coeffs + (size_t)b * p.coeff_row_stride + (size_t)interval * 4 * C;
           bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
         }
       };
-      // (row, channel) items of this thread: i = ptid, ptid + 96, ...; the pair is advanced incrementally
-      // (no division in the loop) and the loop is NOT unrolled - compact code beats ILP here (I-cache).
-      const int r_first = ptid / C, c_first = ptid - r_first * C;
-      const int r_inc = kProdThreads / C, c_inc = kProdThreads - r_inc * C;
+      auto expect = [&](int s) {                        // one thread announces the bytes of step s (before any copy of it)
+        if (ptid == 0 && s < p.S) mbar_arrive_expect_tx(bar_cfull + 8 * (s % p.nstg), row_bytes * NR);
+      };
+      constexpr int kItems = 4;                         // items evaluated together; more (wide inputs) loop around
+      int item_src[kItems], item_dst[kItems];
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) {
+        const int i = ptid + k * kProdThreads;
+        const int r = i / C, c = i - r * C;
+        item_src[k] = (i < NR * C) ? r * 4 * C + c : -1;
+        item_dst[k] = (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+      }
+      auto eval_item = [&](const float* rows, uint8_t* xs, int src, int dst, float frac) {
+        const float* q0 = rows + src;
+        const float v = q0[3 * C] * frac;
+        float q = v * 0.333333343f;                     // v / 3, correctly rounded: Newton step on the residual
+        q = fmaf(fmaf(-3.0f, q, v), 0.333333343f, q);
+        float inner = 0.5f * q0[2 * C] + q;
+        inner = q0[C] + inner * frac;
+        const float x = q0[0] + inner * frac;
+        __half hi, lo;
+        split_f16(x, hi, lo);
+        if (fabsf(x) > 65504.f) *p.status = 1;
+        *reinterpret_cast<__half*>(xs + dst) = hi;
+        *reinterpret_cast<__half*>(xs + dst + (N / 8) * 128) = lo;
+      };
 #pragma unroll 1
-      for (int s = 0; s < p.nstg - 1; ++s) fetch(s, s < p.S ? p.steps[s].interval : 0);
+      for (int s = 0; s < p.nstg - 1; ++s) {
+        expect(s);
+        asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads));
+        fetch(s, s < p.S ? p.steps[s].interval : 0);
+      }
       int interval_ahead = (p.nstg - 1 < p.S) ? p.steps[p.nstg - 1].interval : 0;
       float frac_cur = p.S > 0 ? p.steps[0].frac : 0.f;
       for (int s = 0; s < p.S; ++s) {
-        asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads));      // all producer warps are done with step s-1
+        expect(s + p.nstg - 1);
+        asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads));      // all producer warps are done with step s-1; expect_tx is posted
         fetch(s + p.nstg - 1, interval_ahead);
         const int sa = s + p.nstg;
         const int interval_next = sa < p.S ? p.steps[sa].interval : 0;       // consumed next iteration
@@ -490,28 +577,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
-        int r = r_first, c = c_first;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k)
+          if (item_src[k] >= 0) eval_item(rows, xs, item_src[k], item_dst[k], frac);
 #pragma unroll 1
-        while (r < NR) {
-          const float* q0 = rows + r * 4 * C + c;
-          float inner = 0.5f * q0[2 * C] + __fdiv_rn(q0[3 * C] * frac, 3.0f);
-          inner = q0[C] + inner * frac;
-          const float x = q0[0] + inner * frac;
-          __half hi, lo;
-          split_f16(x, hi, lo);
-          if (fabsf(x) > 65504.f) *p.status = 1;
-          uint8_t* dst = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
-          *reinterpret_cast<__half*>(dst) = hi;
-          *reinterpret_cast<__half*>(dst + (N / 8) * 128) = lo;
-          r += r_inc; c += c_inc;
-          if (c >= C) { c -= C; ++r; }
+        for (int i = ptid + kItems * kProdThreads; i < NR * C; i += kProdThreads) {      // wide inputs / many rows
+          const int r = i / C, c = i - r * C;
+          eval_item(rows, xs, r * 4 * C + c, (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16, frac);
         }
         interval_ahead = interval_next;
         frac_cur = frac_next;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);
-        TC_TRACE(ptid == 0, s, EV_PROD_DONE);
       }
     }
   } else {
@@ -563,7 +641,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       if (h == 0) *reinterpret_cast<StepInfo*>(slot + (NR + 2) * 512) = si;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pfull + 8 * (s & 1));
-      TC_TRACE(h == 0, s, EV_PREP_DONE);
+
     }
   }
 
