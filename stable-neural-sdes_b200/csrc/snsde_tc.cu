@@ -53,7 +53,7 @@ namespace snsde {
 
 using namespace ptx;
 
-constexpr int kEpiPerQuad = 2;                     // epilogue warps per TMEM lane quadrant, each owning NR/kEpiPerQuad rows
+constexpr int kEpiPerQuad = 4;                     // epilogue warps per TMEM lane quadrant, each owning NR/kEpiPerQuad rows
 constexpr int kEpiWarps = 4 * kEpiPerQuad;
 constexpr int kMmaWarp = kEpiWarps;
 constexpr int kProdWarp0 = kMmaWarp + 1, kPrepWarp0 = kProdWarp0 + 3;
@@ -129,7 +129,7 @@ __device__ __forceinline__ void issue_ts_unrolled(bool leader, const SegOps& o, 
     for (int kb = 0; kb < NK; ++kb) {
       const uint32_t acc = kb < CH ? o.acc0 : 1u;
       umma_f16_ts(o.d + AccRegion<N, CH>::a(kb % CH), o.a_hi + 8 * kb, o.db + b_step * kb, idesc2, acc);
-      umma_f16_ts(o.d + AccRegion<N, CH>::b(kb % CH), o.a_lo + 8 * kb, o.db + b_step * kb, idesc1, acc);
+      umma_f16_ts(o.d + AccRegion<N, CH>::b(kb % CH), o.a_lo + 8 * kb, o.db + b_step * kb, idesc1, 1u);   // corr columns: the hi product just initialised them
     }
   }
 }
@@ -149,8 +149,8 @@ __device__ __forceinline__ void issue_segment(bool leader, const SegOps& o, uint
       if (leader) {
         if (tsh) umma_f16_ts(o.d + AccRegion<N, CH>::a(c), a_hi, db, idesc2, acc);
         else umma_f16(o.d + AccRegion<N, CH>::a(c), da_hi, db, idesc2, acc);
-        if (tsl) umma_f16_ts(o.d + AccRegion<N, CH>::b(c), a_lo, db, idesc1, acc);
-        else umma_f16(o.d + AccRegion<N, CH>::b(c), da_lo, db, idesc1, acc);
+        if (tsl) umma_f16_ts(o.d + AccRegion<N, CH>::b(c), a_lo, db, idesc1, 1u);     // corr columns: always accumulate
+        else umma_f16(o.d + AccRegion<N, CH>::b(c), da_lo, db, idesc1, 1u);
       }
       a_hi += 8; a_lo += 8;                              // 8 TMEM columns = 16 fp16 of K
       da_hi += a_step; da_lo += a_step;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void issue_segment(bool leader, const SegOps& o, uint
 template <int NR, int DIFF, int CH>
 __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams p) {
   constexpr int N = NR < 16 ? 16 : NR;              // MMA N (rows padded to >= 16)
-  using Acc = AccRegion<N, CH>;                     // CH accumulator chains per product; 2 regions of CH*3N columns
+  using Acc = AccRegion<N, CH>;                     // CH accumulator chains per product; 2 regions of CH*2N columns
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, C = p.C, Cpad = p.Cpad, NL = p.NL;
@@ -352,20 +352,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         const uint32_t dreg = tmem + lane_base + dcol(l) + rbase;
 #pragma unroll
         for (int c = 0; c < RT; c += LW) {
-          float m8[CH][LW], a8[CH][LW], b8[CH][LW];
+          float m8[CH][LW], a8[CH][LW];
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch) {
             tmem_ldw<LW>(dreg + Acc::a(ch) + c, m8[ch]);
             tmem_ldw<LW>(dreg + Acc::a(ch) + N + c, a8[ch]);
-            tmem_ldw<LW>(dreg + Acc::b(ch) + c, b8[ch]);
           }
           tmem_ld_wait();
           TC_TRACE(tid == 0 && l < 2 && c == 0, s, l == 0 ? EV_EPI_LD0 : EV_EPI_LD1);
 #pragma unroll
           for (int i = 0; i < LW; ++i) {
-            float m = m8[0][i], cc = a8[0][i] + b8[0][i];
+            float m = m8[0][i], cc = a8[0][i];
 #pragma unroll
-            for (int ch = 1; ch < CH; ++ch) { m += m8[ch][i]; cc += a8[ch][i] + b8[ch][i]; }
+            for (int ch = 1; ch < CH; ++ch) { m += m8[ch][i]; cc += a8[ch][i]; }
             vm[c + i] = m; vc[c + i] = cc;
           }
         }
@@ -685,7 +684,7 @@ static bool is_emb_opt(int io) { return io == 2 || io == 4 || io == 6; }
 // they last (layers first - they are on the critical path - then the control segment), shared memory otherwise.
 // Fills p.img / the layers' handles / p.tmem_cols and returns the bytes of the shared-memory weight area.
 static int tc_place(TcParams& p, int N, int CH, bool use_tmem) {
-  int col = 2 * CH * 3 * N, soff = 0;
+  int col = 2 * CH * 2 * N, soff = 0;
   p.n_img = 0;
   auto place = [&](int g_off, int K, int& handle, int& ts, int bit) {
     TcImg im;

@@ -40,16 +40,19 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 
 __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-// TMEM accumulator region of one layer.  Dependent tcgen05.mma's into the SAME accumulator are ~84 cycles
-// apart on B200 (measured, tests/cuda/umma_probe.cu) whatever the tile size, so the K chunks of a layer are
-// spread over CH independent chains per product and summed in the epilogue:
-//   [main|corrA] chains  (Whi x [ahi;alo'], 2N columns each) : columns [c*2N, (c+1)*2N),            c < CH
-//   corrB chains         (Wlo' x ahi,        N columns each) : columns [CH*2N + c*N, CH*2N+(c+1)*N)
+// TMEM accumulator region of one layer: per chain c the 2N columns [main | corr] at c*2N.
+//   hi product  Whi x [ahi ; alo']  (N' = 2N)  -> [main | corr]
+//   lo product  Wlo' x ahi          (N)        -> accumulated into the SAME corr columns
+// so the epilogue reads two values per element, not three: the TMEM read port (~64 B/cycle) bounds the
+// accumulator load of a phase (3 x NR columns x 128 lanes x 4 B = 12 KB was ~200 cycles at NR = 8).
+// Back-to-back MMAs into the same columns cost nothing extra on the in-order tensor pipe (measured with
+// tests/cuda/umma_probe.cu: 10.8 cycles per TS-form MMA whether or not consecutive ones share the accumulator).
+// CH > 1 spreads the K chunks over independent chains summed in the epilogue (kept for experiments).
 template <int N, int CH>
 struct AccRegion {
-  static constexpr int kCols = CH * 3 * N;
+  static constexpr int kCols = CH * 2 * N;
   __device__ static constexpr uint32_t a(int c) { return (uint32_t)(c * 2 * N); }
-  __device__ static constexpr uint32_t b(int c) { return (uint32_t)(CH * 2 * N + c * N); }
+  __device__ static constexpr uint32_t b(int c) { return (uint32_t)(c * 2 * N + N); }
 };
 
 }  // namespace snsde

@@ -255,7 +255,7 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
   int CH = 2;
   for (;;) {
     const int N = NR < 16 ? 16 : NR;
-    CH = (2 * nacc * 2 * 3 * N <= 512) ? 2 : 1;
+    CH = (2 * nacc * 2 * 2 * N <= 512) ? 2 : 1;
     // X(t) jobs are always resident; then as many others as fit (in issue order), the rest is streamed
     bool ok = false;
     for (int cfg = 0; cfg < 3 && !ok; ++cfg) {

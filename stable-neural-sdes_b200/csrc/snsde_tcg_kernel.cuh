@@ -135,19 +135,18 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       const uint32_t dreg = tmem + lane_base + (ph == 0 ? 0u : region_cols) + (uint32_t)acc * Acc::kCols + rbase;
 #pragma unroll
       for (int c = 0; c < RT; c += LW) {
-        float m8[CH][LW], a8[CH][LW], b8[CH][LW];
+        float m8[CH][LW], a8[CH][LW];
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) {
           tmem_ldw<LW>(dreg + Acc::a(ch) + c, m8[ch]);
           tmem_ldw<LW>(dreg + Acc::a(ch) + N + c, a8[ch]);
-          tmem_ldw<LW>(dreg + Acc::b(ch) + c, b8[ch]);
         }
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < LW; ++i) {
-          float m = m8[0][i], cc = a8[0][i] + b8[0][i];
+          float m = m8[0][i], cc = a8[0][i];
 #pragma unroll
-          for (int ch = 1; ch < CH; ++ch) { m += m8[ch][i]; cc += a8[ch][i] + b8[ch][i]; }
+          for (int ch = 1; ch < CH; ++ch) { m += m8[ch][i]; cc += a8[ch][i]; }
           vm[c + i] = m; vc[c + i] = cc;
         }
       }
@@ -338,7 +337,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
           for (int c = 0; c < CH; ++c) {
             if (leader) {
               umma_f16(d + Acc::a(c), da, db, idesc2, acc);
-              umma_f16(d + Acc::b(c), da + (4096 >> 4), db, idesc1, acc);
+              umma_f16(d + Acc::b(c), da + (4096 >> 4), db, idesc1, 1u);     // corr columns: the hi product just initialised them
             }
             da += (uint64_t)(kTcgSlotBytes >> 4);
             db += b_step;
@@ -354,7 +353,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
             const uint64_t da = ring_desc0 + (uint64_t)(rslot * (kTcgSlotBytes >> 4));
             if (leader) {
               umma_f16(d + Acc::a(c), da, db, idesc2, acc);
-              umma_f16(d + Acc::b(c), da + (4096 >> 4), db, idesc1, acc);
+              umma_f16(d + Acc::b(c), da + (4096 >> 4), db, idesc1, 1u);     // corr columns: the hi product just initialised them
               umma_commit(bar_rempty + 8 * rslot);
             }
             __syncwarp();
