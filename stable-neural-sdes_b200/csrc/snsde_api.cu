@@ -77,9 +77,6 @@ static int validate(const snsde_model_desc* d) {
       return fail(SNSDE_ERR_BAD_ARG, "Unknown noise_option %d.", d->noise_option);   // neuralsde.py:288
     if ((d->input_option == 0 || is_emb_opt(d->input_option)) && d->hidden != d->hidden_hidden)
       return fail(SNSDE_ERR_BAD_ARG, "input_option %d requires hidden_hidden == hidden (emb is Linear(2H,H), neuralsde.py:154,210)", d->input_option);
-    const int n = d->noise_option;
-    if (d->method == SNSDE_METHOD_MILSTEIN && (n == 14 || n == 15 || n == 18 || n == 19))
-      return fail(SNSDE_ERR_UNSUPPORTED, "milstein with state-network noise_option %d needs a full vjp; not implemented", n);
   }
   const int n_ops = d->family == SNSDE_FAMILY_BENCHMARK ? 6 + d->num_hidden_layers : 6 + 2 * d->num_hidden_layers;
   if (n_ops > kMaxOps) return fail(SNSDE_ERR_UNSUPPORTED, "num_hidden_layers too large");
@@ -234,9 +231,11 @@ static void compile_benchmark(const snsde_model_desc& d, const float* blob, Prog
                         deep ? ACT_RELU : ACT_NONE);
     o.tmode = TM_SINCOS; o.tw_off = ib.add_T(W1, H, H + 2, 0, 2);
     pg.ops[n++] = o;
+    t.vjp_kind = deep ? 2 : 1; t.vjp_w1 = o.w_off; t.vjp_w2 = -1; t.vjp_h1 = BUF_P;
     if (deep) {
       const float* W2 = bc.take((size_t)H * H); const float* b2 = bc.take(H);
       pg.ops[n++] = make_op(BUF_Q, BUF_P, H, H, ib.add_T(W2, H, H, 0, H), ib.add_vec(b2, H), ACT_RELU);
+      t.vjp_w2 = pg.ops[n - 1].w_off;
     }
     t.coef_src = CO_RBUF; t.coef_ref = BUF_Q;
     t.mult = (no == 15 || no == 19) ? MU_Y : MU_ONE;
@@ -347,7 +346,11 @@ int snsde_plan_create(const snsde_model_desc* desc, int device, snsde_plan** out
   p->smem_optin = (int)prop.sharedMemPerBlockOptin;
   const bool force_general = getenv("SNSDE_FORCE_TCG") != nullptr;           // testing aid: general kernel even where the resident one applies
   const bool tc_ok = tc_supported(*desc, prop.major, p->smem_optin) && !force_general;
-  const bool tcg_ok = tcg_supported(*desc, prop.major, p->smem_optin);
+  const int no_ = desc->noise_option;
+  // Milstein through a state-dependent noise network needs the full vjp: implemented in the FMA kernel only
+  const bool net_vjp = desc->family == SNSDE_FAMILY_BENCHMARK && desc->method == SNSDE_METHOD_MILSTEIN &&
+                       (no_ == 14 || no_ == 15 || no_ == 18 || no_ == 19);
+  const bool tcg_ok = tcg_supported(*desc, prop.major, p->smem_optin) && !net_vjp;
   if (desc->precision == SNSDE_PRECISION_TC && !tc_ok && !tcg_ok) {
     delete p;
     return fail(SNSDE_ERR_UNSUPPORTED, "tensor-core path does not support this model/shape/device: %s", tcg_unsupported_reason());

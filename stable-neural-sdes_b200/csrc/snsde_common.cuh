@@ -45,6 +45,12 @@ struct TailOp {
   int bounded;        // g = tanh(sigmoid(theta) * nan_to_num(raw)) (benchmark) vs g = raw (tutorial)
   float s_theta;      // sigmoid(theta)
   int milstein;       // method
+  // Milstein with a state-dependent noise NETWORK (options 14,15,18,19): g_i depends on every y_j, so torchsde's
+  // vjp_y(g; g*(dW^2-h)) is a full transposed product through noise_y.  0: none (diagonal closed form),
+  // 1: q = Linear(H+2,H)([tf,y]);  2: q = relu(Linear(H,H)(relu(Linear(H+2,H)([tf,y])))).   (FMA kernel only)
+  int vjp_kind;
+  int vjp_w1, vjp_w2; // float offsets of the transposed images [in][out] of noise_y.0 (y columns) / noise_y.2
+  int vjp_h1;         // buffer holding relu(noise_y.0(...)) (kind 2)
 };
 
 struct Program {

@@ -70,6 +70,19 @@ __device__ __forceinline__ void dot_accumulate(float (&acc)[ROWS], const float* 
   }
 }
 
+// acc[r] += sum_k src[r][k] * wrow[k]   - the TRANSPOSED product: thread j walks row j of an [in][out] image
+// (contiguous), used by the Milstein vjp through the noise network; read through L1/L2 (a shared-memory copy
+// would be 32-way bank conflicted at this access pattern).
+template <int ROWS>
+__device__ __forceinline__ void dot_rows_T(float (&acc)[ROWS], const float* __restrict__ src, int ld,
+                                           const float* __restrict__ wrow, int K) {
+  for (int k = 0; k < K; ++k) {
+    const float wk = __ldg(wrow + k);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(src[r * ld + k], wk, acc[r]);
+  }
+}
+
 template <int ROWS>
 __device__ __forceinline__ void dense_eval(float (&acc)[ROWS], const DenseOp& op, const FmaParams& p,
                                            const SmemMap& sm, const snsde_step& st, int j) {
@@ -208,8 +221,11 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
     }
 
     // ---- SDE update (torchsde Euler.step / Milstein.step) ----
+    const TailOp& t = pg.tail;
+    const bool net_vjp = t.milstein && t.vjp_kind != 0;       // block-uniform
+    float* const sA = sm.buf(BUF_X);                            // scratch of the vjp (dead since the first ops)
+    float* const sB = sm.buf(BUF_U);
     if (jact) {
-      const TailOp& t = pg.tail;
       float vcoef = t.coef_scalar;
       if (t.coef_src == CO_IMG) vcoef = p.wimg[t.coef_ref + tid];
       else if (t.coef_src == CO_VBUF) vcoef = sm.buf(t.coef_ref)[tid];
@@ -234,11 +250,48 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
         float yn = __fadd_rn(__fadd_rn(y[r], __fmul_rn(d, st.h)), __fmul_rn(g, w));
         if (t.milstein) {
           const float v = __fmul_rn(w, w) - st.h;
-          yn = __fadd_rn(yn, 0.5f * ((g * v) * dgdy));
+          yn = __fadd_rn(yn, 0.5f * ((g * v) * dgdy));          // direct (diagonal) part of d g_j / d y_j
+          if (net_vjp) {
+            // cotangent reaching q_j:  (g v) * tanh' * s_theta * [nan_to_num passes] * d raw / d q  (* relu' for kind 2)
+            const float raw = (t.mult == MU_Y) ? coef * y[r] : coef;
+            float a = (g * v) * ((1.f - g * g) * t.s_theta) * (is_finite_f(raw) ? 1.f : 0.f);
+            if (t.mult == MU_Y) a *= y[r];
+            if (t.vjp_kind == 2 && !(coef > 0.f)) a = 0.f;
+            sA[r * ld + tid] = a;
+          }
         }
         yprev[r] = y[r];
         y[r] = yn;
-        sY[r * ld + tid] = yn;
+        if (!net_vjp) sY[r * ld + tid] = yn;
+      }
+    }
+    if (net_vjp) {
+      // torchsde: + 0.5 * vjp_y(g; g * (dW^2 - h)); the path through noise_y is W1y^T [relu'] W2^T [relu'] a
+      __syncthreads();
+      const float* src = sA;
+      if (t.vjp_kind == 2) {
+        if (jact) {
+          float b[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) b[r] = 0.f;
+          dot_rows_T<R>(b, sA, ld, p.wimg + t.vjp_w2 + (size_t)tid * H, H);
+          const float* h1 = sm.buf(t.vjp_h1);
+#pragma unroll
+          for (int r = 0; r < R; ++r) sB[r * ld + tid] = (h1[r * ld + tid] > 0.f) ? b[r] : 0.f;
+        }
+        __syncthreads();
+        src = sB;
+      }
+      if (jact) {
+        float c[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) c[r] = 0.f;
+        dot_rows_T<R>(c, src, ld, p.wimg + t.vjp_w1 + (size_t)tid * H, H);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          y[r] = __fadd_rn(y[r], 0.5f * c[r]);
+          sY[r * ld + tid] = y[r];
+        }
       }
     }
     for (int e = st.emit_begin; e < st.emit_end; ++e) emit(p.emits[e]);

@@ -398,33 +398,60 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     }
   } else if (warp < kGStreamWarp) {
     // =========================== CONTROL PRODUCER ===========================
+    // Same scheme as the resident kernel (snsde_tc.cu): copies spread over the producer warps, the items of a thread
+    // tabulated once and evaluated interleaved, x/3 by the FMA-corrected reciprocal product.
     if (p.uses_control) {
       const int ptid = tid - 32 * kGProdWarp0;
       const int pwarp = warp - kGProdWarp0;
       const uint32_t row_bytes = 16u * C;
-      // Step metadata is loaded one iteration ahead (an exposed L2 round trip per step made this role the
-      // bottleneck of the whole kernel), and each thread's (row, channel) items are tabulated once.
-      auto fetch = [&](int s, int interval) {           // spline rows of step s -> staging slot (first producer warp only)
-        if (pwarp != 0 || s >= p.S) return;
+      const int rows_per_warp = (NR + kGProdWarps - 1) / kGProdWarps;
+      auto fetch = [&](int s, int interval) {           // spline rows of step s -> staging slot
+        if (s >= p.S) return;
         const int stg = s % p.nstg;
         const uint32_t bar = bar_cfull + 8 * stg;
-        if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * NR);
-        __syncwarp();
-        for (int r = lane; r < NR; r += 32) {
+        const int r = pwarp * rows_per_warp + lane;
+        if (lane < rows_per_warp && r < NR) {
           const int b = min(row0 + r, p.B - 1);
           const float* src = p.coeffs + (size_t)b * p.coeff_row_stride + (size_t)interval * 4 * C;
           bulk_g2s(smem_u32(smem + L.stg + stg * L.stg_bytes + r * row_bytes), src, row_bytes, bar);
         }
       };
-      // (row, channel) items of this thread: i = ptid, ptid + 64, ...; the pair is advanced incrementally
-      // (no division in the loop) and the loop is NOT unrolled - compact code beats ILP here (I-cache).
-      const int r_first = ptid / C, c_first = ptid - r_first * C;
-      const int r_inc = kGProdThreads / C, c_inc = kGProdThreads - r_inc * C;
+      auto expect = [&](int s) {                        // one thread announces the bytes of step s
+        if (ptid == 0 && s < p.S) mbar_arrive_expect_tx(bar_cfull + 8 * (s % p.nstg), row_bytes * NR);
+      };
+      constexpr int kItems = 4;
+      int item_src[kItems], item_dst[kItems];
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) {
+        const int i = ptid + k * kGProdThreads;
+        const int r = i / C, c = i - r * C;
+        item_src[k] = (i < NR * C) ? r * 4 * C + c : -1;
+        item_dst[k] = (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
+      }
+      auto eval_item = [&](const float* rows, uint8_t* xs, int src, int dst, float frac) {
+        const float* q0 = rows + src;
+        const float v = q0[3 * C] * frac;
+        float q = v * 0.333333343f;                     // v / 3, correctly rounded: Newton step on the residual
+        q = fmaf(fmaf(-3.0f, q, v), 0.333333343f, q);
+        float inner = 0.5f * q0[2 * C] + q;
+        inner = q0[C] + inner * frac;
+        const float x = q0[0] + inner * frac;
+        __half hi, lo;
+        split_f16(x, hi, lo);
+        if (fabsf(x) > 65504.f) *p.status = 1;
+        *reinterpret_cast<__half*>(xs + dst) = hi;
+        *reinterpret_cast<__half*>(xs + dst + (N / 8) * 128) = lo;
+      };
 #pragma unroll 1
-      for (int s = 0; s < p.nstg - 1; ++s) fetch(s, s < p.S ? p.steps[s].interval : 0);
+      for (int s = 0; s < p.nstg - 1; ++s) {
+        expect(s);
+        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads));
+        fetch(s, s < p.S ? p.steps[s].interval : 0);
+      }
       int interval_ahead = (p.nstg - 1 < p.S) ? p.steps[p.nstg - 1].interval : 0;
       float frac_cur = p.S > 0 ? p.steps[0].frac : 0.f;
       for (int s = 0; s < p.S; ++s) {
+        expect(s + p.nstg - 1);
         asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads));      // all producer warps are done with step s-1
         fetch(s + p.nstg - 1, interval_ahead);
         const int sa = s + p.nstg;
@@ -436,21 +463,13 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
-        int r = r_first, c = c_first;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k)
+          if (item_src[k] >= 0) eval_item(rows, xs, item_src[k], item_dst[k], frac);
 #pragma unroll 1
-        while (r < NR) {
-          const float* q0 = rows + r * 4 * C + c;
-          float inner = 0.5f * q0[2 * C] + __fdiv_rn(q0[3 * C] * frac, 3.0f);
-          inner = q0[C] + inner * frac;
-          const float x = q0[0] + inner * frac;
-          __half hi, lo;
-          split_f16(x, hi, lo);
-          if (fabsf(x) > 65504.f) *p.status = 1;
-          uint8_t* dst = xs + (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
-          *reinterpret_cast<__half*>(dst) = hi;
-          *reinterpret_cast<__half*>(dst + (N / 8) * 128) = lo;
-          r += r_inc; c += c_inc;
-          if (c >= C) { c -= C; ++r; }
+        for (int i = ptid + kItems * kGProdThreads; i < NR * C; i += kGProdThreads) {
+          const int r = i / C, c = i - r * C;
+          eval_item(rows, xs, r * 4 * C + c, (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16, frac);
         }
         interval_ahead = interval_next;
         frac_cur = frac_next;

@@ -103,7 +103,9 @@ def test_euler_trajectories_named_models(name, io, no, H, C, L, B, dev):
 
 
 @pytest.mark.parametrize("io,no", [(6, 17), (4, 17), (2, 16), (1, 3), (3, 6), (5, 8), (1, 9), (3, 10), (5, 11), (4, 13),
-                                   (1, 7), (0, 12), (1, 0), (2, 5)])
+                                   (1, 7), (0, 12), (1, 0), (2, 5),
+                                   # state-dependent noise NETWORKS: full vjp through noise_y (torchsde gdg_prod)
+                                   (3, 18), (1, 19), (4, 14), (6, 15), (0, 19), (2, 18)])
 def test_milstein_vs_autograd_oracle(io, no, dev):
     B, H, C, L, K = 11, 16, 4, 2, 13
     m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, K, seed=no, HH=(24 if io in (1, 3, 5) else None),
