@@ -608,6 +608,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     const unsigned long long gb0 = p.row_offset + (unsigned long long)row0;
     const int lane0 = (int)(gb0 & 3ull);
     const int nq = (lane0 + NR + 3) >> 2;
+    if (t.coef_src == CO_VBUF) asm volatile("griddepcontrol.wait;" ::: "memory");   // a_tab comes from the tables kernel (PDL)
     for (int s = 0; s < p.S; ++s) {
       const snsde_step st = p.steps[s];
       uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
@@ -655,6 +656,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
 __global__ void __launch_bounds__(256) snsde_tc_tables_kernel(const float* __restrict__ vec, TcNoiseNet nn, int H,
                                                               const snsde_step* __restrict__ steps, float* __restrict__ a_tab) {
   __shared__ float h1[256];
+  // programmatic dependent launch: the solve kernel may start its prologue (weights -> TMEM/smem, barriers) now;
+  // it executes griddepcontrol.wait before the first read of a_tab
+  asm volatile("griddepcontrol.launch_dependents;");
   const int s = blockIdx.x, h = threadIdx.x;
   const snsde_step st = steps[s];
   float v = 0.f;
@@ -870,12 +874,19 @@ int tc_set_weights(TcPlan& tc, const snsde_model_desc& d, const Program& pg, con
 }
 
 template <int NR, int DIFF, int CH>
-static cudaError_t tc_launch_one(const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
+static cudaError_t tc_launch_one(const TcParams& p, int grid, size_t smem, cudaStream_t stream, bool pdl) {
+  // pdl: the launch follows the tables kernel - overlap the prologue with it (programmatic dependent launch)
   auto kern = snsde_tc_kernel<NR, DIFF, CH>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kTcThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, int* n_launches) {
@@ -885,6 +896,7 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
   p.row_slot = a.row_slot; p.dW = a.dW; p.seed = a.seed; p.row_offset = a.row_offset; p.out = a.out;
   p.status = a.status;
   *n_launches = 0;
+  bool pdl = false;
   if (tc.noise.kind != 0 && a.S > 0) {
     if (a.S * p.H > tc.atab_cap) {
       cudaFree(tc.d_atab); tc.d_atab = nullptr;
@@ -896,6 +908,7 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     *n_launches += 1;
+    pdl = getenv("SNSDE_NO_PDL") == nullptr;
   }
   p.a_tab = tc.d_atab;
   p.dbg = nullptr;
@@ -931,18 +944,18 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
   // Accumulator chains per product: with the weights in TMEM the MMA phase is short and one chain is best (fewer
   // TMEM loads/adds in the epilogue); two chains stay selectable (SNSDE_TC_CH=2) for experiments.
   switch ((CH == 2 ? 128 : 0) + NR * 2 + (fast_diff ? 1 : 0)) {
-    case 16: e = tc_launch_one<8, 0, 1>(p, grid, L.total, stream); break;
-    case 17: e = tc_launch_one<8, 1, 1>(p, grid, L.total, stream); break;
-    case 32: e = tc_launch_one<16, 0, 1>(p, grid, L.total, stream); break;
-    case 33: e = tc_launch_one<16, 1, 1>(p, grid, L.total, stream); break;
-    case 64: e = tc_launch_one<32, 0, 1>(p, grid, L.total, stream); break;
-    case 65: e = tc_launch_one<32, 1, 1>(p, grid, L.total, stream); break;
-    case 128 + 16: e = tc_launch_one<8, 0, 2>(p, grid, L.total, stream); break;
-    case 128 + 17: e = tc_launch_one<8, 1, 2>(p, grid, L.total, stream); break;
-    case 128 + 32: e = tc_launch_one<16, 0, 2>(p, grid, L.total, stream); break;
-    case 128 + 33: e = tc_launch_one<16, 1, 2>(p, grid, L.total, stream); break;
-    case 128 + 64: e = tc_launch_one<32, 0, 2>(p, grid, L.total, stream); break;
-    default: e = tc_launch_one<32, 1, 2>(p, grid, L.total, stream); break;
+    case 16: e = tc_launch_one<8, 0, 1>(p, grid, L.total, stream, pdl); break;
+    case 17: e = tc_launch_one<8, 1, 1>(p, grid, L.total, stream, pdl); break;
+    case 32: e = tc_launch_one<16, 0, 1>(p, grid, L.total, stream, pdl); break;
+    case 33: e = tc_launch_one<16, 1, 1>(p, grid, L.total, stream, pdl); break;
+    case 64: e = tc_launch_one<32, 0, 1>(p, grid, L.total, stream, pdl); break;
+    case 65: e = tc_launch_one<32, 1, 1>(p, grid, L.total, stream, pdl); break;
+    case 128 + 16: e = tc_launch_one<8, 0, 2>(p, grid, L.total, stream, pdl); break;
+    case 128 + 17: e = tc_launch_one<8, 1, 2>(p, grid, L.total, stream, pdl); break;
+    case 128 + 32: e = tc_launch_one<16, 0, 2>(p, grid, L.total, stream, pdl); break;
+    case 128 + 33: e = tc_launch_one<16, 1, 2>(p, grid, L.total, stream, pdl); break;
+    case 128 + 64: e = tc_launch_one<32, 0, 2>(p, grid, L.total, stream, pdl); break;
+    default: e = tc_launch_one<32, 1, 2>(p, grid, L.total, stream, pdl); break;
   }
   if (e == cudaSuccess) *n_launches += 1;
   if (p.dbg != nullptr && e == cudaSuccess) {             // debug only: synchronous dump of the trace
