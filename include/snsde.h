@@ -153,6 +153,19 @@ int snsde_plan_status(snsde_plan* plan, void* stream);
 int snsde_hermite_coeffs(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
                          float* coeffs_dev, int device, void* stream);
 
+/* Natural cubic spline coefficients on device: the in-tree builder of the forecasting benchmark,
+ * benchmark_forecasting/controldiffeq/interpolate.py:7-53 (called at benchmark_forecasting/datasets/common.py:79-81,
+ * packed by benchmark_forecasting/models_sde/neuralsde.py:161).  x_dev [B,K,C] NaN-free, knots_dev [K] ->
+ * coeffs_dev [B,K-1,4C].  scratch_dev: 3*K floats owned by the caller (knot-only sweep factors). */
+int snsde_natural_coeffs(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
+                         float* coeffs_dev, float* scratch_dev, int device, void* stream);
+
+/* Missing-value (NaN) fill that torchcde applies before the Hermite builder (linear_interpolation_coeffs):
+ * linear in t between observed neighbours, first observed value at the head, forward fill at the tail.
+ * x_dev [B,K,C] -> out_dev [B,K,C] (must not alias x_dev). */
+int snsde_fill_missing(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
+                       float* out_dev, int device, void* stream);
+
 /* Number of engine kernels launched by this plan so far (for bench.py's gpu_launches). */
 int64_t snsde_plan_launch_count(const snsde_plan* plan);
 

@@ -30,7 +30,8 @@ class Emit(ctypes.Structure):
 
 EXPORTS = ("snsde_abi_version", "snsde_last_error", "snsde_weight_count", "snsde_plan_create",
            "snsde_plan_destroy", "snsde_plan_set_weights", "snsde_plan_kernel_kind", "snsde_forward",
-           "snsde_philox_fill", "snsde_plan_launch_count", "snsde_plan_status", "snsde_hermite_coeffs")
+           "snsde_philox_fill", "snsde_plan_launch_count", "snsde_plan_status", "snsde_hermite_coeffs",
+           "snsde_natural_coeffs", "snsde_fill_missing")
 
 _lib = None
 
@@ -62,6 +63,8 @@ def load():
     lib.snsde_plan_launch_count.restype = i64
     lib.snsde_plan_status.argtypes = [vp, vp]
     lib.snsde_hermite_coeffs.argtypes = [vp, vp, i32, i32, i32, vp, ctypes.c_int, vp]
+    lib.snsde_natural_coeffs.argtypes = [vp, vp, i32, i32, i32, vp, vp, ctypes.c_int, vp]
+    lib.snsde_fill_missing.argtypes = [vp, vp, i32, i32, i32, vp, ctypes.c_int, vp]
     lib.snsde_forward.argtypes = [vp, vp, i64, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp, vp, u64, u64, vp, vp]
     lib.snsde_philox_fill.argtypes = [u64, u64, i32, i32, i32, vp, vp, ctypes.c_int, vp]
     for name in EXPORTS:

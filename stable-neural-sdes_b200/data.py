@@ -58,17 +58,54 @@ def natural_cubic_coeffs(x, t):
     return torch.cat((x[..., :-1, :], k0, two_c, three_d), dim=-1)
 
 
-def hermite_coeffs_cuda(x, t, out=None):
-    """Fused CUDA version of :func:`hermite_backward_difference_coeffs` for a NaN-free CUDA tensor
-    ``x [B, K, C]`` (one HBM pass through the C ABI, ``snsde_hermite_coeffs``)."""
-    from . import _lib
+def _cuda_args(x, t, who):
     if not x.is_cuda or x.dim() != 3:
-        raise ValueError("snsde: hermite_coeffs_cuda needs a CUDA tensor [B, K, C]")
+        raise ValueError(f"snsde: {who} needs a CUDA tensor [B, K, C]")
     x = x.detach().to(torch.float32).contiguous()
     t = t.detach().to(device=x.device, dtype=torch.float32).contiguous()
-    B, K, C = x.shape
-    if t.shape != (K,):
+    if t.shape != (x.shape[1],):
         raise ValueError("snsde: knots must be [K]")
+    return x, t
+
+
+def fill_missing_cuda(x, t):
+    """NaN fill torchcde applies before the Hermite builder (linear in t between observed neighbours, first
+    observed value at the head, forward fill at the tail) on device: ``snsde_fill_missing``."""
+    from . import _lib
+    x, t = _cuda_args(x, t, "fill_missing_cuda")
+    B, K, C = x.shape
+    out = torch.empty_like(x)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.load().snsde_fill_missing(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(t.data_ptr()), B, K, C,
+                                              ctypes.c_void_p(out.data_ptr()), x.device.index or 0, ctypes.c_void_p(stream)))
+    return out
+
+
+def natural_coeffs_cuda(x, t, out=None):
+    """CUDA version of :func:`natural_cubic_coeffs` (bit-identical to that torch-op chain) for a NaN-free CUDA tensor
+    ``x [B, K, C]``: knot-only Thomas factors once, then one thread per (row, channel) series (``snsde_natural_coeffs``)."""
+    from . import _lib
+    x, t = _cuda_args(x, t, "natural_coeffs_cuda")
+    B, K, C = x.shape
+    if out is None:
+        out = torch.empty((B, K - 1, 4 * C), device=x.device, dtype=torch.float32)
+    scratch = torch.empty(3 * K, device=x.device, dtype=torch.float32)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.load().snsde_natural_coeffs(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(t.data_ptr()), B, K, C,
+                                                ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(scratch.data_ptr()),
+                                                x.device.index or 0, ctypes.c_void_p(stream)))
+    return out
+
+
+def hermite_coeffs_cuda(x, t, out=None, fill_missing=False):
+    """Fused CUDA version of :func:`hermite_backward_difference_coeffs` for a CUDA tensor ``x [B, K, C]`` (one HBM
+    pass through the C ABI, ``snsde_hermite_coeffs``).  ``fill_missing=True`` first fills NaNs on device the way
+    torchcde does (:func:`fill_missing_cuda`)."""
+    from . import _lib
+    x, t = _cuda_args(x, t, "hermite_coeffs_cuda")
+    if fill_missing:
+        x = fill_missing_cuda(x, t)
+    B, K, C = x.shape
     if out is None:
         out = torch.empty((B, K - 1, 4 * C), device=x.device, dtype=torch.float32)
     stream = torch.cuda.current_stream(x.device).cuda_stream

@@ -468,3 +468,50 @@ def test_hermite_coefficients_on_device_match_the_oracle_builder(dev):
         mg.set_X(c_dev, times.to(dev))
         z = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=3)
     assert torch.isfinite(z).all()
+
+
+def test_natural_spline_coefficients_on_device_match_the_pinned_oracle(dev):
+    """snsde_natural_coeffs against the oracle builder (itself pinned to the reference's in-tree controldiffeq by
+    tests/golden/spline_golden.pt) and, bit for bit, against the torch-op chain the package ships for data prep."""
+    from snsde_b200 import data
+    g = torch.Generator().manual_seed(1)
+    for B, K, C in ((3, 2, 1), (4, 3, 2), (5, 7, 3), (64, 501, 14), (300, 33, 5)):
+        times = torch.cat([torch.zeros(1), torch.rand(K - 1, generator=g) + 0.3]).cumsum(0)
+        x = torch.randn(B, K, C, generator=g).cumsum(1)
+        want = torch.cat(spline.natural_cubic_spline_coeffs(times, x), dim=-1)
+        got = data.natural_coeffs_cuda(x.to(dev), times.to(dev)).cpu()
+        assert got.shape == want.shape == (B, K - 1, 4 * C)
+        scale = want.abs().amax(dim=(0, 1), keepdim=True).clamp_min(1.0)
+        assert float(((got - want).abs() / scale).max()) <= 2e-5
+        chain = data.natural_cubic_coeffs(x.to(dev), times.to(dev)).cpu()
+        assert torch.equal(got, chain)
+        # the spline interpolates the knots and is C2: value / first / second derivative continuous at interior knots
+        a, b, c2, d3 = got.double().chunk(4, dim=-1)
+        h = (times[1:] - times[:-1]).double()[None, :, None]
+        end = a + (b + (c2 / 2 + d3 * h / 3) * h) * h
+        assert torch.allclose(end[:, :-1], a[:, 1:], atol=1e-4 * float(x.abs().max()))
+        assert torch.allclose(end[:, -1], x[:, -1].double(), atol=1e-4 * float(x.abs().max()))
+
+
+def test_missing_value_fill_on_device_matches_the_oracle_and_feeds_the_hermite_builder(dev):
+    from snsde_b200 import data
+    g = torch.Generator().manual_seed(2)
+    B, K, C = 40, 23, 6
+    times = torch.cat([torch.zeros(1), torch.rand(K - 1, generator=g) + 0.2]).cumsum(0)
+    x = torch.randn(B, K, C, generator=g).cumsum(1)
+    holes = torch.rand(B, K, C, generator=g) < 0.35
+    holes[0] = False                       # a complete series
+    holes[1, :, 0] = True                  # nothing observed: stays NaN
+    holes[2, :5, 1] = True                 # leading gap
+    holes[3, -6:, 2] = True                # trailing gap
+    xm = x.masked_fill(holes, float("nan"))
+    want = spline._fill_missing_linear(xm, times)
+    got = data.fill_missing_cuda(xm.to(dev), times.to(dev)).cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.isnan(got[1, :, 0]).all() and not torch.isnan(got[0]).any()
+    ok = ~torch.isnan(want)
+    assert torch.allclose(got[ok], want[ok], rtol=1e-6, atol=1e-6)
+    keep = torch.ones(B, dtype=torch.bool); keep[1] = False
+    co_want = spline.hermite_cubic_coefficients_with_backward_differences(xm[keep], times)
+    co_got = data.hermite_coeffs_cuda(xm[keep].to(dev), times.to(dev), fill_missing=True).cpu()
+    assert torch.allclose(co_got, co_want, rtol=1e-4, atol=1e-5)
