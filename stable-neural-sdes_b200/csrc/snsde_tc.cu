@@ -61,7 +61,17 @@ constexpr int kTcThreads = 32 * (kPrepWarp0 + 4);
 constexpr int kProdWarps = 3;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kPrepWarps = 4;
+constexpr int kCntIn = 32 * (kEpiWarps + 1), kCntPrep = 32 * (kEpiWarps + kPrepWarps);
 constexpr uint32_t kASbo = 128, kALbo = 2048;      // A images: 16 row groups contiguous, then K chunks
+// Warp-to-warp hand-offs inside the CTA use HARDWARE named barriers (bar.arrive / bar.sync), not mbarriers: with 16
+// epilogue warps every mbarrier operation (a shared-memory atomic through the SYNCS unit) was measured at 230-460
+// cycles on the critical path (trace: arrive 467, try_wait 229 / 231); only the hand-offs whose producer is the
+// async proxy (tcgen05.commit, TMA) need an mbarrier.  Barrier 0 is __syncthreads, 1 the producers' own.
+constexpr int kBarIn = 2;                           // epilogue warps arrive, MMA warp syncs
+constexpr int kBarPFull = 3;                        // +slot: step-prefetch warps arrive, epilogue warps sync
+constexpr int kBarPEmpty = 5;                       // +slot: epilogue warps arrive, step-prefetch warps sync
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 struct TcSmem {
   int w, b, x, stg, prep, bias, bars, total;
@@ -203,11 +213,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     }
   }
   if (tid == 0) {
-    mbar_init(bar_in, kEpiWarps);
     mbar_init(bar_acc, 1);
     for (int i = 0; i < p.nx; ++i) { mbar_init(bar_xfull + 8 * i, kProdWarps); mbar_init(bar_xempty + 8 * i, 1); }
     for (int i = 0; i < p.nstg; ++i) mbar_init(bar_cfull + 8 * i, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_pfull + 8 * i, kPrepWarps); mbar_init(bar_pempty + 8 * i, kEpiWarps); }
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -262,8 +270,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     auto hand_over = [&]() {                 // operands written -> MMA issuer (one arrival per warp)
       tc_fence_before();
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_in);
+      named_arrive(kBarIn, kCntIn);
     };
     const float* sbias = reinterpret_cast<const float*>(smem + L.bias) + h;
     const float bias_last = sbias[(NL - 1) * 128];
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       // ---- step data from the prefetch warps (normally already there) ----
       const uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
       const float* sdw = reinterpret_cast<const float*>(slot);
-      mbar_wait(bar_pfull + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+      named_sync(kBarPFull + (s & 1), kCntPrep);
       TC_TRACE(tid == 0, s, EV_EPI_PFULL);
       const StepInfo si = *reinterpret_cast<const StepInfo*>(slot + (NR + 2) * 512);
       const float add0 = sdw[NR * 128 + h];
@@ -427,8 +434,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         if (l == 0) prepare_state(cf, si.t0);
       }
       // ---- in the shadow of the next step's layer-0 MMAs ----
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pempty + 8 * (s & 1));             // slot consumed
+      named_arrive(kBarPEmpty + (s & 1), kCntPrep);                     // slot consumed
       if (si.n_emits > 0) emit(si.first);
       for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);
       TC_TRACE(tid == 0, s, EV_EPI_SHADOW_END);
@@ -455,7 +461,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
                      x_base + slot * L.x_slot_bytes, Cpad / 16, L.lbo_b, tmem + dcol(0), true);
     };
     auto run_segment = [&](const SegOps& o, uint32_t wait_bar, uint32_t wait_par, uint32_t commit_bar, int s = -1, int ev = -1) {
-      mbar_wait(wait_bar, wait_par);
+      if (wait_bar == 0) named_sync(kBarIn, kCntIn);        // operands from the epilogue warps
+      else mbar_wait(wait_bar, wait_par);                   // X(t) operand ring
       tc_fence_after();
       TC_TRACE(lane == 0 && ev >= 0, s, ev);
       issue_segment<N, CH>(leader, o, L.lbo_b);
@@ -472,9 +479,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       const uint64_t x_slot_desc = (uint64_t)(L.x_slot_bytes >> 4);
       for (int s = -1; s < p.S; ++s) {
         if (s >= 0) {
-          run_segment(o0, bar_in, pin, bar_acc, s, EV_MMA_WAKE0);
+          run_segment(o0, 0, 0, bar_acc, s, EV_MMA_WAKE0);
           TC_TRACE(lane == 0, s, EV_MMA_COMMIT0);
-          run_segment(o1, bar_in, pin ^ 1, bar_acc, s, EV_MMA_WAKE1);
+          run_segment(o1, 0, 0, bar_acc, s, EV_MMA_WAKE1);
           TC_TRACE(lane == 0, s, EV_MMA_COMMIT1);
         }
         if (has_x && s + 1 < p.S) {
@@ -499,8 +506,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
           } else {
             const SegOps o = layer_ops(seg);
             asm volatile("" ::"r"(o.ts), "r"(o.nk), "r"(o.a_hi), "r"(o.a_lo), "r"(o.d), "l"(o.db), "r"(o.acc0));
-            run_segment(o, bar_in, pin, bar_acc);
-            pin ^= 1;
+            run_segment(o, 0, 0, bar_acc);
           }
         }
       }
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       si.h = st.h; si.t0 = st.t0; si.n_emits = st.emit_end - st.emit_begin; si.emit_begin = st.emit_begin;
       si.first.slot = 0; si.first.w_prev = 0.f; si.first.w_curr = 0.f;
       if (h == 0 && si.n_emits > 0) si.first = p.emits[st.emit_begin];
-      if (s >= 2) mbar_wait_relaxed(bar_pempty + 8 * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
+      if (s >= 2) named_sync(kBarPEmpty + (s & 1), kCntPrep);
       if (act) {
         if (p.dW != nullptr) {
 #pragma unroll 4
@@ -639,8 +645,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         sdw[(NR + 1) * 128 + h] = cf;
       }
       if (h == 0) *reinterpret_cast<StepInfo*>(slot + (NR + 2) * 512) = si;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pfull + 8 * (s & 1));
+      named_arrive(kBarPFull + (s & 1), kCntPrep);
 
     }
   }
