@@ -70,7 +70,7 @@ def alg_bytes_per_sde_step(w, n_out):
     return (16 * C if ctl else 0) + 4.0 * H * n_out / S + 4.0 * H / S
 
 
-def make_inputs(w, B, seed):
+def make_inputs(w, B, seed, keep_raw=None):
     """Synthetic inputs of SURVEY 8d on the CPU (fp32): integer knots, time channel + random-walk channels,
     Hermite/backward-difference coefficients (natural spline for c5), z0 ~ N(0, 0.1^2), random final_index."""
     from snsde_b200 import data
@@ -89,6 +89,8 @@ def make_inputs(w, B, seed):
         final_index = torch.randint(2, S + 1, (B,), generator=g)
     else:
         final_index = torch.full((B,), S, dtype=torch.long)
+    if keep_raw is not None:
+        keep_raw.append(x.contiguous())
     return times, coeffs, z0, final_index
 
 
@@ -273,8 +275,10 @@ def main():
     Bg = B * world
     row_offset = rank * B
     model = make_model(w).to(dev)
-    sets_host = [make_inputs(w, B, seed=1000 * rank + i) for i in range(N_INPUT_SETS)]
+    raw_host = []
+    sets_host = [make_inputs(w, B, seed=1000 * rank + i, keep_raw=raw_host) for i in range(N_INPUT_SETS)]
     pinned = [tuple(t.pin_memory() for t in s) for s in sets_host]
+    raw_pinned = [x.pin_memory() for x in raw_host]
     sets_dev = [tuple(t.to(dev) for t in s) for s in sets_host]
     times_dev = sets_dev[0][0]
     ts_fixed = output_times(w, times_dev)
@@ -316,10 +320,16 @@ def main():
     e2e_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
     host_outs = [torch.empty((B, H) if w["out"] == "final_index" else (n_out, B, H)).pin_memory() for _ in range(2)]
 
-    def enqueue_e2e(i):
+    from snsde_b200 import data as sdata
+    build_dev = sdata.natural_coeffs_cuda if w["out"] == "tail10" else sdata.hermite_coeffs_cuda
+
+    def enqueue_e2e(i, raw=False):
         times, coeffs, z0, fi = pinned[i % N_INPUT_SETS]
         t_d = times.to(dev, non_blocking=True)
-        c_d = coeffs.to(dev, non_blocking=True)
+        if raw:       # ship the raw path x [B,K,C] (4x fewer bytes) and build the coefficients on device
+            c_d = build_dev(raw_pinned[i % N_INPUT_SETS].to(dev, non_blocking=True), t_d)
+        else:
+            c_d = coeffs.to(dev, non_blocking=True)
         z_d = z0.to(dev, non_blocking=True)
         model.set_X(c_d, t_d)
         if w["out"] == "final_index":
@@ -334,12 +344,12 @@ def main():
             dist.all_gather_into_tensor(buf, z)
         host_outs[i % 2].copy_(z, non_blocking=True)
 
-    def run_e2e(n):
+    def run_e2e(n, raw=False):
         pending = None
         for i in range(n):
             st = e2e_streams[i % 2]
             with torch.cuda.stream(st):
-                enqueue_e2e(i)
+                enqueue_e2e(i, raw)
             if pending is not None:
                 pending.synchronize()              # step i-1 fully done (result is in host memory)
             pending = st
@@ -347,6 +357,7 @@ def main():
     host_out = host_outs[0]
 
     h2d = sum(t.numel() * t.element_size() for t in pinned[0])
+    h2d_raw = h2d - pinned[0][1].numel() * 4 + (raw_pinned[0].numel() * 4 if raw_pinned else 0)
     d2h = host_out.numel() * 4
 
     def barrier():
@@ -395,6 +406,14 @@ def main():
         run_e2e(args.steps)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_raw_s = None
+        if w["family"] == "benchmark":             # secondary: raw path over PCIe + coefficient construction on device
+            run_e2e(args.warmup, raw=True)
+            barrier()
+            t0 = time.perf_counter()
+            run_e2e(args.steps, raw=True)
+            barrier()
+            e2e_raw_s = max_over_ranks(time.perf_counter() - t0)
 
     value = Bg * S * args.steps / (dev_ms * 1e-3)
     e2e_value = Bg * S * args.steps / e2e_s
@@ -442,6 +461,13 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
         }
+        if e2e_raw_s is not None:
+            # NOT the headline: a different host interface (the raw path x instead of the reference's precomputed
+            # coefficients; they are built on device by snsde_hermite_coeffs / snsde_natural_coeffs)
+            line["e2e_raw_path"] = {"value": Bg * S * args.steps / e2e_raw_s, "unit": "SDE-steps/s",
+                                    "h2d_bytes_per_step": h2d_raw, "d2h_bytes_per_step": d2h,
+                                    "ms_per_step": 1e3 * e2e_raw_s / args.steps,
+                                    "note": "host buffers = raw path x[B,K,C]; coefficients built on device per step"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
