@@ -54,6 +54,9 @@ struct snsde_plan {
   snsde_emit* d_emits = nullptr; int emits_cap = 0; std::vector<snsde_emit> h_emits;
   int64_t launches = 0;
   int* d_status = nullptr;            // sticky device flags (snsde_plan_status)
+  // The plan owns device tables (steps, emits, noise tables) that every solve reads: consecutive solves of one
+  // plan are serialised across streams by this event (the caller's copies on other streams still overlap).
+  cudaEvent_t done_ev = nullptr; void* last_stream = nullptr; bool ev_pending = false;
 };
 
 static bool is_time_opt(int io) { return io >= 3 && io <= 6; }
@@ -361,6 +364,7 @@ int snsde_plan_create(const snsde_model_desc* desc, int device, snsde_plan** out
     delete p;
     return fail(SNSDE_ERR_CUDA, "cannot allocate the plan status word");
   }
+  if (cudaEventCreateWithFlags(&p->done_ev, cudaEventDisableTiming) != cudaSuccess) p->done_ev = nullptr;
   *out_plan = p;
   return SNSDE_OK;
 }
@@ -372,6 +376,7 @@ int snsde_plan_destroy(snsde_plan* p) {
   cudaFree(p->d_steps);
   cudaFree(p->d_emits);
   cudaFree(p->d_status);
+  if (p->done_ev) cudaEventDestroy(p->done_ev);
   tc_release(p->tc);
   tcg_release(p->tcg);
   delete p;
@@ -494,8 +499,13 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
 
   cudaStream_t stream = (cudaStream_t)stream_v;
   CUDA_TRY(cudaSetDevice(p->device));
+  if (p->ev_pending && p->last_stream != stream_v) CUDA_TRY(cudaStreamWaitEvent(stream, p->done_ev, 0));
   int rc = upload_tables(p, steps_host, S, emits_host, E, stream);
   if (rc != SNSDE_OK) return rc;
+  struct Done {                      // record the completion event on every exit path after this point
+    snsde_plan* p; cudaStream_t st; void* sv;
+    ~Done() { if (p->done_ev && cudaEventRecord(p->done_ev, st) == cudaSuccess) { p->ev_pending = true; p->last_stream = sv; } }
+  } done_guard{p, stream, stream_v};
 
   if (p->kind >= 1) {
     TcForwardArgs a;

@@ -6,31 +6,34 @@
 // (/root/reference/benchmark_classification/models_sde/neuralsde.py:295-307) + CubicSpline.evaluate.
 //
 // Orientation.  The batch is tiny per SM (1024 rows / 148 SMs ~ 8 rows), the hidden width is
-// 64..128.  So the WEIGHTS are the M=128 operand A (resident in shared memory for the whole
-// kernel) and the batch rows are the small N: D^T[feature, row] = W[feature, :] . act[row, :].
+// 64..128.  So the WEIGHTS are the M=128 operand A - resident in TENSOR MEMORY for the whole kernel
+// (TS-form tcgen05.mma; what does not fit stays in shared memory as SS-form images) - and the batch
+// rows are the small N: D^T[feature, row] = W[feature, :] . act[row, :].
 // TMEM lane i then holds feature i for every row, i.e. epilogue thread i owns feature i - the
 // same thread/feature mapping as the FMA kernel, so the SDE state never leaves registers.
 //
 // Precision.  fp32 parity (1e-4 over hundreds of recurrent steps) on fp16 tensor cores:
 // every operand v is split v ~ hi + 2^-11 * lo', hi = fp16(v), lo' = fp16((v - hi) * 2^11)
 // (22 significant bits), and   W.a ~ Whi.ahi + 2^-11 (Wlo'.ahi + Whi.alo')   with the main and the
-// correction sums in separate fp32 TMEM accumulators, combined in the epilogue.  Two MMAs per
-// 16-wide K chunk:  Whi x [ahi ; alo'] (N' = 2N columns: [main | corr]) and Wlo' x ahi -> corr.
+// correction sums in separate fp32 TMEM accumulator columns, combined in the epilogue.  Two MMAs per
+// 16-wide K chunk:  Whi x [ahi ; alo'] (N' = 2N columns: [main | corr]) and Wlo' x ahi -> the same corr columns.
 //
 // Algebra.  Input options 2,4,6 have no nonlinearity between linear_in and emb
 // (neuralsde.py:202,210), so layer 0 is collapsed on the host in double precision:
 //   z0 = (We1 Win_y) y + (We2 Wi) X(t) + [be + We1 bin + We2 bi] + (We1 Win_tau) [sin t, cos t].
 //
-// Warp roles (512 threads, 1 CTA/SM):
-//   warps 0-7   epilogue (two warps per TMEM lane quadrant, each thread owns one feature of half the
-//               rows): tcgen05.ld accumulators -> bias/activation or SDE update -> split -> write the
-//               next B operand; diffusion of the new state and emits run in the shadow of the MMAs
-//   warp  8     issues every tcgen05.mma (warp-uniform code, one elected lane) and commits to mbarriers
-//   warps 9-11  control producer: 1-D bulk async copies (TMA) of the spline rows several steps
+// Warp roles (768 threads, 1 CTA/SM):
+//   warps 0-15  epilogue (four warps per TMEM lane quadrant, each thread owns one feature of a quarter of
+//               the rows): tcgen05.ld accumulators -> bias/activation or SDE update -> split -> write the
+//               next B operand; outputs and the diffusion of the new state run in the shadow of the MMAs
+//   warp  16    issues every tcgen05.mma (warp-uniform code, one elected lane) and commits to mbarriers
+//   warps 17-19 control producer: 1-D bulk async copies (TMA) of the spline rows several steps
 //               ahead, cubic evaluation, split, write of the X(t) operand ring
-//   warps 12-15 step prefetch: everything that depends on time only - Philox/Box-Muller (or table)
+//   warps 20-23 step prefetch: everything that depends on time only - Philox/Box-Muller (or table)
 //               increments, folded layer-0 bias, diffusion coefficient, step/emit descriptors -
 //               one step ahead, through a 2-deep shared-memory ring
+// Hand-offs between warps are hardware named barriers; mbarriers only where the async proxy (tcgen05.commit,
+// TMA) is the producer.  The hot code is kept inside the 32 KB instruction cache (compact loops, one emit site).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -183,10 +186,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
   const int row0 = blockIdx.x * NR;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  const uint32_t bar_in = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
+  const uint32_t bar_acc = smem_u32(&bars[1]);
   const uint32_t bar_xfull = smem_u32(&bars[2]), bar_xempty = smem_u32(&bars[2 + p.nx]);
   const uint32_t bar_cfull = smem_u32(&bars[2 + 2 * p.nx]);
-  const uint32_t bar_pfull = smem_u32(&bars[2 + 2 * p.nx + p.nstg]), bar_pempty = bar_pfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 + 2 * p.nx + p.nstg + 4]);
   // Two accumulator regions suffice: layer 0 owns region 0 (the X(t) segment of the NEXT step is issued into it
   // while the last layer's epilogue still reads), every later layer reuses region 1 (its MMAs are only issued
@@ -235,11 +237,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       if (im.tmem_col < 0) continue;
       const uint8_t* src = p.wimg + im.g_off + (m >> 3) * kASbo + (m & 7) * 16;
       const int nkc = im.bytes / (2 * (int)kALbo);
-      for (int kc = (warp >> 2); kc < nkc; kc += kEpiPerQuad) {
+      // two chunks per trip: all four 16-byte loads are in flight before the first tcgen05.st (the prologue is one
+      // L2 round trip per trip; it is ~8 % of the launch at S = 200)
+      for (int kc = (warp >> 2); kc < nkc; kc += 2 * kEpiPerQuad) {
+        const int kc2 = kc + kEpiPerQuad;
+        const bool two = kc2 < nkc;
         const uint4 lo = *reinterpret_cast<const uint4*>(src + (size_t)(2 * kc) * kALbo);
         const uint4 hi = *reinterpret_cast<const uint4*>(src + (size_t)(2 * kc + 1) * kALbo);
+        uint4 lo2 = lo, hi2 = hi;
+        if (two) {
+          lo2 = *reinterpret_cast<const uint4*>(src + (size_t)(2 * kc2) * kALbo);
+          hi2 = *reinterpret_cast<const uint4*>(src + (size_t)(2 * kc2 + 1) * kALbo);
+        }
         const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         tmem_st8(tmem + lane_base + (uint32_t)(im.tmem_col + kc * 8), r);
+        if (two) {
+          const uint32_t r2[8] = {lo2.x, lo2.y, lo2.z, lo2.w, hi2.x, hi2.y, hi2.z, hi2.w};
+          tmem_st8(tmem + lane_base + (uint32_t)(im.tmem_col + kc2 * 8), r2);
+        }
       }
     }
     tmem_st_wait();
@@ -448,7 +463,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     const bool leader = elect_one();
     const uint32_t w_base = smem_u32(smem + L.w), b_base = smem_u32(smem + L.b), x_base = smem_u32(smem + L.x);
     const bool has_x = p.uses_control != 0;
-    uint32_t pin = 0, xphase = 0;
+    uint32_t xphase = 0;
     int xslot = 0;
     auto layer_ops = [&](int l) {
       const int ts = p.layer[l].ts;
@@ -874,6 +889,7 @@ int tc_set_weights(TcPlan& tc, const snsde_model_desc& d, const Program& pg, con
   cudaMemcpyAsync(tc.d_vec, img.vec.data(), img.vec.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
   P.wimg = tc.d_wimg; P.wimg_bytes = tc.wimg_bytes; P.vec = tc.d_vec;
   tc.num_sms = num_sms; tc.smem_optin = smem_optin;
+  tc.atab_valid = false;                    // the noise tables depend on the weights
   tc.ready = true;
   return SNSDE_OK;
 }
@@ -903,17 +919,27 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
   *n_launches = 0;
   bool pdl = false;
   if (tc.noise.kind != 0 && a.S > 0) {
-    if (a.S * p.H > tc.atab_cap) {
-      cudaFree(tc.d_atab); tc.d_atab = nullptr;
-      cudaError_t e = cudaMalloc(&tc.d_atab, sizeof(float) * (size_t)a.S * p.H);
-      if (e != cudaSuccess) return e;
-      tc.atab_cap = a.S * p.H;
+    unsigned long long key = 1469598103934665603ull ^ (unsigned long long)a.S;
+    for (int s2 = 0; s2 < a.S; ++s2) {
+      unsigned int w2[2];
+      memcpy(&w2[0], &a.steps_host[s2].sin_t0, 4); memcpy(&w2[1], &a.steps_host[s2].cos_t0, 4);
+      key = (key ^ w2[0]) * 1099511628211ull;
+      key = (key ^ w2[1]) * 1099511628211ull;
     }
-    snsde_tc_tables_kernel<<<a.S, 128, 0, stream>>>(tc.d_vec, tc.noise, p.H, a.steps, tc.d_atab);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    *n_launches += 1;
-    pdl = getenv("SNSDE_NO_PDL") == nullptr;
+    if (!(tc.atab_valid && tc.atab_key == key) || getenv("SNSDE_NO_ATAB_CACHE") != nullptr) {
+      if (a.S * p.H > tc.atab_cap) {
+        cudaFree(tc.d_atab); tc.d_atab = nullptr;
+        cudaError_t e = cudaMalloc(&tc.d_atab, sizeof(float) * (size_t)a.S * p.H);
+        if (e != cudaSuccess) return e;
+        tc.atab_cap = a.S * p.H;
+      }
+      snsde_tc_tables_kernel<<<a.S, 128, 0, stream>>>(tc.d_vec, tc.noise, p.H, a.steps, tc.d_atab);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      *n_launches += 1;
+      pdl = getenv("SNSDE_NO_PDL") == nullptr;
+      tc.atab_key = key; tc.atab_valid = true;
+    }
   }
   p.a_tab = tc.d_atab;
   p.dbg = nullptr;

@@ -63,6 +63,9 @@ struct TcPlan {
   uint8_t* d_wimg = nullptr; int wimg_bytes = 0;
   float* d_vec = nullptr; int vec_floats = 0;
   float* d_atab = nullptr; int atab_cap = 0;
+  // a_tab depends on the step times and the noise-net weights only: it is reused while both are unchanged
+  // (every batch of a dataset shares its knots).  Key = FNV-1a of the steps' (sin t0, cos t0) + S.
+  unsigned long long atab_key = 0; bool atab_valid = false;
   TcParams proto;            // model part of the params
   TcNoiseNet noise;
   int num_sms = 0, smem_optin = 0;

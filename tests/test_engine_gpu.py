@@ -515,3 +515,35 @@ def test_missing_value_fill_on_device_matches_the_oracle_and_feeds_the_hermite_b
     co_want = spline.hermite_cubic_coefficients_with_backward_differences(xm[keep], times)
     co_got = data.hermite_coeffs_cuda(xm[keep].to(dev), times.to(dev), fill_missing=True).cpu()
     assert torch.allclose(co_got, co_want, rtol=1e-4, atol=1e-5)
+
+
+def test_noise_table_cache_follows_weight_updates_and_plan_is_safe_across_streams(dev):
+    """The per-step noise table of the tcgen05 path is reused while (step times, weights) are unchanged; it must be
+    rebuilt after a parameter update, and one plan used from two streams must serialise its solves."""
+    B, H, C, L, K = 48, 64, 5, 1, 17
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=11)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    y0d, td = y0.to(dev), times.to(dev)
+    with torch.no_grad():
+        a1 = snsde_b200.sdeint(mg, y0d, td, dt=1.0, seed=5, precision="tc")
+        a2 = snsde_b200.sdeint(mg, y0d, td, dt=1.0, seed=5, precision="tc")          # cached table
+        assert torch.equal(a1, a2)
+        for p_ in mg.noise_t.parameters():
+            p_.mul_(1.5)                                                               # in-place update -> new version
+        b1 = snsde_b200.sdeint(mg, y0d, td, dt=1.0, seed=5, precision="tc")
+        b_ref = snsde_b200.sdeint(mg, y0d, td, dt=1.0, seed=5, precision="fp32")       # FMA kernel: no table at all
+        assert not torch.equal(a1, b1)
+        close(b1, b_ref)
+        # two streams, one plan, different step grids back to back
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize()
+        outs = []
+        for i in range(6):
+            with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+                ts = td if i % 2 == 0 else td[::2].contiguous()
+                outs.append((i, snsde_b200.sdeint(mg, y0d, ts, dt=1.0, seed=5, precision="tc")))
+        torch.cuda.synchronize()
+        want_full = snsde_b200.sdeint(mg, y0d, td, dt=1.0, seed=5, precision="tc")
+        for i, z in outs:
+            assert torch.equal(z, want_full if i % 2 == 0 else want_full[::2])
