@@ -274,10 +274,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     const TailOp t = p.tail;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* bact = smem + L.b + (h >> 3) * L.lbo_b + (h & 7) * 2;       // + (r/8)*128 + (r%8)*16 ; lo: + (N/8)*128
+    float vmax = 0.f;
     auto write_operand = [&](int r, float v) {
       __half hi, lo;
       split_f16(v, hi, lo);
-      if (fabsf(v) > 65504.f) *p.status = 1;        // saturated: outside the split-fp16 operand range
+      vmax = fmaxf(vmax, fabsf(v));                 // range check of the split-fp16 operands: one flag write at the end
       uint8_t* q = bact + (r >> 3) * 128 + (r & 7) * 16;
       *reinterpret_cast<__half*>(q) = hi;
       *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
@@ -454,6 +455,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);
       TC_TRACE(tid == 0, s, EV_EPI_SHADOW_END);
     }
+    if (vmax > 65504.f) *p.status = 1;              // an operand beyond the fp16 range was saturated (sticky flag)
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
     // The whole warp runs this code (descriptor arithmetic stays on the uniform datapath); one elected
@@ -562,6 +564,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         item_src[k] = (i < NR * C) ? r * 4 * C + c : -1;
         item_dst[k] = (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
       }
+      float xmax = 0.f;
       auto eval_item = [&](const float* rows, uint8_t* xs, int src, int dst, float frac) {
         const float* q0 = rows + src;
         const float v = q0[3 * C] * frac;
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         const float x = q0[0] + inner * frac;
         __half hi, lo;
         split_f16(x, hi, lo);
-        if (fabsf(x) > 65504.f) *p.status = 1;
+        xmax = fmaxf(xmax, fabsf(x));
         *reinterpret_cast<__half*>(xs + dst) = hi;
         *reinterpret_cast<__half*>(xs + dst + (N / 8) * 128) = lo;
       };
@@ -611,6 +614,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);
       }
+      if (xmax > 65504.f) *p.status = 1;
     }
   } else {
     // =========================== STEP PREFETCH (time-only work) ===========================
