@@ -332,11 +332,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     // the rows' dependent MUFU/FMA chains; with per-row branches each row's ~150-cycle chain ran back to back.
     auto diffusion_rows = [&](const float (&yv)[RT], float cf, float t0, float (&g)[RT], float (&dgy)[RT]) {
       if (DIFF == 1) {
+        if (t.milstein) {
 #pragma unroll
-        for (int i = 0; i < RT; ++i) {
-          const float raw = cf * yv[i];
-          g[i] = tanh_fast(t.s_theta * nan_to_num_f(raw));
-          dgy[i] = ((1.f - g[i] * g[i]) * t.s_theta) * (is_finite_f(raw) ? cf : 0.f);
+          for (int i = 0; i < RT; ++i) {
+            const float raw = cf * yv[i];
+            g[i] = tanh_fast(t.s_theta * nan_to_num_f(raw));
+            dgy[i] = ((1.f - g[i] * g[i]) * t.s_theta) * (is_finite_f(raw) ? cf : 0.f);
+          }
+        } else {                                     // Euler: the derivative is never used
+#pragma unroll
+          for (int i = 0; i < RT; ++i) {
+            g[i] = tanh_fast(t.s_theta * nan_to_num_f(cf * yv[i]));
+            dgy[i] = 0.f;
+          }
         }
       } else {
 #pragma unroll
