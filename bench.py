@@ -256,6 +256,15 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, w)
     args.warmup = max(args.warmup, 3)
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:      # no-op when libsnsde.so is current (it ships with the snapshot)
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("snsde_build", ROOT / "stable-neural-sdes_b200" / "build.py")
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as exc:                          # noqa: BLE001
+            print(f"[bench] could not build libsnsde.so: {exc}", file=sys.stderr)
 
     import torch.distributed as dist
     import snsde_b200
