@@ -371,8 +371,17 @@ static double run(int N, int K, bool swap_desc, uint32_t b_pad, int iters, doubl
 int main(int argc, char** argv) {
   srand(1);
   if (argc > 1) {
-    for (int g : {1, 2, 4, 37, 74, 128, 148, 296}) klike(8, 48, 80, 96, 160, 8, 1, g);
-    for (int g : {1, 148}) klike(8, 48, 80, 96, 160, 0, 0, g);
+    // back-to-back issue rate: SS-form vs TS-form, small N (the numbers quoted in DESIGN.md / profiles/r1_umma_probe.txt)
+    rate<16, 1, 0>(512, 0); rate<32, 1, 0>(512, 0); rate<64, 1, 0>(512, 0); rate<128, 2, 0>(512, 0); rate<256, 1, 0>(512, 0);
+    rate<16, 1, 1>(512, 0); rate<16, 4, 1>(512, 0); rate<32, 4, 1>(512, 0); rate<64, 4, 1>(512, 0); rate<128, 2, 1>(512, 0);
+    rate<32, 4, 1, 16, 1>(512, 0); rate<32, 4, 0, 16, 1>(512, 0);
+    // bursts with a commit/wait round trip, as in a persistent per-layer pipeline
+    for (int n : {8, 16, 32, 64}) rate<32, 4, 1, 16, 1>(n, 0, 200, 0);
+    for (int n : {8, 16, 32, 64}) rate<32, 4, 0, 16, 1>(n, 0, 200, 0);
+    // the solve kernel's operand geometry (c2: N = 16, 8 K chunks), alone / with waiting warps / on every SM
+    klike(8, 48, 80, 96, 160);
+    klike(8, 48, 80, 96, 160, 8, 1);
+    for (int g : {1, 148}) klike(8, 48, 80, 96, 160, 8, 1, g);
     return 0;
   }
   for (g_a_tmem = 0; g_a_tmem < 2; ++g_a_tmem) {
