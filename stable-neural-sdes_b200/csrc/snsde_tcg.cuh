@@ -1,7 +1,8 @@
 // General tcgen05 path: host-visible interface + kernel parameter block.
 //
 // Same algorithm, orientation and precision scheme as snsde_tc.cu, without its capacity limits:
-//   * weight operand segments are either RESIDENT in shared memory or STREAMED from L2 every step through a
+//   * weight operand segments are RESIDENT in tensor memory (TS-form MMAs, while the columns behind the
+//     accumulators last), RESIDENT in shared memory, or STREAMED from L2 every step through a
 //     ring of 8 KB slots filled by 1-D bulk async copies (the weight sequence of a step is static, so the
 //     producer runs ahead across layers and steps);
 //   * the output features span up to two 128-row M tiles (hidden <= 256: BASELINE config c5);
@@ -30,6 +31,8 @@ struct TcgJob {
   int stream;       // A tiles come through the ring
   int a_off;        // resident: byte offset in the shared-memory weight area (packed per launch)
   int g_off;        // byte offset of the job's tiles in the global weight blob ([chunk][hi 4 KB | lo 4 KB])
+  int tmem_col;     // >= 0: the job's tiles are resident in TMEM (TS-form MMAs): hi images at [col, col + 8 nk),
+                    // lo images at [col + 8 nk, col + 16 nk); -1: shared memory / ring
 };
 
 struct TcgParams {

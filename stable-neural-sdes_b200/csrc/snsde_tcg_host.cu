@@ -252,17 +252,27 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
   while (NR < nr_max && (a.B + NR - 1) / NR > tc.num_sms) NR *= 2;
   if (getenv("SNSDE_TCG_NR") != nullptr) NR = std::min(nr_max, std::max(8, atoi(getenv("SNSDE_TCG_NR"))));   // experiment knob
   TcgSmem L;
-  int CH = 2;
+  const int CH = 1;
+  const bool use_tmem = getenv("SNSDE_TC_NO_TMEM") == nullptr;
   for (;;) {
     const int N = NR < 16 ? 16 : NR;
-    CH = (2 * nacc * 2 * 2 * N <= 512) ? 2 : 1;
+    // Tensor memory behind the two accumulator regions holds whole jobs (hi + lo images: 16 columns per K chunk),
+    // taken greedily in issue order; what is left goes to shared memory or through the ring as before.
+    {
+      int col = 2 * nacc * CH * 2 * N;
+      for (int j = 0; j < p.n_jobs; ++j) {
+        const int need = 16 * p.jobs[j].nk;
+        p.jobs[j].tmem_col = -1;
+        if (use_tmem && col + need <= 512) { p.jobs[j].tmem_col = col; col += need; }
+      }
+    }
     // X(t) jobs are always resident; then as many others as fit (in issue order), the rest is streamed
     bool ok = false;
     for (int cfg = 0; cfg < 3 && !ok; ++cfg) {
       p.nx = cfg == 0 ? 4 : 2;
       p.nstg = cfg == 2 ? 2 : 4;
       size_t total_tiles = 0;
-      for (int j = 0; j < p.n_jobs; ++j) total_tiles += (size_t)p.jobs[j].nk * kTcgSlotBytes;
+      for (int j = 0; j < p.n_jobs; ++j) if (p.jobs[j].tmem_col < 0) total_tiles += (size_t)p.jobs[j].nk * kTcgSlotBytes;
       const TcgSmem base = tcg_smem_layout(0, 0, p.HP, p.nets, p.C, p.Cpad, N, NR, p.nx, p.nstg, p.NP, p.uses_control);
       const long long room = (long long)tc.smem_optin - base.total - 256;
       if (room < 0) continue;
@@ -276,6 +286,7 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
         long long budget = room - (long long)nslot * kTcgSlotBytes - 16 * nslot;
         res_bytes = 0; n_stream = 0; x_ok = budget >= 0;
         for (int j : order) {
+          if (p.jobs[j].tmem_col >= 0) { if (commit) p.jobs[j].stream = 0; continue; }
           const int sz = p.jobs[j].nk * kTcgSlotBytes;
           const bool resident = x_ok && (nslot == 0 || sz <= budget);
           if (resident) { budget -= sz; res_bytes += sz; }
@@ -293,7 +304,7 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
       if (!x_ok) continue;
       // resident jobs are copied once from the global blob (g_off) into a packed smem area (a_off)
       int packed = 0;
-      for (int j : order) if (!p.jobs[j].stream) { p.jobs[j].a_off = packed; packed += p.jobs[j].nk * kTcgSlotBytes; }
+      for (int j : order) if (!p.jobs[j].stream && p.jobs[j].tmem_col < 0) { p.jobs[j].a_off = packed; packed += p.jobs[j].nk * kTcgSlotBytes; }
       p.nslot = nslot; p.n_stream_chunks = n_stream; p.wres_bytes = res_bytes;
       L = tcg_smem_layout(res_bytes, nslot, p.HP, p.nets, p.C, p.Cpad, N, NR, p.nx, p.nstg, p.NP, p.uses_control);
       ok = L.total <= tc.smem_optin;
@@ -311,8 +322,8 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
     e = fast_diff ? tcg_launch<nr, ch, mt, 1>(p, grid, L.total, stream) : tcg_launch<nr, ch, mt, 0>(p, grid, L.total, stream); \
     break;
   switch (key) {
-    TCG_CASE(8, 2, 1) TCG_CASE(16, 2, 1) TCG_CASE(32, 2, 1) TCG_CASE(32, 1, 1)
-    TCG_CASE(8, 2, 2) TCG_CASE(16, 2, 2)
+    TCG_CASE(8, 1, 1) TCG_CASE(16, 1, 1) TCG_CASE(32, 1, 1)
+    TCG_CASE(8, 1, 2) TCG_CASE(16, 1, 2)
     default: break;
   }
 #undef TCG_CASE

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
   // ---- one-time setup ----
   for (int j = 0; j < p.n_jobs; ++j) {                 // resident weight segments -> smem
     const TcgJob& jb = p.jobs[j];
-    if (jb.stream) continue;
+    if (jb.stream || jb.tmem_col >= 0) continue;
     const uint4* src = reinterpret_cast<const uint4*>(p.wblob + jb.g_off);
     uint4* dst = reinterpret_cast<uint4*>(smem + L.w + jb.a_off);
     for (int i = tid; i < jb.nk * (kTcgSlotBytes / 16); i += kTcgThreads) dst[i] = src[i];
@@ -104,6 +104,29 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // TMEM-resident jobs: lane m = weight row m of the tile, each 32-bit column packs two consecutive K elements
+  // (one 16-byte core-matrix row of the tile image = 4 columns).  Warp w may only touch lane quadrant w % 4.
+  if (warp < kGEpiWarps) {
+    const int m = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int j = 0; j < p.n_jobs; ++j) {
+      const int col = p.jobs[j].tmem_col, nk = p.jobs[j].nk;
+      if (col < 0) continue;
+      const uint8_t* src = p.wblob + p.jobs[j].g_off + (m >> 3) * kGASbo + (m & 7) * 16;
+      for (int i = (warp >> 2); i < 2 * nk; i += kGEpiPerQuad) {          // i < nk: hi image of chunk i; else lo image
+        const int kb = i < nk ? i : i - nk;
+        const uint8_t* q = src + (size_t)kb * kTcgSlotBytes + (i < nk ? 0 : 4096);
+        const uint4 lo = *reinterpret_cast<const uint4*>(q);
+        const uint4 hi = *reinterpret_cast<const uint4*>(q + kGALbo);
+        const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tmem_st8(tmem + lane_base + (uint32_t)(col + 8 * i), r);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp < kGEpiWarps) {
     // =========================== EPILOGUE / SDE STATE ===========================
@@ -329,7 +352,22 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       const uint32_t d = tmem + (p.jobs[j].phase == 0 ? 0u : region_cols) + (uint32_t)p.jobs[j].acc * Acc::kCols;
       uint64_t db = umma_smem_desc(bbase + p.jobs[j].b_chunk0 * 2 * L.lbo_b, L.lbo_b, 128);
       uint32_t acc = p.jobs[j].fresh ? 0u : 1u;
-      if (!p.jobs[j].stream) {
+      if (p.jobs[j].tmem_col >= 0) {                     // tiles resident in TMEM: TS-form MMAs (11-17 vs >= 39 cycles)
+        uint32_t ah = tmem + (uint32_t)p.jobs[j].tmem_col, al = ah + 8u * (uint32_t)nk;
+#pragma unroll 2
+        for (int kb = 0; kb < nk; kb += CH) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if (leader) {
+              umma_f16_ts(d + Acc::a(c), ah, db, idesc2, acc);
+              umma_f16_ts(d + Acc::b(c), al, db, idesc1, 1u);
+            }
+            ah += 8; al += 8;
+            db += b_step;
+          }
+          acc = 1u;
+        }
+      } else if (!p.jobs[j].stream) {
         uint64_t da = umma_smem_desc(w_base + p.jobs[j].a_off, kGALbo, kGASbo);
 #pragma unroll 2
         for (int kb = 0; kb < nk; kb += CH) {
