@@ -73,8 +73,7 @@ constexpr uint32_t kASbo = 128, kALbo = 2048;      // A images: 16 row groups co
 constexpr int kBarIn = 2;                           // epilogue warps arrive, MMA warp syncs
 constexpr int kBarPFull = 3;                        // +slot: step-prefetch warps arrive, epilogue warps sync
 constexpr int kBarPEmpty = 5;                       // +slot: epilogue warps arrive, step-prefetch warps sync
-__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 
 struct TcSmem {
   int w, b, x, stg, prep, bias, bars, total;
@@ -604,8 +603,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         const float frac_next = s + 1 < p.S ? p.steps[s + 1].frac : 0.f;
         const int stg = s % p.nstg, slot = s % p.nx;
         const float frac = frac_cur;
-        mbar_wait_relaxed(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
-        if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
+        mbar_wait(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
+        if (s >= p.nx) mbar_wait(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
 #pragma unroll

@@ -38,8 +38,6 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
 }
 
-__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
-
 // TMEM accumulator region of one layer: per chain c the 2N columns [main | corr] at c*2N.
 //   hi product  Whi x [ahi ; alo']  (N' = 2N)  -> [main | corr]
 //   lo product  Wlo' x ahi          (N)        -> accumulated into the SAME corr columns

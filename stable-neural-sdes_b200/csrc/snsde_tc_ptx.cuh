@@ -43,19 +43,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Hardware named barriers (ids 1..15; 0 is __syncthreads): producer warps arrive, consumer warps sync; `count` =
+// threads of ALL participating warps.  Used for warp-to-warp hand-offs inside the CTA (much cheaper than mbarriers
+// when 8-16 warps take part); mbarriers stay where the async proxy (tcgen05.commit, TMA) is the producer.
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // One lane of a converged warp (warp-uniform code keeps descriptor arithmetic on the uniform datapath).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
   return pred != 0;
 }
-
-// Wait used by the roles that run AHEAD of the critical path (kept as a separate name for readability).
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
-
-// Register re-balancing between warp roles (all warps of a warpgroup must execute the same one).
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- fences -------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -23,6 +23,9 @@ constexpr int kGPrepWarps = 4;
 constexpr int kTcgThreads = 32 * (kGPrepWarp0 + kGPrepWarps);
 constexpr int kGProdThreads = 32 * kGProdWarps;
 constexpr uint32_t kGALbo = 2048, kGASbo = 128;       // inside one 4 KB tile image: [k/8][row/8][row%8][k%8]
+// named hardware barriers of the CTA-internal hand-offs (see snsde_tc.cu); 1 is the producers' own
+constexpr int kGBarIn = 2, kGBarPFull = 3, kGBarPEmpty = 5;
+constexpr int kGCntIn = 32 * (kGEpiWarps + 1), kGCntPrep = 32 * (kGEpiWarps + kGPrepWarps);
 
 struct TcgSmem {
   int w, ring, b0, b1, x, stg, prep, bias, bars, total;
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
   const uint32_t region_cols = (uint32_t)(nets * MT) * Acc::kCols;       // 2 regions: phase 0 | later phases
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  const uint32_t bar_in = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
+  const uint32_t bar_acc = smem_u32(&bars[1]);
   const uint32_t bar_xfull = smem_u32(&bars[2]), bar_xempty = bar_xfull + 8 * p.nx;
   const uint32_t bar_cfull = bar_xempty + 8 * p.nx;
   const uint32_t bar_pfull = bar_cfull + 8 * p.nstg, bar_pempty = bar_pfull + 16;
@@ -90,11 +93,9 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     }
   }
   if (tid == 0) {
-    mbar_init(bar_in, kGEpiWarps);
     mbar_init(bar_acc, 1);
     for (int i = 0; i < p.nx; ++i) { mbar_init(bar_xfull + 8 * i, kGProdWarps); mbar_init(bar_xempty + 8 * i, 1); }
     for (int i = 0; i < p.nstg; ++i) mbar_init(bar_cfull + 8 * i, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_pfull + 8 * i, kGPrepWarps); mbar_init(bar_pempty + 8 * i, kGEpiWarps); }
     for (int i = 0; i < p.nslot; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rempty + 8 * i, 1); }
     mbar_fence_init();
   }
@@ -137,10 +138,11 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     const TailOp t = p.tail;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const bool net2 = nets > 1;
+    float vmax = 0.f;
     auto write_operand = [&](int buf_off, int f, int r, float v) {
       __half hi, lo;
       split_f16(v, hi, lo);
-      if (fabsf(v) > 65504.f) *p.status = 1;        // saturated: outside the split-fp16 operand range
+      vmax = fmaxf(vmax, fabsf(v));                 // range check of the split-fp16 operands: one flag write at the end
       uint8_t* q = smem + buf_off + (f >> 3) * L.lbo_b + (f & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
       *reinterpret_cast<__half*>(q) = hi;
       *reinterpret_cast<__half*>(q + (N / 8) * 128) = lo;
@@ -148,8 +150,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     auto hand_over = [&]() {
       tc_fence_before();
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_in);
+      named_arrive(kGBarIn, kGCntIn);
     };
     const float* sbias = reinterpret_cast<const float*>(smem + L.bias);
     auto bias_of = [&](int ph, int net, int f) { return sbias[(ph * nets + net) * HP + f]; };
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       if (s == p.S) break;
       const uint8_t* slot = smem + L.prep + (s & 1) * L.prep_bytes;
       const float* sdw = reinterpret_cast<const float*>(slot);
-      mbar_wait(bar_pfull + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+      named_sync(kGBarPFull + (s & 1), kGCntPrep);
       const StepInfo si = *reinterpret_cast<const StepInfo*>(slot + (NR + 2) * HP * 4);
       float add0[MT], vec1[MT];                       // folded layer-0 bias; diffusion coefficient or noise-net layer-0 bias
 #pragma unroll
@@ -329,11 +330,11 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         hand_over();
         TC_TRACE(tid == 0 && ph < 2, s, ph == 0 ? EV_EPI_DONE0 : EV_EPI_DONE1);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pempty + 8 * (s & 1));
+      named_arrive(kGBarPEmpty + (s & 1), kGCntPrep);
       pend_n = si.n_emits; pend_begin = si.emit_begin; pend_first = si.first;
       TC_TRACE(tid == 0, s, EV_EPI_SHADOW_END);
     }
+    if (vmax > 65504.f) *p.status = 1;              // an operand beyond the fp16 range was saturated (sticky flag)
   } else if (warp == kGMmaWarp) {
     // =========================== MMA ISSUER (warp-uniform, one elected lane) ===========================
     const bool leader = elect_one();
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     const uint32_t x_base = smem_u32(smem + L.x);
     constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * N), idesc1 = umma_idesc_f16(128, N);
     const uint64_t b_step = (uint64_t)((2 * L.lbo_b) >> 4);
-    uint32_t pin = 0, rslot = 0, rphase = 0, xphase = 0;
+    uint32_t rslot = 0, rphase = 0, xphase = 0;
     int xslot = 0;
     // Descriptor arithmetic is incremental (one 64-bit add per operand and chunk) and the resident / streamed
     // cases are separate loops: the issue rate of this warp bounds the step time.
@@ -419,8 +420,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
           commit_bar = bar_xempty + 8 * xslot;
           if (++xslot == p.nx) { xslot = 0; xphase ^= 1; }
         } else {
-          mbar_wait(bar_in, pin);
-          pin ^= 1;
+          named_sync(kGBarIn, kGCntIn);
           j_end = j;
           while (j_end < n_main && p.jobs[j_end].phase == ph) ++j_end;
           commit_bar = bar_acc;
@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         item_src[k] = (i < NR * C) ? r * 4 * C + c : -1;
         item_dst[k] = (c >> 3) * L.lbo_b + (c & 7) * 2 + (r >> 3) * 128 + (r & 7) * 16;
       }
+      float xmax = 0.f;
       auto eval_item = [&](const float* rows, uint8_t* xs, int src, int dst, float frac) {
         const float* q0 = rows + src;
         const float v = q0[3 * C] * frac;
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         const float x = q0[0] + inner * frac;
         __half hi, lo;
         split_f16(x, hi, lo);
-        if (fabsf(x) > 65504.f) *p.status = 1;
+        xmax = fmaxf(xmax, fabsf(x));
         *reinterpret_cast<__half*>(xs + dst) = hi;
         *reinterpret_cast<__half*>(xs + dst + (N / 8) * 128) = lo;
       };
@@ -497,8 +498,8 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         const float frac_next = s + 1 < p.S ? p.steps[s + 1].frac : 0.f;
         const int stg = s % p.nstg, slot = s % p.nx;
         const float frac = frac_cur;
-        mbar_wait_relaxed(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
-        if (s >= p.nx) mbar_wait_relaxed(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
+        mbar_wait(bar_cfull + 8 * stg, (uint32_t)((s / p.nstg) & 1));
+        if (s >= p.nx) mbar_wait(bar_xempty + 8 * slot, (uint32_t)(((s / p.nx) - 1) & 1));
         const float* rows = reinterpret_cast<const float*>(smem + L.stg + stg * L.stg_bytes);
         uint8_t* xs = smem + L.x + slot * L.x_slot_bytes;
 #pragma unroll
@@ -515,6 +516,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_xfull + 8 * slot);
       }
+      if (xmax > 65504.f) *p.status = 1;
     }
   } else if (warp >= kGPrepWarp0) {
     // =========================== STEP PREFETCH (time-only work) ===========================
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       si.h = st.h; si.t0 = st.t0; si.n_emits = st.emit_end - st.emit_begin; si.emit_begin = st.emit_begin;
       si.first.slot = 0; si.first.w_prev = 0.f; si.first.w_curr = 0.f;
       if (h == 0 && si.n_emits > 0) si.first = p.emits[st.emit_begin];
-      if (s >= 2) mbar_wait_relaxed(bar_pempty + 8 * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
+      if (s >= 2) named_sync(kGBarPEmpty + (s & 1), kGCntPrep);
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int f = h + 128 * mt;
@@ -584,8 +586,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         sdw[(NR + 1) * HP + f] = v1[mt];
       }
       if (h == 0) *reinterpret_cast<StepInfo*>(slot + (NR + 2) * HP * 4) = si;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pfull + 8 * (s & 1));
+      named_arrive(kGBarPFull + (s & 1), kGCntPrep);
     }
   } else {
     // =========================== WEIGHT STREAMER ===========================
