@@ -233,3 +233,18 @@ def test_torch_ists_style_wrapper_requires_an_explicit_method():
         m._solve_sde_path(torch.arange(4.0), torch.zeros(2, 8), {})
     with pytest.raises(ValueError, match="srk"):
         m._solve_sde_path(torch.arange(4.0), torch.zeros(2, 8), {"method": "srk"})
+
+
+def test_bench_algorithmic_costs_match_the_survey_contract():
+    """bench.py's roofline numerators are SURVEY 8(d)'s per-SDE-step figures (layer-wise form, L = 1)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    flops = {"c1": 10368, "c2": 140544, "c3": 37504, "c4": 132096, "c5": 532480}
+    for k, f in flops.items():
+        assert bench.alg_flops_per_sde_step(bench.WORKLOADS[k]) == f
+    # bytes: one 16C-byte spline row per step (models that read the control) + outputs + z0, amortised over S
+    assert abs(bench.alg_bytes_per_sde_step(bench.WORKLOADS["c2"], 1) - (560 + 4 * 128 * 2 / 200)) < 1e-9
+    assert bench.alg_bytes_per_sde_step(bench.WORKLOADS["c4"], 2) < 16          # input option 3 never reads X(t)
+    assert abs(bench.alg_bytes_per_sde_step(bench.WORKLOADS["c5"], 10) - (224 + 4 * 256 * 11 / 500)) < 1e-9
