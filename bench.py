@@ -236,6 +236,223 @@ def run_reference_arm(args, w):
 
 
 # ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off, so the
+    host<->device copies of the e2e leg do not cross the socket interconnect (e2e erratic on the 8-GPU box)."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        if all(hasattr(pr, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            bus = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().lower()
+            if len(bus.split(":")[0]) == 8:             # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+                bus = bus[4:]
+        node = int(pathlib.Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = []
+        for part in pathlib.Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:                                    # noqa: BLE001
+        return None
+
+
+def oracle_model_for(w, model):
+    from oracle import vector_field
+    if w["family"] == "tutorial":
+        m = vector_field.TutorialLSDEFunc(w["C"], w["H"], w["H"], w["L"])
+    else:
+        m = vector_field.DiffusionModel(w["C"], w["H"], w["H"], w["L"], input_option=w["io"], noise_option=w["no"])
+    m.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+    return m
+
+
+def parity_gate(w, model, inputs_host, inputs_dev, plan, dt, dev, row_offset, precision, rows=48, horizon=None, tol=1e-4):
+    """"parity gate run with every measurement".  The engine solves the FULL batch of the workload (same
+    kernel, same launch shape as the timed solve, in-kernel Philox increments); the CPU oracle integrates the first
+    `rows` rows on the materialised increments (rows never interact); rel err = max|z - z_oracle| / max(|z_oracle|, 1e-3)
+    over those rows' outputs.  `horizon`: number of solver steps checked (None = the whole trajectory)."""
+    import snsde_b200
+    from oracle import solver, wrapper
+    times, coeffs, z0, fi = inputs_host
+    times_d, coeffs_d, z0_d, fi_d = inputs_dev
+    S = w["S"] if horizon is None else min(horizon, w["S"])
+    if S < w["S"]:
+        times, coeffs, times_d, coeffs_d = times[:S + 1], coeffs[:, :S], times_d[:S + 1], coeffs_d[:, :S]
+        fi, fi_d = fi.clamp(max=S), fi_d.clamp(max=S)
+    model.set_X(coeffs_d, times_d)
+    seed = 4242
+    with torch.no_grad():
+        if w["out"] == "final_index":
+            ts, slots = snsde_b200.final_index_slots(times, fi)
+            sp = plan.step_plan(ts, dt, times)
+            got = plan.forward(z0_d, sp, coeffs=coeffs_d, row_slot=slots.to(torch.int32), seed=seed, row_offset=row_offset)
+        else:
+            ts = times if w["out"] == "stream" else (torch.cat([times[:1], times[-min(10, S):]]) if w["out"] == "tail10" else times[[0, -1]])
+            sp = plan.step_plan(ts, dt, times)
+            got = plan.forward(z0_d, sp, coeffs=coeffs_d, seed=seed, row_offset=row_offset)
+        dW = snsde_b200.philox_increments(seed, sp, rows, w["H"], dev, row_offset=row_offset).cpu()
+        flags = plan.status()
+    got = got.cpu()
+    m = oracle_model_for(w, model)
+    bm = solver.BrownianTable(dW)
+    with torch.no_grad():
+        if w["out"] == "final_index":
+            want = wrapper.classification_latent(m, times, coeffs[:rows], fi[:rows], z0[:rows], bm, method=w["method"])
+            got = got[:rows]
+        else:
+            m.set_X(coeffs[:rows], times)
+            want = solver.sdeint(m, z0[:rows], ts, dt, bm, method=w["method"])
+            got = got[:, :rows]
+    err = float((got - want).abs().max()) / max(float(want.abs().max()), 1e-3)
+    return {"rel_err": err, "tol": tol, "ok": bool(err <= tol and not (flags & 1)), "rows": rows, "solver_steps": S,
+            "batch_solved": int(z0.shape[0]), "increments": "in-kernel Philox, materialised for the oracle",
+            "oracle": "oracle/ (CPU port; torchsde/torchcde parity unpinned, see oracle/__init__.py)",
+            "fp16_range_flag": int(flags)}
+
+
+class Workload:
+    """Device-resident state of one benchmark workload on this rank."""
+
+    def __init__(self, name, w, precision, dev, rank, world):
+        import snsde_b200
+        self.name, self.w, self.dev, self.rank, self.world = name, w, dev, rank, world
+        B, H, S = w["B"], w["H"], w["S"]
+        self.row_offset = rank * B
+        self.model = make_model(w).to(dev)
+        self.raw_host = []
+        self.sets_host = [make_inputs(w, B, seed=1000 * rank + i, keep_raw=self.raw_host) for i in range(N_INPUT_SETS)]
+        self.sets_dev = [tuple(t.to(dev) for t in s) for s in self.sets_host]
+        with torch.no_grad():
+            self.plan = snsde_b200.plan_for(self.model, w["method"], precision, dev)
+        self.dt = 1.0 / S if w["family"] == "tutorial" else snsde_b200.solver_dt(self.sets_host[0][0].numpy())
+        t0 = time.perf_counter()
+        self.step_plans, self.slots = [], []
+        ts_fixed = output_times(w, self.sets_dev[0][0])
+        for (times, coeffs, z0, fi) in self.sets_host:
+            if w["out"] == "final_index":
+                ts, sl = snsde_b200.final_index_slots(times, fi)
+                self.step_plans.append(self.plan.step_plan(ts, self.dt, times)); self.slots.append(sl.to(torch.int32).to(dev))
+            else:
+                self.step_plans.append(self.plan.step_plan(ts_fixed, self.dt, times)); self.slots.append(None)
+        self.host_plan_ms = 1e3 * (time.perf_counter() - t0) / N_INPUT_SETS      # reported, not part of `value` (SURVEY 8d)
+        self.n_out = self.step_plans[0].n_out if w["out"] != "final_index" else 1
+        Bg = B * world
+        shape = (Bg, H) if w["out"] == "final_index" else (self.n_out, Bg, H)
+        # two gather buffers: the all-gather of solve i runs on a side stream under solve i+1
+        self.gather = [torch.empty(shape, device=dev) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=dev) if world > 1 else None
+        self.gather_done = [None, None]
+
+    def step(self, i):
+        import torch.distributed as dist
+        from snsde_b200 import dist as sdist
+        w, B, H = self.w, self.w["B"], self.w["H"]
+        times, coeffs, z0, fi = self.sets_dev[i % N_INPUT_SETS]
+        sp, sl = self.step_plans[i % N_INPUT_SETS], self.slots[i % N_INPUT_SETS]
+        buf = self.gather[i % 2]
+        main = torch.cuda.current_stream(self.dev)
+        if self.gather_done[i % 2] is not None:
+            main.wait_event(self.gather_done[i % 2])                 # the gather that last used this buffer (2 steps ago)
+        lo = self.row_offset
+        if w["out"] == "final_index":
+            self.plan.forward(z0, sp, coeffs=coeffs, row_slot=sl, seed=i, row_offset=lo, out=buf[lo:lo + B])
+        else:
+            z = self.plan.forward(z0, sp, coeffs=coeffs, seed=i, row_offset=lo)
+        if self.world > 1:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                if w["out"] == "final_index":
+                    sdist.all_gather_rows(buf, self.rank, self.world)
+                else:
+                    z.record_stream(self.side)
+                    tmp = torch.empty((self.world, self.n_out, B, H), device=self.dev)
+                    dist.all_gather_into_tensor(tmp, z)
+                    buf.view(self.n_out, self.world, B, H).copy_(tmp.transpose(0, 1))
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+                self.gather_done[i % 2] = ev
+        return buf
+
+    def drain(self):
+        """Make the main stream wait for every outstanding all-gather (end of a timed region)."""
+        if self.side is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
+
+
+def roofline_block(name, w, plan, kern_ms, n_out_rows):
+    hbm_peak, tf_peak, peak_src = peaks()
+    B, S = w["B"], w["S"]
+    abytes = alg_bytes_per_sde_step(w, n_out_rows)
+    aflops = alg_flops_per_sde_step(w)
+    sde_per_s_kernel = B * S / (kern_ms * 1e-3)                   # one launch, this GPU
+    hbm_gbs = sde_per_s_kernel * abytes / 1e9
+    tflops = sde_per_s_kernel * aflops / 1e12
+    hbm_frac, tf_frac = hbm_gbs / hbm_peak, tflops / tf_peak
+    if tf_frac >= hbm_frac:
+        roof = {"bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_frac}
+    else:
+        roof = {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac}
+    traffic = None
+    tj = ROOT / "profiles" / "traffic.json"
+    if tj.exists():
+        rec = json.loads(tj.read_text()).get(name)
+        if rec and rec["kernel"] == plan.kernel and B == WORKLOADS[name]["B"]:
+            traffic = rec["bytes"]                 # measured once with ncu --set full (see profiles/)
+    roof.update({"traffic": traffic, "alg_bytes_per_launch": abytes * B * S, "kernel": plan.kernel, "kernel_ms_per_launch": kern_ms, "peak_source": peak_src,
+                 "alg_bytes_per_sde_step": abytes, "alg_flops_per_sde_step": aflops,
+                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_frac},
+                 "tensor": {"achieved_tflops": tflops, "peak_tflops": tf_peak, "frac": tf_frac},
+                 "note": "latency-bound chain of small dependent GEMMs (SURVEY 8d); both fractions reported"})
+    return roof
+
+
+def time_resident(wl, steps, warmup, barrier, max_over_ranks, clock_index=None):
+    """W warm-up + K timed device-resident solves (CUDA events on the launching stream; max over ranks)."""
+    with torch.no_grad():
+        for i in range(warmup):
+            wl.step(i)
+        wl.drain()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        end = torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(clock_index) if clock_index is not None else None
+        if sampler:
+            sampler.__enter__()
+        barrier()
+        launches0 = wl.plan.launches
+        t_wall = time.perf_counter()
+        for i in range(steps):
+            evs[i][0].record()
+            wl.step(i)
+            evs[i][1].record()
+        wl.drain()                                  # the last all-gathers are part of the timed region
+        end.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+        launches = wl.plan.launches - launches0
+        if sampler and t_wall < 1.5:                # keep the GPU under load long enough for >= 10 clock samples
+            t_end = time.perf_counter() + 1.5
+            j = 0
+            while time.perf_counter() < t_end:
+                wl.step(j); j += 1
+                if j % 8 == 0:
+                    torch.cuda.synchronize()
+            wl.drain()
+            torch.cuda.synchronize()
+        if sampler:
+            sampler.__exit__()
+    dev_ms = max_over_ranks(evs[0][0].elapsed_time(end))          # whole K-step region on the device, gathers included
+    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)   # the solve launches alone (roofline numerator)
+    return dev_ms, kern_ms, launches, (sampler.summary() if sampler else None)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +463,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--rows", type=int, default=None, help="rows per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c3/c4/c5 blocks of the default line")
     ap.add_argument("--solver-steps", type=int, default=None, help="override the workload's S (launch-overhead sweeps)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -268,7 +486,6 @@ def main():
 
     import torch.distributed as dist
     import snsde_b200
-    from snsde_b200 import dist as sdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -277,51 +494,32 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_node = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     B, H, S = w["B"], w["H"], w["S"]
     Bg = B * world
     row_offset = rank * B
-    model = make_model(w).to(dev)
-    raw_host = []
-    sets_host = [make_inputs(w, B, seed=1000 * rank + i, keep_raw=raw_host) for i in range(N_INPUT_SETS)]
-    pinned = [tuple(t.pin_memory() for t in s) for s in sets_host]
-    raw_pinned = [x.pin_memory() for x in raw_host]
-    sets_dev = [tuple(t.to(dev) for t in s) for s in sets_host]
-    times_dev = sets_dev[0][0]
-    ts_fixed = output_times(w, times_dev)
-    out_rows = (Bg, H) if w["out"] == "final_index" else None
-    method = w["method"]
+    wl = Workload(args.workload, w, args.precision, dev, rank, world)
+    model, plan, dt, method, n_out = wl.model, wl.plan, wl.dt, w["method"], wl.n_out
+    pinned = [tuple(t.pin_memory() for t in s) for s in wl.sets_host]
+    raw_pinned = [x.pin_memory() for x in wl.raw_host]
 
-    with torch.no_grad():
-        plan = snsde_b200.engine._plan_for(model, method, args.precision, dev)
-    dt = 1.0 / S if w["family"] == "tutorial" else snsde_b200.solver_dt(sets_host[0][0].numpy())
-
-    # resident-input step: everything on the device, result written into this rank's slice of the gather buffer
-    step_plans, slots = [], []
-    for (times, coeffs, z0, fi) in sets_dev:
-        if w["out"] == "final_index":
-            ts, sl = snsde_b200.final_index_slots(times, fi)
-            step_plans.append(plan.step_plan(ts, dt, times)); slots.append(sl.to(torch.int32))
-        else:
-            step_plans.append(plan.step_plan(ts_fixed, dt, times)); slots.append(None)
-    n_out = step_plans[0].n_out if w["out"] != "final_index" else 1
-    gather = torch.empty((Bg, H) if w["out"] == "final_index" else (n_out, Bg, H), device=dev)
-
-    def step_resident(i):
-        times, coeffs, z0, fi = sets_dev[i % N_INPUT_SETS]
-        sp, sl = step_plans[i % N_INPUT_SETS], slots[i % N_INPUT_SETS]
-        if w["out"] == "final_index":
-            plan.forward(z0, sp, coeffs=coeffs, row_slot=sl, seed=i, row_offset=row_offset,
-                         out=gather[row_offset:row_offset + B])
-            if world > 1:
-                sdist.all_gather_rows(gather, rank, world)
-        else:
-            z = plan.forward(z0, sp, coeffs=coeffs, seed=i, row_offset=row_offset)
-            if world > 1:
-                dist.all_gather_into_tensor(gather.view(n_out, world, B, H).transpose(0, 1).contiguous(), z)
-        return gather
+    # parity gate of THIS measurement (rank 0's shard): full-batch launch vs the oracle on a row slice
+    parity = parity_gate(w, model, wl.sets_host[0], wl.sets_dev[0], plan, dt, dev, row_offset, args.precision) if rank == 0 else None
 
     # end-to-end step: the public API with HOST (pinned) inputs; H2D + solve + D2H of the latents.  Steps are
     # double-buffered over two CUDA streams so the H2D of step i+1 overlaps the solve of step i; every step's
@@ -374,46 +572,9 @@ def main():
     h2d_raw = h2d - pinned[0][1].numel() * 4 + (raw_pinned[0].numel() * 4 if raw_pinned else 0)
     d2h = host_out.numel() * 4
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    dev_ms, kern_ms, launches, clocks = time_resident(wl, args.steps, args.warmup, barrier, max_over_ranks, clock_index=local_rank)
 
     with torch.no_grad():
-        for i in range(args.warmup):
-            step_resident(i)
-        barrier()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        with ClockSampler(local_rank) as clocks:
-            barrier()
-            launches0 = plan.launches
-            t_wall = time.perf_counter()
-            for i in range(args.steps):
-                evs[i][0].record()
-                step_resident(i)
-                evs[i][1].record()
-            barrier()
-            t_wall = time.perf_counter() - t_wall
-            launches = plan.launches - launches0         # engine kernels launched inside the timed region
-            if t_wall < 1.5:                       # keep the GPU under load long enough for >= 10 clock samples
-                t_end = time.perf_counter() + 1.5
-                j = 0
-                while time.perf_counter() < t_end:
-                    step_resident(j); j += 1
-                    if j % 8 == 0:
-                        torch.cuda.synchronize()
-                torch.cuda.synchronize()
-        per_step_ms = [a.elapsed_time(b) for a, b in evs]
-        dev_ms = max_over_ranks(evs[0][0].elapsed_time(evs[-1][1]))       # whole K-step region on the device
-        kern_ms = statistics.mean(per_step_ms)
-
         run_e2e(args.warmup)
         barrier()
         t0 = time.perf_counter()
@@ -432,30 +593,35 @@ def main():
     value = Bg * S * args.steps / (dev_ms * 1e-3)
     e2e_value = Bg * S * args.steps / e2e_s
 
+    # ---- the other BASELINE configs (c3 single GPU; c4 = B 4096 over 4 GPUs; c5 = B 8192 over 8 GPUs): device-resident
+    # value + roofline + parity, 1024 (c3: 2048) rows per GPU at whatever N this run has ----
+    configs = {}
+    if args.workload == "c2" and not args.no_configs and not args.rows and not args.solver_steps:
+        del pinned, raw_pinned
+        for name in ("c3", "c4", "c5"):
+            cw = dict(WORKLOADS[name])
+            cwl = Workload(name, cw, args.precision, dev, rank, world)
+            # long-horizon trajectories of these models are ill-conditioned in fp32 (tests/test_fullsize_gpu.py):
+            # the gate attached to the measurement checks the full-batch launch over the first 24 solver steps
+            cpar = parity_gate(cw, cwl.model, cwl.sets_host[0], cwl.sets_dev[0], cwl.plan, cwl.dt, dev, rank * cw["B"],
+                               args.precision, horizon=24) if rank == 0 else None
+            c_dev_ms, c_kern_ms, c_launches, _ = time_resident(cwl, args.steps, args.warmup, barrier, max_over_ranks)
+            if rank == 0:
+                nrows = 1 if cw["out"] == "final_index" else cwl.n_out
+                target_n = {"c3": 1, "c4": 4, "c5": 8}[name]
+                configs[name] = {
+                    "workload": cw["desc"], "value": cw["B"] * world * cw["S"] * args.steps / (c_dev_ms * 1e-3),
+                    "unit": "SDE-steps/s", "global_rows": cw["B"] * world, "rows_per_gpu": cw["B"], "solver_steps": cw["S"],
+                    "ms_per_step": c_dev_ms / args.steps, "kernel_ms": c_kern_ms, "kernel": cwl.plan.kernel,
+                    "gpu_launches": c_launches, "host_step_plan_ms": cwl.host_plan_ms,
+                    "baseline_config_n_gpus": target_n, "is_baseline_shape": world == target_n,
+                    "roofline": roofline_block(name, cw, cwl.plan, c_kern_ms, nrows), "parity": cpar}
+            del cwl
+            torch.cuda.empty_cache()
+
     if rank == 0:
-        hbm_peak, tf_peak, peak_src = peaks()
         n_out_rows = 1 if w["out"] == "final_index" else n_out
-        abytes = alg_bytes_per_sde_step(w, n_out_rows)
-        aflops = alg_flops_per_sde_step(w)
-        sde_per_s_kernel = B * S / (kern_ms * 1e-3)                   # one launch, this GPU
-        hbm_gbs = sde_per_s_kernel * abytes / 1e9
-        tflops = sde_per_s_kernel * aflops / 1e12
-        hbm_frac, tf_frac = hbm_gbs / hbm_peak, tflops / tf_peak
-        if tf_frac >= hbm_frac:
-            roof = {"bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_frac}
-        else:
-            roof = {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac}
-        traffic = None
-        tj = ROOT / "profiles" / "traffic.json"
-        if tj.exists():
-            rec = json.loads(tj.read_text()).get(args.workload)
-            if rec and rec["kernel"] == plan.kernel and B == WORKLOADS[args.workload]["B"]:
-                traffic = rec["bytes"]                 # measured once with ncu --set full (see profiles/)
-        roof.update({"traffic": traffic, "alg_bytes_per_launch": abytes * B * S, "kernel": plan.kernel, "kernel_ms_per_launch": kern_ms, "peak_source": peak_src,
-                     "alg_bytes_per_sde_step": abytes, "alg_flops_per_sde_step": aflops,
-                     "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_frac},
-                     "tensor": {"achieved_tflops": tflops, "peak_tflops": tf_peak, "frac": tf_frac},
-                     "note": "latency-bound chain of small dependent GEMMs (SURVEY 8d); both fractions reported"})
+        roof = roofline_block(args.workload, w, plan, kern_ms, n_out_rows)
         cpu = None
         if not args.no_cpu_baseline:
             v, ts_cpu = time_cpu_reference(w, B)
@@ -467,13 +633,14 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "global_rows": Bg, "rows_per_gpu": B,
                        "solver_steps": S, "precision": args.precision, "kernel": plan.kernel,
-                       "parallelism": f"batch-shard x{world}" + (" + NCCL all-gather of final latents" if world > 1 else ""),
+                       "parallelism": f"batch-shard x{world}" + (" + NCCL all-gather of final latents (side stream, double-buffered: "
+                                                                 "the gather of solve i runs under solve i+1)" if world > 1 else ""),
                        "l2": f"rotating {N_INPUT_SETS} input sets ({N_INPUT_SETS * h2d / 1e6:.0f} MB) > 126 MB L2",
-                       "brownian": "in-kernel Philox4x32-10"},
+                       "brownian": "in-kernel Philox4x32-10", "numa_node": numa_node},
             "e2e": {"value": e2e_value, "unit": "SDE-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": launches,
-            "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "host_step_plan_ms": wl.host_plan_ms,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
         }
         if e2e_raw_s is not None:
             # NOT the headline: a different host interface (the raw path x instead of the reference's precomputed
@@ -482,9 +649,14 @@ def main():
                                     "h2d_bytes_per_step": h2d_raw, "d2h_bytes_per_step": d2h,
                                     "ms_per_step": 1e3 * e2e_raw_s / args.steps,
                                     "note": "host buffers = raw path x[B,K,C]; coefficients built on device per step"}
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
+    bad = rank == 0 and ((parity and not parity["ok"]) or any(c["parity"] and not c["parity"]["ok"] for c in configs.values()))
     if world > 1:
         dist.destroy_process_group()
+    if bad:
+        raise SystemExit("[bench] parity gate failed (see `parity` in the JSON line): the measurement is not valid")
 
 
 if __name__ == "__main__":

@@ -15,6 +15,7 @@
  *  - every entry point returns 0 on success or a negative snsde_status; nothing is written
  *    to `out` on a negative return that is detected before launch; no exception crosses;
  *  - `snsde_last_error()` returns a thread-local, NUL-terminated description of the last failure;
+ *  - every entry point restores the caller's current CUDA device before returning;
  *  - entry points only ENQUEUE work on `stream` (a cudaStream_t passed as void*); they never
  *    synchronise the device, except `snsde_plan_set_weights` with `on_device=1`
  *    (one blocking D2H copy of <= a few MB) ;
@@ -30,20 +31,23 @@
 extern "C" {
 #endif
 
-#define SNSDE_ABI_VERSION 1
+#define SNSDE_ABI_VERSION 2
 
 typedef enum {
   SNSDE_OK = 0,
   SNSDE_ERR_BAD_ARG = -1,        /* NULL pointer, non-positive size, inconsistent plan/step tables  */
   SNSDE_ERR_UNSUPPORTED = -2,    /* option pair / method / precision the engine does not implement  */
   SNSDE_ERR_CUDA = -3,           /* CUDA runtime error (allocation, launch); text in last_error      */
-  SNSDE_ERR_NO_WEIGHTS = -4      /* forward called before snsde_plan_set_weights                     */
+  SNSDE_ERR_NO_WEIGHTS = -4,     /* forward called before snsde_plan_set_weights                     */
+  SNSDE_ERR_INTERNAL = -5        /* host allocation failure / unexpected C++ exception (never thrown) */
 } snsde_status;
 
 enum { SNSDE_FAMILY_BENCHMARK = 0,   /* Diffusion_model, neuralsde.py:123-307                        */
        SNSDE_FAMILY_TUTORIAL_LSDE = 1 /* NeuralLSDEFunc, tutorial "Neural LSDE" notebook cell 7      */ };
 enum { SNSDE_METHOD_EULER = 0,       /* torchsde Euler.step (Ito)                                     */
-       SNSDE_METHOD_MILSTEIN = 1     /* torchsde Milstein.step (Ito, diagonal, derivative-based)      */ };
+       SNSDE_METHOD_MILSTEIN = 1,    /* torchsde Milstein.step (Ito, diagonal, derivative-based)      */
+       SNSDE_METHOD_SRK = 2          /* torchsde SRK.diagonal_or_scalar_step (SRID2 tableau, strong
+                                        order 1.5): the torch-ists wrapper's default, nsde_model.py:67  */ };
 enum { SNSDE_PRECISION_FP32 = 0,     /* fp32 FMA kernel, every model/shape                            */
        SNSDE_PRECISION_TC = 1,       /* tcgen05 tensor-core kernel, split-fp16 operands (fp32-class)   */
        SNSDE_PRECISION_AUTO = 2      /* TC when the model/shape is supported, else FP32               */ };
@@ -85,6 +89,17 @@ typedef struct {
   float w_curr;
 } snsde_emit;
 
+/* One evaluation time inside a step (method SRK only): the stages of the SRID2 tableau evaluate f at
+ * t0 + {0, 1, 1/2} h and g at t0 + {0, 1/4, 1} h; the host tabulates per step the four points
+ * t0, t0 + h/4, t0 + h/2, t0 + h (fp32 arithmetic of torchsde: t0 + c*h).  20 bytes. */
+typedef struct {
+  float t;             /* evaluation time                                             */
+  float sin_t;         /* time features at t                                          */
+  float cos_t;
+  float frac;          /* fp32(t - knots[interval])                                   */
+  int32_t interval;    /* clamp(bucketize(t, knots) - 1, 0, K-2)                      */
+} snsde_point;
+
 typedef struct snsde_plan snsde_plan;
 
 int snsde_abi_version(void);
@@ -120,8 +135,12 @@ int snsde_plan_kernel_kind(const snsde_plan* plan);
  *   row_slot_dev     NULL: out_dev is [n_out, B, H] (the torchsde layout);
  *                    else int32[B]: out_dev is [B, H] and row b keeps only slot row_slot[b]
  *                    (fused `z_t.gather(final_index)` of neuralsde.py:115-116)
+ *   points_host      method SRK: [S][4] evaluation points (see snsde_point); NULL otherwise
  *   dW_dev           NULL: increments drawn in-kernel from Philox4x32-10(seed; feature,
  *                    (row_offset+b)>>2, step); else explicit increments [S, B, H] (parity mode)
+ *   dU_dev           method SRK with dW_dev != NULL: the space-time Levy integrals U[S, B, H] paired with dW
+ *                    (torchsde `bm(t0, t1, return_U=True)`: U = h (W/2 + Hst), Hst ~ N(0, h/12)); with
+ *                    dW_dev == NULL they come from a second Philox stream.  NULL otherwise
  *   row_offset       global index of local row 0 (batch sharding keeps the stream invariant)
  */
 int snsde_forward(snsde_plan* plan,
@@ -129,14 +148,17 @@ int snsde_forward(snsde_plan* plan,
                   const float* y0_dev, int32_t B,
                   const snsde_step* steps_host, int32_t S,
                   const snsde_emit* emits_host, int32_t E, int32_t n_init_emits, int32_t n_out,
+                  const snsde_point* points_host,
                   const int32_t* row_slot_dev,
-                  const float* dW_dev, uint64_t seed, uint64_t row_offset,
+                  const float* dW_dev, const float* dU_dev, uint64_t seed, uint64_t row_offset,
                   float* out_dev, void* stream);
 
-/* Materialises the increments the kernels would draw: dW_dev[s,b,j] for s<S, b<B, j<H,
- * scaled by sqrt_h_host[s].  Used to feed the oracle the identical Brownian path. */
+/* Materialises the increments the kernels would draw: dW_dev[s,b,j] = n1 * steps[s].sqrt_h for s<S, b<B, j<H.
+ * Used to feed the oracle the identical Brownian path.
+ * dU_dev (may be NULL): the SRK kernels' space-time Levy integrals for the same path,
+ * U = h (W/2 + sqrt_h sqrt(1/12) n2) with n2 from the second Philox stream (tag 'SNSU'). */
 int snsde_philox_fill(uint64_t seed, uint64_t row_offset, int32_t S, int32_t B, int32_t H,
-                      const float* sqrt_h_host, float* dW_dev, int device, void* stream);
+                      const snsde_step* steps_host, float* dW_dev, float* dU_dev, int device, void* stream);
 
 /* Sticky device-side status of the plan's solves since the last call (synchronises `stream`, then clears):
  *   bit 0: a tensor-core kernel met an operand beyond the fp16 range (|v| > 65504) of its split-precision
@@ -145,6 +167,38 @@ int snsde_philox_fill(uint64_t seed, uint64_t row_offset, int32_t S, int32_t B, 
  *          |z| <= |z0| + sum(h + 6.7 sqrt(h)) because drift and diffusion are tanh-clipped.)
  * Returns the flags (>= 0) or a negative snsde_status. */
 int snsde_plan_status(snsde_plan* plan, void* stream);
+
+/* Non-blocking variant: the flags raised by the solves that have COMPLETED so far (cleared when non-zero); touches
+ * no stream.  The Python layer polls it on every call so that a saturated solve is reported on the next call
+ * at the latest instead of staying silent. */
+int snsde_plan_status_nowait(snsde_plan* plan);
+
+/* ---- backward pass through the solve -------------------------------------------------------------
+ * Replaces the autograd graph the reference builds through torchsde.sdeint when it trains
+ * (benchmark_classification/common_sde.py:156-162: `pred_y = model(...); loss.backward()`;
+ * benchmark_forecasting/common_sde.py:145-150).  Method euler.
+ *
+ * Protocol: run snsde_forward with a step plan that emits EVERY solver state (slot s+1 = state after step s;
+ * out_dev = states [S+1, B, H]); form the requested outputs from those states (linear interpolation / per-row
+ * final_index capture) in the caller; hand the cotangent of every state back here.
+ *   states_dev        [S+1, B, H] saved solver states
+ *   grad_states_dev   [S+1, B, H] dL/d state from the output selection (zero where a state is not an output)
+ *   dW_dev / seed     the same Brownian path as the forward call (table, or Philox replay)
+ *   grad_y0_dev       [B, H]   dL/d y0                                    (written)
+ *   grad_blob_dev     [snsde_weight_count] dL/d weights in the blob layout of snsde_plan_set_weights (overwritten;
+ *                     parameters that do not influence the solve - e.g. initial_network under input options
+ *                     1,3,5 - get zeros, where autograd would report None)
+ *   workspace_dev     snsde_backward_workspace_bytes(plan, B, S) bytes, 16-byte aligned, owned by the caller: the
+ *                     per-op cotangents and activations behind the weight-gradient GEMMs
+ * Coefficients are data: no gradient flows to coeffs_dev. */
+int64_t snsde_backward_workspace_bytes(const snsde_plan* plan, int32_t B, int32_t S);
+int snsde_backward(snsde_plan* plan,
+                   const float* coeffs_dev, int64_t coeff_row_stride, int32_t n_knots, int32_t B,
+                   const snsde_step* steps_host, int32_t S,
+                   const float* states_dev, const float* grad_states_dev,
+                   const float* dW_dev, uint64_t seed, uint64_t row_offset,
+                   float* grad_y0_dev, float* grad_blob_dev,
+                   void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /* Control-path coefficients on device.  Replaces, for NaN-free inputs,
  * torchcde.hermite_cubic_coefficients_with_backward_differences(x, t) as the reference calls it at

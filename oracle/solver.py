@@ -16,6 +16,11 @@ methods/euler.py, methods/milstein.py, _core/interp.py):
 * Euler (Ito):      ``y1 = y0 + f*dt + g*dW``        (diagonal noise: elementwise)
 * Milstein (Ito, diagonal, derivative-based):
                     ``y1 = y0 + f*dt + g*dW + 0.5*vjp_y(g; g*(dW^2-dt))``
+* SRK (Ito, diagonal noise -> ``SRK.diagonal_or_scalar_step``, strong order 1.5, tableau
+  ``tableaus/srid2.py`` = Roessler 2010 SRI2 for diagonal noise): the torch-ists wrapper's
+  default method (torch-ists/torch_ists/diff_module/NSDE/nsde_model.py:63-74, ``default_method='srk'``).
+  It queries ``bm(t0, t1, return_U=True)`` -> ``(I_k, I_k0)`` where ``I_k0 = U`` is the space-time
+  Levy integral ``h (W/2 + Hst)``, ``Hst ~ N(0, h/12)`` (brownian_interval.py ``_H_to_U``).
 * before the loop ``sdeint`` evaluates ``f`` and ``g`` once at ``ts[0]`` (shape checks).
 """
 import torch
@@ -27,18 +32,20 @@ class BrownianTable:
     ``**kwargs`` pass-through (neuralsde.py:84,105,82); parity is defined on identical
     increments because ``BrownianInterval`` streams are not reproducible on device."""
 
-    def __init__(self, dW, check_times=None):
+    def __init__(self, dW, check_times=None, dU=None):
         self.dW = dW
+        self.dU = dU                        # space-time Levy integrals U[S,B,H] (method 'srk')
         self.k = 0
         self.check_times = check_times      # optional [(t0,t1)] list to assert the call pattern
 
-    def __call__(self, t0, t1):
+    def __call__(self, t0, t1, return_U=False):
         if self.check_times is not None:
             e0, e1 = self.check_times[self.k]
             assert float(t0) == e0 and float(t1) == e1, (self.k, float(t0), float(t1), e0, e1)
         w = self.dW[self.k]
+        u = self.dU[self.k] if return_U else None
         self.k += 1
-        return w
+        return (w, u) if return_U else w
 
 
 def _lerp(t0, y0, t1, y1, t):
@@ -69,7 +76,52 @@ def milstein_step(sde, bm, t0, t1, y0):
     return y0 + f * dt + g_prod + 0.5 * gdg
 
 
-_STEPPERS = {"euler": euler_step, "milstein": milstein_step}
+class SRID2:
+    """torchsde/_core/methods/tableaus/srid2.py (Roessler 2010, SRI2 for diagonal noise)."""
+    STAGES = 4
+    C0 = (0, 1, 1 / 2, 0)
+    C1 = (0, 1 / 4, 1, 1 / 4)
+    A0 = ((), (1,), (1 / 4, 1 / 4), (0, 0, 0))
+    A1 = ((), (1 / 4,), (1, 0), (0, 0, 1 / 4))
+    B0 = ((), (0,), (1, 1 / 2), (0, 0, 0))
+    B1 = ((), (-1 / 2,), (1, 0), (2, -1, 1 / 2))
+    alpha = (1 / 6, 1 / 6, 2 / 3, 0)
+    beta1 = (-1, 4 / 3, 2 / 3, 0)
+    beta2 = (1, -4 / 3, 1 / 3, 0)
+    beta3 = (2, -4 / 3, -2 / 3, 0)
+    beta4 = (-2, 5 / 3, -2 / 3, 1)
+
+
+def srk_step(sde, bm, t0, t1, y0):
+    """torchsde 0.2.5 ``SRK.diagonal_or_scalar_step`` (methods/srk.py), statement for statement - including
+    its re-evaluation of f and g of the earlier stages inside every stage."""
+    tab = SRID2
+    dt = t1 - t0
+    rdt = 1 / dt
+    sqrt_dt = dt.sqrt() if torch.is_tensor(dt) else dt ** 0.5
+    I_k, I_k0 = bm(t0, t1, return_U=True)
+    I_kk = (I_k ** 2 - dt) * (1 / 2)
+    I_kkk = (I_k ** 3 - 3 * dt * I_k) * (1 / 6)
+    y1 = y0
+    H0, H1 = [], []
+    for s in range(tab.STAGES):
+        H0s, H1s = y0, y0
+        for j in range(s):
+            f = sde.f(t0 + tab.C0[j] * dt, H0[j])
+            g = sde.g(t0 + tab.C1[j] * dt, H1[j])
+            H0s = H0s + tab.A0[s][j] * f * dt + tab.B0[s][j] * g * I_k0 * rdt
+            H1s = H1s + tab.A1[s][j] * f * dt + tab.B1[s][j] * g * sqrt_dt
+        H0.append(H0s)
+        H1.append(H1s)
+        f = sde.f(t0 + tab.C0[s] * dt, H0s)
+        g_weight = (tab.beta1[s] * I_k + tab.beta2[s] * I_kk / sqrt_dt
+                    + tab.beta3[s] * I_k0 * rdt + tab.beta4[s] * I_kkk * rdt)
+        g = sde.g(t0 + tab.C1[s] * dt, H1s)
+        y1 = y1 + tab.alpha[s] * f * dt + g_weight * g
+    return y1
+
+
+_STEPPERS = {"euler": euler_step, "milstein": milstein_step, "srk": srk_step}
 
 
 def step_times(ts, dt):

@@ -5,9 +5,10 @@ import pathlib
 HERE = pathlib.Path(__file__).resolve().parent
 LIB_PATH = HERE / "libsnsde.so"
 
-OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_WEIGHTS = 0, -1, -2, -3, -4
+OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_WEIGHTS, ERR_INTERNAL = 0, -1, -2, -3, -4, -5
+ABI_VERSION = 2
 FAMILY_BENCHMARK, FAMILY_TUTORIAL_LSDE = 0, 1
-METHOD = {"euler": 0, "milstein": 1}
+METHOD = {"euler": 0, "milstein": 1, "srk": 2}
 PRECISION = {"fp32": 0, "tc": 1, "auto": 2}
 
 
@@ -28,7 +29,12 @@ class Emit(ctypes.Structure):
     _fields_ = [("slot", ctypes.c_int32), ("w_prev", ctypes.c_float), ("w_curr", ctypes.c_float)]
 
 
-EXPORTS = ("snsde_abi_version", "snsde_last_error", "snsde_weight_count", "snsde_plan_create",
+class Point(ctypes.Structure):
+    _fields_ = [("t", ctypes.c_float), ("sin_t", ctypes.c_float), ("cos_t", ctypes.c_float),
+                ("frac", ctypes.c_float), ("interval", ctypes.c_int32)]
+
+
+EXPORTS = ("snsde_plan_status_nowait", "snsde_backward", "snsde_backward_workspace_bytes", "snsde_abi_version", "snsde_last_error", "snsde_weight_count", "snsde_plan_create",
            "snsde_plan_destroy", "snsde_plan_set_weights", "snsde_plan_kernel_kind", "snsde_forward",
            "snsde_philox_fill", "snsde_plan_launch_count", "snsde_plan_status", "snsde_hermite_coeffs",
            "snsde_natural_coeffs", "snsde_fill_missing")
@@ -65,11 +71,15 @@ def load():
     lib.snsde_hermite_coeffs.argtypes = [vp, vp, i32, i32, i32, vp, ctypes.c_int, vp]
     lib.snsde_natural_coeffs.argtypes = [vp, vp, i32, i32, i32, vp, vp, ctypes.c_int, vp]
     lib.snsde_fill_missing.argtypes = [vp, vp, i32, i32, i32, vp, ctypes.c_int, vp]
-    lib.snsde_forward.argtypes = [vp, vp, i64, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp, vp, u64, u64, vp, vp]
-    lib.snsde_philox_fill.argtypes = [u64, u64, i32, i32, i32, vp, vp, ctypes.c_int, vp]
+    lib.snsde_plan_status_nowait.argtypes = [vp]
+    lib.snsde_forward.argtypes = [vp, vp, i64, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, u64, u64, vp, vp]
+    lib.snsde_philox_fill.argtypes = [u64, u64, i32, i32, i32, vp, vp, vp, ctypes.c_int, vp]
+    lib.snsde_backward_workspace_bytes.restype = i64
+    lib.snsde_backward_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.snsde_backward.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, vp, vp, u64, u64, vp, vp, vp, i64, vp]
     for name in EXPORTS:
         getattr(lib, name)
-    if lib.snsde_abi_version() != 1:
+    if lib.snsde_abi_version() != ABI_VERSION:
         raise EngineError("libsnsde.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -63,7 +63,10 @@ def build(force=False, verbose=False):
         for _, _, log in results:
             sys.stderr.write(log)
     if any(changed for _, changed, _ in results) or not LIB.exists():
-        cmd = ["nvcc", "-shared", "-o", str(LIB), *[str(o) for o, _, _ in results]]
+        # cuBLAS: the weight-gradient GEMMs of the backward pass (plain library GEMMs); resolved at load time to the
+        # copy torch has already loaded (same soname), or to the toolkit's through the rpath
+        cmd = ["nvcc", "-shared", "-o", str(LIB), *[str(o) for o, _, _ in results], "-lcublas",
+               "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n" + res.stdout + res.stderr)

@@ -8,31 +8,38 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <string>
 #include <vector>
 
+#include <cublas_v2.h>
+
+#include "snsde_bwd.cuh"
 #include "snsde_common.cuh"
+#include "snsde_host.cuh"
 #include "snsde_rng.cuh"
 #include "snsde_tc.cuh"
 #include "snsde_tcg.cuh"
 
 namespace snsde {
-size_t fma_smem_bytes(const Program& pg, int R, int smem_w_floats);
-cudaError_t fma_launch(const FmaParams& p, int R, int nt, size_t smem, cudaStream_t stream);
-}  // namespace snsde
-
-using namespace snsde;
+size_t fma_group_smem_floats(const Program& pg, int R, int method);
+cudaError_t fma_launch(const FmaParams& p, int R, int method, size_t smem, cudaStream_t stream);
+cudaError_t vec_tables_launch(const Program& pg, const float* wimg, const snsde_step* steps, const snsde_point* points,
+                              int S, int npg, float* vtab, cudaStream_t stream);
 
 // ---- error plumbing ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
 }
+}  // namespace snsde
+
+using namespace snsde;
 #define CUDA_TRY(expr)                                                                         \
   do {                                                                                         \
     cudaError_t e__ = (expr);                                                                  \
@@ -50,10 +57,16 @@ struct snsde_plan {
   int wimg_floats = 0;
   TcPlan tc;                          // tensor-core path state (kind == 1)
   TcgPlan tcg;                        // general tensor-core path state (kind == 2)
+  float* d_blob = nullptr; int blob_floats = 0;     // raw nn.Linear blob (the backward pass reads W in its [out][in] layout)
   snsde_step* d_steps = nullptr; int steps_cap = 0; std::vector<snsde_step> h_steps;
   snsde_emit* d_emits = nullptr; int emits_cap = 0; std::vector<snsde_emit> h_emits;
+  snsde_point* d_points = nullptr; int points_cap = 0; std::vector<snsde_point> h_points;
+  float* d_vtab = nullptr; size_t vtab_cap = 0;     // [S][npg][H] row-independent diffusion coefficient (FMA kernels)
+  cublasHandle_t cublas = nullptr;                  // weight-gradient GEMMs of the backward pass (created lazily)
   int64_t launches = 0;
-  int* d_status = nullptr;            // sticky device flags (snsde_plan_status)
+  // sticky flags raised by the kernels: one word of mapped page-locked host memory (the rare device store travels over
+  // PCIe; the host reads it without touching any stream)
+  int* h_status = nullptr; int* d_status = nullptr;
   // The plan owns device tables (steps, emits, noise tables) that every solve reads: consecutive solves of one
   // plan are serialised across streams by this event (the caller's copies on other streams still overlap).
   cudaEvent_t done_ev = nullptr; void* last_stream = nullptr; bool ev_pending = false;
@@ -71,8 +84,8 @@ static int validate(const snsde_model_desc* d) {
     return fail(SNSDE_ERR_BAD_ARG, "C/H/HH/L must be >= 1");
   if (std::max(d->hidden, d->hidden_hidden) > 1024)
     return fail(SNSDE_ERR_UNSUPPORTED, "hidden sizes above 1024 are not supported");
-  if (d->method != SNSDE_METHOD_EULER && d->method != SNSDE_METHOD_MILSTEIN)
-    return fail(SNSDE_ERR_UNSUPPORTED, "method %d: only euler(0) and milstein(1) are implemented ('srk' is SURVEY 8f2)", d->method);
+  if (d->method != SNSDE_METHOD_EULER && d->method != SNSDE_METHOD_MILSTEIN && d->method != SNSDE_METHOD_SRK)
+    return fail(SNSDE_ERR_UNSUPPORTED, "method %d: implemented methods are euler(0), milstein(1), srk(2)", d->method);
   if (d->precision < 0 || d->precision > SNSDE_PRECISION_AUTO) return fail(SNSDE_ERR_BAD_ARG, "bad precision %d", d->precision);
   if (d->family == SNSDE_FAMILY_BENCHMARK) {
     if (d->input_option < 0 || d->input_option > 6) return fail(SNSDE_ERR_BAD_ARG, "input_option %d not in 0..6", d->input_option);
@@ -140,19 +153,44 @@ static DenseOp make_op(int dst, int src, int K, int N, int w, int b, int act) {
   memset(&o, 0, sizeof(o));
   o.dst = dst; o.src = src; o.src2 = BUF_NONE; o.K = K; o.N = N;
   o.w_off = w; o.w2_off = -1; o.b_off = b; o.tw_off = -1; o.tmode = TM_NONE; o.act = act;
+  o.g_w = -1; o.g_ldw = 0; o.g_col = 0; o.g_col2 = 0; o.g_b = -1;
+  o.src_op = SRC_ABSENT; o.src2_op = SRC_ABSENT;
   return o;
 }
 
 struct BlobCursor {
+  const float* base;
   const float* q;
+  explicit BlobCursor(const float* b) : base(b), q(b) {}
   const float* take(size_t n) { const float* r = q; q += n; return r; }
+  int off(const float* ptr) const { return (int)(ptr - base); }
+};
+
+// Appends ops to a program and records, per op, which earlier op produced each of its inputs (the backward
+// pass keeps every op's output in its own slot) and where its parameters sit in the blob.
+struct ProgramBuilder {
+  Program& pg;
+  const BlobCursor& bc;
+  int n = 0;
+  int writer[BUF_COUNT];
+  ProgramBuilder(Program& p, const BlobCursor& b) : pg(p), bc(b) { for (int& w : writer) w = SRC_ABSENT; }
+  int producer(int buf) const { return buf == BUF_Y ? SRC_STATE : (buf == BUF_X ? SRC_CONTROL : (buf < 0 ? SRC_ABSENT : writer[buf])); }
+  // W: the nn.Linear weight [N][ldw] the op reads (src at columns col.., src2 at col2..), bias b
+  DenseOp& push(DenseOp o, int part, const float* W, int ldw, int col, int col2, const float* b) {
+    o.part = part;
+    o.g_w = W ? bc.off(W) : -1; o.g_ldw = ldw; o.g_col = col; o.g_col2 = col2; o.g_b = b ? bc.off(b) : -1;
+    o.src_op = producer(o.src); o.src2_op = producer(o.src2);
+    pg.ops[n] = o;
+    if (o.dst >= 0) writer[o.dst] = n;
+    return pg.ops[n++];
+  }
 };
 
 static void compile_benchmark(const snsde_model_desc& d, const float* blob, Program& pg, ImageBuilder& ib) {
   const int C = d.input_channels, H = d.hidden, HH = d.hidden_hidden, L = d.num_hidden_layers;
   const int io = d.input_option, no = d.noise_option;
   const int tau = is_time_opt(io) ? 2 : 0;
-  BlobCursor bc{blob};
+  BlobCursor bc(blob);
   const float* Wi = bc.take((size_t)H * C); const float* bi = bc.take(H);
   const float* Win = bc.take((size_t)HH * (H + tau)); const float* bin = bc.take(HH);
   const float *We = nullptr, *be = nullptr;
@@ -160,17 +198,18 @@ static void compile_benchmark(const snsde_model_desc& d, const float* blob, Prog
   std::vector<const float*> Wl(L - 1), bl(L - 1);
   for (int l = 0; l < L - 1; ++l) { Wl[l] = bc.take((size_t)HH * HH); bl[l] = bc.take(HH); }
   const float* Wo = bc.take((size_t)H * HH); const float* bo = bc.take(H);
-  const float theta = *bc.take(1);
+  const float* theta_p = bc.take(1);
+  const float theta = *theta_p;
 
   memset(&pg, 0, sizeof(pg));
   pg.C = C; pg.H = H; pg.HH = HH;
   pg.ld = (std::max(std::max(H, HH), C) + 3) & ~3;
   pg.uses_control = uses_control(io);
-  int n = 0;
+  ProgramBuilder pb(pg, bc);
   int cur;
   if (pg.uses_control) {                      // Xt = initial_network(X(t))      neuralsde.py:296-297
-    pg.ops[n++] = make_op(BUF_U, BUF_X, C, H, ib.add_T(Wi, H, C, 0, C), ib.add_vec(bi, H),
-                          io == 0 ? ACT_RELU : ACT_NONE);
+    pb.push(make_op(BUF_U, BUF_X, C, H, ib.add_T(Wi, H, C, 0, C), ib.add_vec(bi, H), io == 0 ? ACT_RELU : ACT_NONE),
+            0, Wi, C, 0, 0, bi);
   }
   if (io == 0) {
     cur = BUF_U;                              // z = Xt                         :206-207
@@ -178,16 +217,16 @@ static void compile_benchmark(const snsde_model_desc& d, const float* blob, Prog
     DenseOp o = make_op(BUF_A, BUF_Y, H, HH, ib.add_T(Win, HH, H + tau, tau, H), ib.add_vec(bin, HH),
                         is_emb_opt(io) ? ACT_NONE : ACT_RELU);
     if (tau) { o.tmode = TM_SINCOS; o.tw_off = ib.add_T(Win, HH, H + tau, 0, 2); }
-    pg.ops[n++] = o;
+    pb.push(o, 0, Win, H + tau, tau, 0, bin);
     cur = BUF_A;
     if (is_emb_opt(io)) {                     // z = emb(cat(yy, Xt))           :210
       DenseOp e = make_op(BUF_B, BUF_A, H, H, ib.add_T(We, H, 2 * H, 0, H), ib.add_vec(be, H), ACT_RELU);
       e.src2 = BUF_U; e.K2 = H; e.w2_off = ib.add_T(We, H, 2 * H, H, H);
-      pg.ops[n++] = e;
+      pb.push(e, 0, We, 2 * H, 0, H, be);
       cur = BUF_B;
     }
   }
-  // noise networks (row-independent ones run on ONE row per CTA)              :170-179, 271-286
+  // noise networks (row-independent ones are tabulated per step, not evaluated per row)  :170-179, 271-286
   TailOp& t = pg.tail;
   t.geometric = (io == 5 || io == 6);
   t.clip_drift = 1;
@@ -195,16 +234,18 @@ static void compile_benchmark(const snsde_model_desc& d, const float* blob, Prog
   t.s_theta = 1.f / (1.f + expf(-theta));
   t.milstein = d.method == SNSDE_METHOD_MILSTEIN;
   t.special = SP_NONE; t.mult = MU_ONE; t.coef_src = CO_NONE; t.coef_scalar = 0.f;
+  t.g_theta = bc.off(theta_p); t.g_sigma = -1; t.coef_op = -1;
   if (no == 0) t.special = SP_ZERO;
   if (no >= 1 && no <= 3) {
-    t.coef_src = CO_SCALAR; t.coef_scalar = expf(*bc.take(1));
+    const float* sg = bc.take(1);
+    t.coef_src = CO_SCALAR; t.coef_scalar = expf(*sg); t.g_sigma = bc.off(sg);
     t.mult = no == 1 ? MU_ONE : (no == 2 ? MU_T : MU_Y);
   }
   if (no >= 4 && no <= 6) {
     const float* sd = bc.take(H);
     std::vector<float> e(H);
     for (int j = 0; j < H; ++j) e[j] = expf(sd[j]);
-    t.coef_src = CO_IMG; t.coef_ref = ib.add_vec(e.data(), H);
+    t.coef_src = CO_IMG; t.coef_ref = ib.add_vec(e.data(), H); t.g_sigma = bc.off(sd);
     t.mult = no == 4 ? MU_ONE : (no == 5 ? MU_T : MU_Y);
   }
   if (no == 7) t.special = SP_SQRT;
@@ -216,13 +257,13 @@ static void compile_benchmark(const snsde_model_desc& d, const float* blob, Prog
     const float* W1 = bc.take((size_t)H * 2); const float* b1 = bc.take(H);
     DenseOp o = make_op(BUF_V0, BUF_NONE, 0, H, -1, ib.add_vec(b1, H), no >= 16 ? ACT_RELU : ACT_NONE);
     o.vec = 1; o.tmode = TM_SINCOS; o.tw_off = ib.add_T(W1, H, 2, 0, 2);
-    pg.ops[n++] = o;
+    pb.push(o, 1, W1, 2, 2, 0, b1);
     t.coef_src = CO_VBUF; t.coef_ref = BUF_V0;
     if (no >= 16) {
       const float* W2 = bc.take((size_t)H * H); const float* b2 = bc.take(H);
       DenseOp o2 = make_op(BUF_V1, BUF_V0, H, H, ib.add_T(W2, H, H, 0, H), ib.add_vec(b2, H), ACT_RELU);
       o2.vec = 1;
-      pg.ops[n++] = o2;
+      pb.push(o2, 1, W2, H, 0, 0, b2);
       t.coef_ref = BUF_V1;
     }
     t.mult = (no == 13 || no == 17) ? MU_Y : MU_ONE;
@@ -233,42 +274,44 @@ static void compile_benchmark(const snsde_model_desc& d, const float* blob, Prog
     DenseOp o = make_op(deep ? BUF_P : BUF_Q, BUF_Y, H, H, ib.add_T(W1, H, H + 2, 2, H), ib.add_vec(b1, H),
                         deep ? ACT_RELU : ACT_NONE);
     o.tmode = TM_SINCOS; o.tw_off = ib.add_T(W1, H, H + 2, 0, 2);
-    pg.ops[n++] = o;
-    t.vjp_kind = deep ? 2 : 1; t.vjp_w1 = o.w_off; t.vjp_w2 = -1; t.vjp_h1 = BUF_P;
+    const DenseOp& o1 = pb.push(o, 1, W1, H + 2, 2, 0, b1);
+    t.vjp_kind = deep ? 2 : 1; t.vjp_w1 = o1.w_off; t.vjp_w2 = -1; t.vjp_h1 = BUF_P;
     if (deep) {
       const float* W2 = bc.take((size_t)H * H); const float* b2 = bc.take(H);
-      pg.ops[n++] = make_op(BUF_Q, BUF_P, H, H, ib.add_T(W2, H, H, 0, H), ib.add_vec(b2, H), ACT_RELU);
-      t.vjp_w2 = pg.ops[n - 1].w_off;
+      const DenseOp& o2 = pb.push(make_op(BUF_Q, BUF_P, H, H, ib.add_T(W2, H, H, 0, H), ib.add_vec(b2, H), ACT_RELU),
+                                  1, W2, H, 0, 0, b2);
+      t.vjp_w2 = o2.w_off;
     }
-    t.coef_src = CO_RBUF; t.coef_ref = BUF_Q;
+    t.coef_src = CO_RBUF; t.coef_ref = BUF_Q; t.coef_op = pb.n - 1;
     t.mult = (no == 15 || no == 19) ? MU_Y : MU_ONE;
   }
   // shared MLP tail: relu -> (Linear, relu)* -> linear_out                     :212-217
   for (int l = 0; l < L - 1; ++l) {
     const int dst = (cur == BUF_A) ? BUF_B : BUF_A;
-    pg.ops[n++] = make_op(dst, cur, HH, HH, ib.add_T(Wl[l], HH, HH, 0, HH), ib.add_vec(bl[l], HH), ACT_RELU);
+    pb.push(make_op(dst, cur, HH, HH, ib.add_T(Wl[l], HH, HH, 0, HH), ib.add_vec(bl[l], HH), ACT_RELU),
+            0, Wl[l], HH, 0, 0, bl[l]);
     cur = dst;
   }
   DenseOp fo = make_op(BUF_NONE, cur, HH, H, ib.add_T(Wo, H, HH, 0, HH), ib.add_vec(bo, H), ACT_NONE);
   fo.final_drift = 1;
-  pg.ops[n++] = fo;
-  pg.n_ops = n;
+  pb.push(fo, 0, Wo, HH, 0, 0, bo);
+  pg.n_ops = pb.n;
 }
 
 static void compile_tutorial(const snsde_model_desc& d, const float* blob, Program& pg, ImageBuilder& ib) {
   const int C = d.input_channels, H = d.hidden, HH = d.hidden_hidden, L = d.num_hidden_layers;
-  BlobCursor bc{blob};
+  BlobCursor bc(blob);
   memset(&pg, 0, sizeof(pg));
   pg.C = C; pg.H = H; pg.HH = HH;
   pg.ld = (std::max(std::max(H, HH), C) + 3) & ~3;
   pg.uses_control = 1;
-  int n = 0;
+  ProgramBuilder pb(pg, bc);
   const float* WX = bc.take((size_t)H * C); const float* bX = bc.take(H);
   const float* We = bc.take((size_t)H * 2 * H); const float* be = bc.take(H);
-  pg.ops[n++] = make_op(BUF_U, BUF_X, C, H, ib.add_T(WX, H, C, 0, C), ib.add_vec(bX, H), ACT_NONE);
+  pb.push(make_op(BUF_U, BUF_X, C, H, ib.add_T(WX, H, C, 0, C), ib.add_vec(bX, H), ACT_NONE), 0, WX, C, 0, 0, bX);
   DenseOp e = make_op(BUF_A, BUF_Y, H, H, ib.add_T(We, H, 2 * H, 0, H), ib.add_vec(be, H), ACT_NONE);
   e.src2 = BUF_U; e.K2 = H; e.w2_off = ib.add_T(We, H, 2 * H, H, H);     // emb(cat(y, Xt))
-  pg.ops[n++] = e;
+  pb.push(e, 0, We, 2 * H, 0, H, be);
   auto mlp = [&](int cur, int b0, int b1, bool vec) {
     int in = H;
     for (int l = 0; l < L; ++l) {            // Linear(in->HH) + LipSwish, L times
@@ -276,14 +319,14 @@ static void compile_tutorial(const snsde_model_desc& d, const float* blob, Progr
       const int dst = (cur == b0) ? b1 : b0;
       DenseOp o = make_op(dst, cur, in, HH, ib.add_T(W, HH, in, 0, in), ib.add_vec(b, HH), ACT_LIPSWISH);
       o.vec = vec;
-      pg.ops[n++] = o;
+      pb.push(o, vec ? 1 : 0, W, in, 0, 0, b);
       cur = dst; in = HH;
     }
     const float* W = bc.take((size_t)H * HH); const float* b = bc.take(H);
     const int dst = (cur == b0) ? b1 : b0;
     DenseOp o = make_op(dst, cur, HH, H, ib.add_T(W, H, HH, 0, HH), ib.add_vec(b, H), ACT_NONE);
     o.vec = vec;
-    pg.ops[n++] = o;
+    pb.push(o, vec ? 1 : 0, W, HH, 0, 0, b);
     return dst;
   };
   const int fcur = mlp(BUF_A, BUF_A, BUF_B, false);
@@ -291,32 +334,134 @@ static void compile_tutorial(const snsde_model_desc& d, const float* blob, Progr
   const float* Wni = bc.take((size_t)H); const float* bni = bc.take(H);
   DenseOp ni = make_op(BUF_V0, BUF_NONE, 0, H, -1, ib.add_vec(bni, H), ACT_NONE);
   ni.vec = 1; ni.tmode = TM_RAW; ni.tw_off = ib.add_T(Wni, H, 1, 0, 1);
-  pg.ops[n++] = ni;
+  pb.push(ni, 1, Wni, 1, 1, 0, bni);
   const int gcur = mlp(BUF_V0, BUF_V0, BUF_V1, true);
   DenseOp fo = make_op(BUF_NONE, fcur, H, H, ib.add_T(Wlo, H, H, 0, H), ib.add_vec(blo, H), ACT_NONE);
   fo.final_drift = 1;
-  pg.ops[n++] = fo;
-  pg.n_ops = n;
+  pb.push(fo, 0, Wlo, H, 0, 0, blo);
+  pg.n_ops = pb.n;
   TailOp& t = pg.tail;
   memset(&t, 0, sizeof(t));
   t.coef_src = CO_VBUF; t.coef_ref = gcur; t.mult = MU_ONE; t.special = SP_NONE;
   t.bounded = 0; t.clip_drift = 0; t.geometric = 0; t.s_theta = 1.f;
   t.milstein = d.method == SNSDE_METHOD_MILSTEIN;
+  t.g_theta = -1; t.g_sigma = -1; t.coef_op = -1;
 }
 
 // ---- Philox materialisation kernel -------------------------------------------------------------
 __global__ void philox_fill_kernel(unsigned long long seed, unsigned long long row_offset, int S, int B, int H,
-                                   const float* __restrict__ sqrt_h, float* __restrict__ dW) {
+                                   const snsde_step* __restrict__ steps, float* __restrict__ dW, float* __restrict__ dU) {
   const size_t n = (size_t)S * B * H;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % H);
     const size_t sb = i / H;
     const int b = (int)(sb % B), s = (int)(sb / B);
     const unsigned long long gb = row_offset + (unsigned long long)b;
+    const float h = steps[s].h, sqrt_h = steps[s].sqrt_h;
     float nrm[4];
     philox_normals4(seed, (uint32_t)j, (uint32_t)(gb >> 2), (uint32_t)s, nrm);
-    dW[i] = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), sqrt_h[s]);
+    const float w = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), sqrt_h);
+    if (dW != nullptr) dW[i] = w;
+    if (dU != nullptr) {
+      float nu[4];
+      philox_normals4_u(seed, (uint32_t)j, (uint32_t)(gb >> 2), (uint32_t)s, nu);
+      dU[i] = levy_U(w, pick4(nu, (int)(gb & 3ull)), h, sqrt_h);
+    }
   }
+}
+
+// ---- table upload (steps / emits / points are host data; uploaded only when they change) ------------
+template <typename T>
+static int upload_table(T*& d_ptr, int& cap, std::vector<T>& host_copy, const T* src, int n, cudaStream_t stream) {
+  if (n > cap) {
+    cudaFree(d_ptr); d_ptr = nullptr; host_copy.clear(); cap = 0;
+    CUDA_TRY(cudaMalloc(&d_ptr, sizeof(T) * (size_t)std::max(n, 64)));
+    cap = std::max(n, 64);
+  }
+  if ((int)host_copy.size() != n || (n && memcmp(host_copy.data(), src, sizeof(T) * n) != 0)) {
+    host_copy.assign(src, src + n);
+    // pageable source: the runtime stages it before returning
+    if (n) CUDA_TRY(cudaMemcpyAsync(d_ptr, src, sizeof(T) * n, cudaMemcpyHostToDevice, stream));
+  }
+  return SNSDE_OK;
+}
+
+static int upload_tables(snsde_plan* p, const snsde_step* steps, int S, const snsde_emit* emits, int E,
+                         const snsde_point* points, cudaStream_t stream) {
+  int rc = upload_table(p->d_steps, p->steps_cap, p->h_steps, steps, S, stream);
+  if (rc != SNSDE_OK) return rc;
+  rc = upload_table(p->d_emits, p->emits_cap, p->h_emits, emits, E, stream);
+  if (rc != SNSDE_OK) return rc;
+  if (points) rc = upload_table(p->d_points, p->points_cap, p->h_points, points, S * kSrkPoints, stream);
+  return rc;
+}
+
+static int validate_steps(const Program& pg, int n_knots, const snsde_step* steps_host, int S) {
+  for (int s = 0; s < S; ++s)
+    if (pg.uses_control && (steps_host[s].interval < 0 || steps_host[s].interval > n_knots - 2))
+      return fail(SNSDE_ERR_BAD_ARG, "step %d: spline interval %d outside [0,%d]", s, steps_host[s].interval, n_knots - 2);
+  return SNSDE_OK;
+}
+
+static int validate_control(const Program& pg, const float* coeffs_dev, int64_t coeff_row_stride, int n_knots) {
+  if (!pg.uses_control) return SNSDE_OK;
+  if (!coeffs_dev) return fail(SNSDE_ERR_BAD_ARG, "model reads the control path but coeffs is NULL");
+  if (n_knots < 2) return fail(SNSDE_ERR_BAD_ARG, "need at least 2 knots");
+  if (coeff_row_stride < (int64_t)(n_knots - 1) * 4 * pg.C)
+    return fail(SNSDE_ERR_BAD_ARG, "coeff_row_stride %lld < (K-1)*4C", (long long)coeff_row_stride);
+  if (((uintptr_t)coeffs_dev & 15) || (coeff_row_stride & 3))
+    return fail(SNSDE_ERR_BAD_ARG, "coeffs must be 16-byte aligned with a row stride multiple of 4 floats");
+  return SNSDE_OK;
+}
+
+// Serialises consecutive uses of one plan across streams (the plan owns device tables every launch reads) and
+// records the completion event on every exit path.
+struct PlanStreamGuard {
+  snsde_plan* p; cudaStream_t st; void* sv;
+  PlanStreamGuard(snsde_plan* p_, void* sv_) : p(p_), st((cudaStream_t)sv_), sv(sv_) {
+    if (p->ev_pending && p->last_stream != sv) cudaStreamWaitEvent(st, p->done_ev, 0);
+  }
+  ~PlanStreamGuard() {
+    if (p->done_ev && cudaEventRecord(p->done_ev, st) == cudaSuccess) { p->ev_pending = true; p->last_stream = sv; }
+  }
+};
+
+// Row groups per CTA, warps per group and the staged share of the weight image for the FMA-style kernels.
+struct GroupConfig { int R, nw, groups, smem_w_floats; size_t smem; };
+static bool pick_group_config(const snsde_plan* p, int B, size_t group_floats_r4, size_t group_floats_r8, bool allow_r8,
+                              GroupConfig& g) {
+  const Program& pg = p->prog;
+  g.nw = (std::max(pg.H, pg.HH) + 31) / 32;
+  const int max_threads = g.nw > 16 ? 1024 : 512;
+  // 8 rows per group amortise each weight read over twice the FMAs; keep 4 while that still fills the machine
+  g.R = (allow_r8 && g.nw <= 16 && (B + 3) / 4 > 4 * p->num_sms) ? 8 : 4;
+  const size_t gf = (g.R == 8 ? group_floats_r8 : group_floats_r4) * sizeof(float);
+  if (gf > (size_t)p->smem_optin) {
+    if (g.R == 8 && group_floats_r4 * sizeof(float) <= (size_t)p->smem_optin) { g.R = 4; return pick_group_config(p, B, group_floats_r4, group_floats_r8, false, g); }
+    return false;
+  }
+  const int n_groups = (B + g.R - 1) / g.R;
+  int G = std::max(1, n_groups / std::max(1, p->num_sms));           // one wave of CTAs first
+  G = std::min(G, std::min(15, max_threads / (g.nw * 32)));           // 15 named barriers, thread limit
+  G = std::max(G, 1);
+  while (G > 1 && (size_t)G * gf > (size_t)p->smem_optin) --G;
+  // trade groups for staged weights while the whole image does not fit beside them
+  const size_t img = (size_t)p->wimg_floats * sizeof(float);
+  while (G > 1 && (size_t)G * gf + img > (size_t)p->smem_optin && (size_t)(G - 1) * gf + img <= (size_t)p->smem_optin) --G;
+  g.groups = G;
+  const size_t room = ((size_t)p->smem_optin - (size_t)G * gf) / sizeof(float);
+  g.smem_w_floats = (int)std::min<size_t>((size_t)p->wimg_floats, room) & ~3;
+  g.smem = (size_t)g.smem_w_floats * sizeof(float) + (size_t)G * gf;
+  return true;
+}
+
+static int ensure_vtab(snsde_plan* p, size_t floats) {
+  if (floats > p->vtab_cap) {
+    cudaFree(p->d_vtab); p->d_vtab = nullptr; p->vtab_cap = 0;
+    CUDA_TRY(cudaMalloc(&p->d_vtab, floats * sizeof(float)));
+    p->vtab_cap = floats;
+  }
+  return SNSDE_OK;
 }
 
 // ---- ABI ----------------------------------------------------------------------------------------
@@ -332,6 +477,7 @@ int64_t snsde_weight_count(const snsde_model_desc* desc) {
 }
 
 int snsde_plan_create(const snsde_model_desc* desc, int device, snsde_plan** out_plan) {
+  SNSDE_API_BEGIN
   if (!out_plan) return fail(SNSDE_ERR_BAD_ARG, "out_plan is NULL");
   *out_plan = nullptr;
   const int rc = validate(desc);
@@ -339,48 +485,57 @@ int snsde_plan_create(const snsde_model_desc* desc, int device, snsde_plan** out
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(SNSDE_ERR_BAD_ARG, "device %d out of range (%d devices)", device, ndev);
-  snsde_plan* p = new snsde_plan();
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err));
+  std::unique_ptr<snsde_plan> p(new snsde_plan());
   p->desc = *desc;
   p->device = device;
   cudaDeviceProp prop;
-  cudaError_t e = cudaGetDeviceProperties(&prop, device);
-  if (e != cudaSuccess) { delete p; return fail(SNSDE_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   p->num_sms = prop.multiProcessorCount;
   p->smem_optin = (int)prop.sharedMemPerBlockOptin;
   const bool force_general = getenv("SNSDE_FORCE_TCG") != nullptr;           // testing aid: general kernel even where the resident one applies
-  const bool tc_ok = tc_supported(*desc, prop.major, p->smem_optin) && !force_general;
+  const bool srk = desc->method == SNSDE_METHOD_SRK;                          // SRK stages run on the FMA kernels
+  const bool tc_ok = !srk && tc_supported(*desc, prop.major, p->smem_optin) && !force_general;
   const int no_ = desc->noise_option;
   // Milstein through a state-dependent noise network needs the full vjp: implemented in the FMA kernel only
   const bool net_vjp = desc->family == SNSDE_FAMILY_BENCHMARK && desc->method == SNSDE_METHOD_MILSTEIN &&
                        (no_ == 14 || no_ == 15 || no_ == 18 || no_ == 19);
-  const bool tcg_ok = tcg_supported(*desc, prop.major, p->smem_optin) && !net_vjp;
-  if (desc->precision == SNSDE_PRECISION_TC && !tc_ok && !tcg_ok) {
-    delete p;
-    return fail(SNSDE_ERR_UNSUPPORTED, "tensor-core path does not support this model/shape/device: %s", tcg_unsupported_reason());
-  }
+  const bool tcg_ok = !srk && tcg_supported(*desc, prop.major, p->smem_optin) && !net_vjp;
+  if (desc->precision == SNSDE_PRECISION_TC && !tc_ok && !tcg_ok)
+    return fail(SNSDE_ERR_UNSUPPORTED, "tensor-core path does not support this model/shape/method/device: %s",
+                srk ? "method 'srk' runs on the fp32 kernels" : tcg_unsupported_reason());
   p->kind = desc->precision == SNSDE_PRECISION_FP32 ? 0 : (tc_ok ? 1 : (tcg_ok ? 2 : 0));
-  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p->d_status, sizeof(int)) != cudaSuccess ||
-      cudaMemset(p->d_status, 0, sizeof(int)) != cudaSuccess) {
-    delete p;
-    return fail(SNSDE_ERR_CUDA, "cannot allocate the plan status word");
+  CUDA_TRY(cudaHostAlloc(&p->h_status, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+  *p->h_status = 0;
+  if (cudaHostGetDevicePointer(&p->d_status, p->h_status, 0) != cudaSuccess) {
+    cudaFreeHost(p->h_status);
+    return fail(SNSDE_ERR_CUDA, "cannot map the plan status word");
   }
   if (cudaEventCreateWithFlags(&p->done_ev, cudaEventDisableTiming) != cudaSuccess) p->done_ev = nullptr;
-  *out_plan = p;
+  *out_plan = p.release();
   return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
 
 int snsde_plan_destroy(snsde_plan* p) {
+  SNSDE_API_BEGIN
   if (!p) return SNSDE_OK;
-  cudaSetDevice(p->device);
+  DeviceGuard guard(p->device);
   cudaFree(p->d_wimg);
+  cudaFree(p->d_blob);
   cudaFree(p->d_steps);
   cudaFree(p->d_emits);
-  cudaFree(p->d_status);
+  cudaFree(p->d_points);
+  cudaFree(p->d_vtab);
+  cudaFreeHost(p->h_status);
+  if (p->cublas) cublasDestroy(p->cublas);
   if (p->done_ev) cudaEventDestroy(p->done_ev);
   tc_release(p->tc);
   tcg_release(p->tcg);
   delete p;
   return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
 
 int snsde_plan_kernel_kind(const snsde_plan* p) {
@@ -391,22 +546,35 @@ int snsde_plan_kernel_kind(const snsde_plan* p) {
 int64_t snsde_plan_launch_count(const snsde_plan* p) { return p ? p->launches : 0; }
 
 int snsde_plan_status(snsde_plan* p, void* stream_v) {
+  SNSDE_API_BEGIN
   if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
-  cudaStream_t stream = (cudaStream_t)stream_v;
-  int flags = 0;
-  CUDA_TRY(cudaSetDevice(p->device));
-  CUDA_TRY(cudaMemcpyAsync(&flags, p->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  CUDA_TRY(cudaMemsetAsync(p->d_status, 0, sizeof(int), stream));
-  CUDA_TRY(cudaStreamSynchronize(stream));
+  DeviceGuard guard(p->device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream_v));
+  volatile int* w = p->h_status;
+  const int flags = *w;
+  *w = 0;
+  return flags;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
+}
+
+int snsde_plan_status_nowait(snsde_plan* p) {
+  if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
+  volatile int* w = p->h_status;
+  const int flags = *w;
+  if (flags) *w = 0;
   return flags;
 }
 
 int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, int on_device, void* stream_v) {
+  SNSDE_API_BEGIN
   if (!p || !blob) return fail(SNSDE_ERR_BAD_ARG, "plan/blob is NULL");
   const int64_t want = weight_count(&p->desc);
   if (n_floats != want) return fail(SNSDE_ERR_BAD_ARG, "weight blob has %lld floats, model needs %lld", (long long)n_floats, (long long)want);
   cudaStream_t stream = (cudaStream_t)stream_v;
-  CUDA_TRY(cudaSetDevice(p->device));
+  DeviceGuard guard(p->device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+  PlanStreamGuard order(p, stream_v);                 // earlier solves of this plan still read the old images
   std::vector<float> host;
   if (on_device) {
     host.resize(n_floats);
@@ -420,12 +588,19 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
   ib.pad4();
   if ((int)ib.img.size() > p->wimg_floats) {
     cudaFree(p->d_wimg);
-    p->d_wimg = nullptr;
+    p->d_wimg = nullptr; p->wimg_floats = 0;
     CUDA_TRY(cudaMalloc(&p->d_wimg, ib.img.size() * sizeof(float)));
   }
   p->wimg_floats = (int)ib.img.size();
   // pageable source: the runtime stages it before returning, so `ib` may die at scope exit
   CUDA_TRY(cudaMemcpyAsync(p->d_wimg, ib.img.data(), ib.img.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+  if ((int)n_floats > p->blob_floats) {
+    cudaFree(p->d_blob);
+    p->d_blob = nullptr; p->blob_floats = 0;
+    CUDA_TRY(cudaMalloc(&p->d_blob, (size_t)n_floats * sizeof(float)));
+    p->blob_floats = (int)n_floats;
+  }
+  CUDA_TRY(cudaMemcpyAsync(p->d_blob, blob, (size_t)n_floats * sizeof(float), cudaMemcpyHostToDevice, stream));
   if (p->kind == 1) {
     const int rc = tc_set_weights(p->tc, p->desc, p->prog, blob, p->num_sms, p->smem_optin, stream);
     if (rc == SNSDE_ERR_UNSUPPORTED && p->desc.precision == SNSDE_PRECISION_AUTO) p->kind = 0;   // e.g. weights beyond fp16 range
@@ -438,56 +613,37 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
   }
   p->has_weights = true;
   return SNSDE_OK;
-}
-
-static int upload_tables(snsde_plan* p, const snsde_step* steps, int S, const snsde_emit* emits, int E,
-                         cudaStream_t stream) {
-  if (S > p->steps_cap) {
-    cudaFree(p->d_steps); p->d_steps = nullptr; p->h_steps.clear();
-    CUDA_TRY(cudaMalloc(&p->d_steps, sizeof(snsde_step) * (size_t)std::max(S, 64)));
-    p->steps_cap = std::max(S, 64);
-  }
-  if (E > p->emits_cap) {
-    cudaFree(p->d_emits); p->d_emits = nullptr; p->h_emits.clear();
-    CUDA_TRY(cudaMalloc(&p->d_emits, sizeof(snsde_emit) * (size_t)std::max(E, 64)));
-    p->emits_cap = std::max(E, 64);
-  }
-  if ((int)p->h_steps.size() != S || (S && memcmp(p->h_steps.data(), steps, sizeof(snsde_step) * S) != 0)) {
-    p->h_steps.assign(steps, steps + S);
-    if (S) CUDA_TRY(cudaMemcpyAsync(p->d_steps, steps, sizeof(snsde_step) * S, cudaMemcpyHostToDevice, stream));
-  }
-  if ((int)p->h_emits.size() != E || (E && memcmp(p->h_emits.data(), emits, sizeof(snsde_emit) * E) != 0)) {
-    p->h_emits.assign(emits, emits + E);
-    if (E) CUDA_TRY(cudaMemcpyAsync(p->d_emits, emits, sizeof(snsde_emit) * E, cudaMemcpyHostToDevice, stream));
-  }
-  return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
 
 int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stride, int32_t n_knots,
                   const float* y0_dev, int32_t B, const snsde_step* steps_host, int32_t S,
                   const snsde_emit* emits_host, int32_t E, int32_t n_init_emits, int32_t n_out,
-                  const int32_t* row_slot_dev, const float* dW_dev, uint64_t seed, uint64_t row_offset,
+                  const snsde_point* points_host, const int32_t* row_slot_dev,
+                  const float* dW_dev, const float* dU_dev, uint64_t seed, uint64_t row_offset,
                   float* out_dev, void* stream_v) {
+  SNSDE_API_BEGIN
   if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
   if (!p->has_weights) return fail(SNSDE_ERR_NO_WEIGHTS, "snsde_forward before snsde_plan_set_weights");
   if (!y0_dev || !out_dev) return fail(SNSDE_ERR_BAD_ARG, "y0/out is NULL");
   if (B < 1 || S < 0 || E < 0 || n_out < 1) return fail(SNSDE_ERR_BAD_ARG, "bad sizes B=%d S=%d E=%d n_out=%d", B, S, E, n_out);
   if ((S && !steps_host) || (E && !emits_host)) return fail(SNSDE_ERR_BAD_ARG, "step/emit table is NULL");
   if (n_init_emits < 0 || n_init_emits > E) return fail(SNSDE_ERR_BAD_ARG, "n_init_emits out of range");
+  const bool srk = p->desc.method == SNSDE_METHOD_SRK;
+  if (srk && S && !points_host) return fail(SNSDE_ERR_BAD_ARG, "method srk needs the per-step evaluation points");
+  if (srk && dW_dev && !dU_dev) return fail(SNSDE_ERR_BAD_ARG, "method srk with explicit increments needs dU (space-time Levy integrals) beside dW");
   const Program& pg = p->prog;
-  if (pg.uses_control) {
-    if (!coeffs_dev) return fail(SNSDE_ERR_BAD_ARG, "model reads the control path but coeffs is NULL");
-    if (n_knots < 2) return fail(SNSDE_ERR_BAD_ARG, "need at least 2 knots");
-    if (coeff_row_stride < (int64_t)(n_knots - 1) * 4 * pg.C)
-      return fail(SNSDE_ERR_BAD_ARG, "coeff_row_stride %lld < (K-1)*4C", (long long)coeff_row_stride);
-    if (((uintptr_t)coeffs_dev & 15) || (coeff_row_stride & 3))
-      return fail(SNSDE_ERR_BAD_ARG, "coeffs must be 16-byte aligned with a row stride multiple of 4 floats");
-  }
+  int rc = validate_control(pg, coeffs_dev, coeff_row_stride, n_knots);
+  if (rc != SNSDE_OK) return rc;
+  rc = validate_steps(pg, n_knots, steps_host, S);
+  if (rc != SNSDE_OK) return rc;
+  if (srk && pg.uses_control)
+    for (int i = 0; i < S * kSrkPoints; ++i)
+      if (points_host[i].interval < 0 || points_host[i].interval > n_knots - 2)
+        return fail(SNSDE_ERR_BAD_ARG, "point %d: spline interval %d outside [0,%d]", i, points_host[i].interval, n_knots - 2);
   int prev_end = n_init_emits;
   for (int s = 0; s < S; ++s) {
     const snsde_step& st = steps_host[s];
-    if (pg.uses_control && (st.interval < 0 || st.interval > n_knots - 2))
-      return fail(SNSDE_ERR_BAD_ARG, "step %d: spline interval %d outside [0,%d]", s, st.interval, n_knots - 2);
     if (st.emit_begin != prev_end || st.emit_end < st.emit_begin || st.emit_end > E)
       return fail(SNSDE_ERR_BAD_ARG, "step %d: emit range [%d,%d) is not contiguous with the previous step", s, st.emit_begin, st.emit_end);
     prev_end = st.emit_end;
@@ -498,14 +654,11 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
       return fail(SNSDE_ERR_BAD_ARG, "emit %d: slot %d outside [0,%d)", e, emits_host[e].slot, n_out);
 
   cudaStream_t stream = (cudaStream_t)stream_v;
-  CUDA_TRY(cudaSetDevice(p->device));
-  if (p->ev_pending && p->last_stream != stream_v) CUDA_TRY(cudaStreamWaitEvent(stream, p->done_ev, 0));
-  int rc = upload_tables(p, steps_host, S, emits_host, E, stream);
+  DeviceGuard guard(p->device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+  PlanStreamGuard order(p, stream_v);
+  rc = upload_tables(p, steps_host, S, emits_host, E, srk ? points_host : nullptr, stream);
   if (rc != SNSDE_OK) return rc;
-  struct Done {                      // record the completion event on every exit path after this point
-    snsde_plan* p; cudaStream_t st; void* sv;
-    ~Done() { if (p->done_ev && cudaEventRecord(p->done_ev, st) == cudaSuccess) { p->ev_pending = true; p->last_stream = sv; } }
-  } done_guard{p, stream, stream_v};
 
   if (p->kind >= 1) {
     TcForwardArgs a;
@@ -525,43 +678,207 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
   fp.wimg = p->d_wimg; fp.wimg_floats = p->wimg_floats;
   fp.coeffs = coeffs_dev; fp.coeff_row_stride = coeff_row_stride;
   fp.y0 = y0_dev; fp.B = B;
-  fp.steps = p->d_steps; fp.S = S; fp.emits = p->d_emits; fp.n_init_emits = n_init_emits; fp.n_out = n_out;
-  fp.row_slot = row_slot_dev; fp.dW = dW_dev; fp.seed = seed; fp.row_offset = row_offset; fp.out = out_dev;
+  fp.steps = p->d_steps; fp.S = S; fp.points = srk ? p->d_points : nullptr;
+  fp.emits = p->d_emits; fp.n_init_emits = n_init_emits; fp.n_out = n_out;
+  fp.row_slot = row_slot_dev; fp.dW = dW_dev; fp.dU = dU_dev; fp.seed = seed; fp.row_offset = row_offset; fp.out = out_dev;
+  fp.vtab = nullptr;
 
-  const int width = std::max(pg.H, pg.HH);
-  const int nt = std::max(32, (width + 31) & ~31);
-  const int r_max = nt <= 256 ? 16 : 4;
-  int R = 1;
-  while (R < r_max && (B + R - 1) / R > p->num_sms) R *= 2;
-  // stage as much of the weight image as fits beside the activation buffers
-  size_t fixed = fma_smem_bytes(pg, R, 0);
-  while (fixed > (size_t)p->smem_optin && R > 1) { R /= 2; fixed = fma_smem_bytes(pg, R, 0); }
-  if (fixed > (size_t)p->smem_optin) return fail(SNSDE_ERR_UNSUPPORTED, "activation buffers do not fit in shared memory");
-  const int room = (int)((p->smem_optin - fixed) / sizeof(float)) & ~3;
-  fp.smem_w_floats = std::min(p->wimg_floats, room);
-  const size_t smem = fma_smem_bytes(pg, R, fp.smem_w_floats);
-  cudaError_t e = fma_launch(fp, R, nt, smem, stream);
-  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "fma kernel launch (R=%d nt=%d smem=%zu): %s", R, nt, smem, cudaGetErrorString(e));
+  GroupConfig gc;
+  if (!pick_group_config(p, B, fma_group_smem_floats(pg, 4, p->desc.method), fma_group_smem_floats(pg, 8, p->desc.method), !srk, gc))
+    return fail(SNSDE_ERR_UNSUPPORTED, "activation buffers do not fit in shared memory");
+  fp.groups = gc.groups; fp.nw = gc.nw; fp.smem_w_floats = gc.smem_w_floats;
+  if (pg.tail.coef_src == CO_VBUF && S > 0) {
+    const int npg = srk ? kSrkGPoints : 1;
+    rc = ensure_vtab(p, (size_t)S * npg * pg.H);
+    if (rc != SNSDE_OK) return rc;
+    cudaError_t e = vec_tables_launch(pg, p->d_wimg, p->d_steps, fp.points, S, npg, p->d_vtab, stream);
+    if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "coefficient table kernel launch: %s", cudaGetErrorString(e));
+    p->launches += 1;
+    fp.vtab = p->d_vtab;
+  }
+  cudaError_t e = fma_launch(fp, gc.R, p->desc.method, gc.smem, stream);
+  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "fma kernel launch (R=%d nw=%d groups=%d smem=%zu): %s", gc.R, gc.nw, gc.groups, gc.smem, cudaGetErrorString(e));
   p->launches += 1;
   return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+struct BwdLayout {
+  size_t aux = 0, xbuf = 0, gvtab = 0, vtab = 0, total = 0;     // float offsets
+  size_t dbuf[kMaxOps], pbuf[kMaxOps];
+  int n_rops = 0; int rop[kMaxOps];
+  bool has_lipswish = false;
+};
+static BwdLayout bwd_layout(const Program& pg, int B, int S) {
+  BwdLayout L;
+  const size_t SB = (size_t)S * B;
+  auto take = [&](size_t n) { const size_t o = L.total; L.total += (n + 3) & ~(size_t)3; return o; };
+  L.aux = take(SB * 3);
+  L.xbuf = pg.uses_control ? take(SB * pg.C) : 0;
+  L.vtab = take((size_t)S * pg.H);
+  L.gvtab = take((size_t)S * pg.H);
+  bool consumed[kMaxOps] = {false};
+  for (int o = 0; o < pg.n_ops; ++o) {
+    const DenseOp& op = pg.ops[o];
+    if (op.vec) continue;
+    if (op.src_op >= 0) consumed[op.src_op] = true;
+    if (op.src2 >= 0 && op.src2_op >= 0) consumed[op.src2_op] = true;
+    if (op.act == ACT_LIPSWISH) L.has_lipswish = true;
+  }
+  for (int o = 0; o < pg.n_ops; ++o) {
+    const DenseOp& op = pg.ops[o];
+    L.dbuf[o] = L.pbuf[o] = (size_t)-1;
+    if (op.vec) continue;
+    L.rop[L.n_rops++] = o;
+    L.dbuf[o] = take(SB * op.N);
+    if (consumed[o]) L.pbuf[o] = take(SB * op.N);
+  }
+  return L;
+}
+
+int64_t snsde_backward_workspace_bytes(const snsde_plan* p, int32_t B, int32_t S) {
+  SNSDE_API_BEGIN
+  if (!p || !p->has_weights) return fail(SNSDE_ERR_NO_WEIGHTS, "plan has no weights");
+  if (B < 1 || S < 0) return fail(SNSDE_ERR_BAD_ARG, "bad sizes B=%d S=%d", B, S);
+  return (int64_t)(bwd_layout(p->prog, B, S).total * sizeof(float));
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
+}
+
+#define CUBLAS_TRY(expr)                                                                        \
+  do {                                                                                          \
+    cublasStatus_t s__ = (expr);                                                                \
+    if (s__ != CUBLAS_STATUS_SUCCESS) return fail(SNSDE_ERR_CUDA, "%s: cuBLAS status %d", #expr, (int)s__); \
+  } while (0)
+
+int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stride, int32_t n_knots, int32_t B,
+                   const snsde_step* steps_host, int32_t S, const float* states_dev, const float* grad_states_dev,
+                   const float* dW_dev, uint64_t seed, uint64_t row_offset,
+                   float* grad_y0_dev, float* grad_blob_dev, void* workspace_dev, int64_t workspace_bytes,
+                   void* stream_v) {
+  SNSDE_API_BEGIN
+  if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
+  if (!p->has_weights) return fail(SNSDE_ERR_NO_WEIGHTS, "snsde_backward before snsde_plan_set_weights");
+  if (p->desc.method != SNSDE_METHOD_EULER)
+    return fail(SNSDE_ERR_UNSUPPORTED, "the backward pass is implemented for method 'euler' (the reference's training default, neuralsde.py:75)");
+  if (!states_dev || !grad_states_dev || !grad_y0_dev || !grad_blob_dev) return fail(SNSDE_ERR_BAD_ARG, "states/grad_states/grad_y0/grad_blob is NULL");
+  if (B < 1 || S < 0 || (S && !steps_host)) return fail(SNSDE_ERR_BAD_ARG, "bad sizes B=%d S=%d", B, S);
+  const Program& pg = p->prog;
+  int rc = validate_control(pg, coeffs_dev, coeff_row_stride, n_knots);
+  if (rc != SNSDE_OK) return rc;
+  rc = validate_steps(pg, n_knots, steps_host, S);
+  if (rc != SNSDE_OK) return rc;
+  const BwdLayout L = bwd_layout(pg, B, S);
+  if (workspace_bytes < (int64_t)(L.total * sizeof(float)) || (L.total && !workspace_dev))
+    return fail(SNSDE_ERR_BAD_ARG, "workspace has %lld bytes, snsde_backward_workspace_bytes says %lld", (long long)workspace_bytes, (long long)(L.total * sizeof(float)));
+  if ((uintptr_t)workspace_dev & 15) return fail(SNSDE_ERR_BAD_ARG, "workspace must be 16-byte aligned");
+
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  DeviceGuard guard(p->device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+  PlanStreamGuard order(p, stream_v);
+  const int64_t n_w = weight_count(&p->desc);
+  CUDA_TRY(cudaMemsetAsync(grad_blob_dev, 0, sizeof(float) * (size_t)n_w, stream));
+  if (S == 0) {                                       // no step: y_0 is the only state
+    CUDA_TRY(cudaMemcpyAsync(grad_y0_dev, grad_states_dev, sizeof(float) * (size_t)B * pg.H, cudaMemcpyDeviceToDevice, stream));
+    return SNSDE_OK;
+  }
+  rc = upload_tables(p, steps_host, S, nullptr, 0, nullptr, stream);
+  if (rc != SNSDE_OK) return rc;
+  float* ws = (float*)workspace_dev;
+
+  BwdParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.prog = pg;
+  bp.wimg = p->d_wimg; bp.wimg_floats = p->wimg_floats; bp.blob = p->d_blob;
+  bp.coeffs = coeffs_dev; bp.coeff_row_stride = coeff_row_stride;
+  bp.B = B; bp.S = S; bp.steps = p->d_steps;
+  bp.states = states_dev; bp.grad_states = grad_states_dev; bp.dW = dW_dev; bp.seed = seed; bp.row_offset = row_offset;
+  bp.grad_y0 = grad_y0_dev; bp.grad_blob = grad_blob_dev;
+  bp.xbuf = pg.uses_control ? ws + L.xbuf : nullptr;
+  bp.n_rops = L.n_rops; bp.has_lipswish = L.has_lipswish;
+  for (int i = 0; i < L.n_rops; ++i) bp.rop[i] = L.rop[i];
+  for (int o = 0; o < pg.n_ops; ++o) {
+    bp.dbuf[o] = L.dbuf[o] == (size_t)-1 ? nullptr : ws + L.dbuf[o];
+    bp.pbuf[o] = L.pbuf[o] == (size_t)-1 ? nullptr : ws + L.pbuf[o];
+  }
+  const bool vbuf = pg.tail.coef_src == CO_VBUF;
+  if (vbuf) {
+    cudaError_t e = vec_tables_launch(pg, p->d_wimg, p->d_steps, nullptr, S, 1, ws + L.vtab, stream);
+    if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "coefficient table kernel launch: %s", cudaGetErrorString(e));
+    CUDA_TRY(cudaMemsetAsync(ws + L.gvtab, 0, sizeof(float) * (size_t)S * pg.H, stream));
+    bp.vtab = ws + L.vtab; bp.gvtab = ws + L.gvtab;
+    p->launches += 1;
+  }
+  GroupConfig gc;
+  const size_t gf = bwd_group_smem_floats(pg, L.n_rops, 4, L.has_lipswish);
+  if (!pick_group_config(p, B, gf, gf, false, gc))
+    return fail(SNSDE_ERR_UNSUPPORTED, "the backward pass keeps every activation of a step in shared memory: hidden size too large (%zu bytes per row group)", gf * sizeof(float));
+  bp.groups = gc.groups; bp.nw = gc.nw; bp.smem_w_floats = gc.smem_w_floats;
+  cudaError_t e = bwd_fill_aux(p->d_steps, S, B, ws + L.aux, stream);
+  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "aux kernel launch: %s", cudaGetErrorString(e));
+  e = bwd_launch(bp, gc.R, gc.smem, stream);
+  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "reverse-sweep kernel launch (nw=%d groups=%d smem=%zu): %s", gc.nw, gc.groups, gc.smem, cudaGetErrorString(e));
+  p->launches += 2;
+  if (vbuf) {
+    e = vec_bwd_launch(pg, p->d_wimg, p->d_blob, p->d_steps, S, ws + L.gvtab, grad_blob_dev, stream);
+    if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "coefficient-network backward launch: %s", cudaGetErrorString(e));
+    p->launches += 1;
+  }
+
+  // ---- weight gradients: dW[N][K] = D^T P as library GEMMs (row-major operands seen column-major) ----
+  if (!p->cublas) CUBLAS_TRY(cublasCreate(&p->cublas));
+  CUBLAS_TRY(cublasSetStream(p->cublas, stream));
+  CUBLAS_TRY(cublasSetMathMode(p->cublas, CUBLAS_PEDANTIC_MATH));                  // fp32 accumulate, no TF32
+  const int SB = S * B;
+  const float one = 1.f;
+  // C'[K x N] (ldc = ldw: the [N][ldw] blob rows) += P'[K x SB] (lda) * D'[N x SB]^T (ldb = N)
+  auto gemm = [&](const float* P, int lda, int K, const float* D, int N, float* C, int ldc) -> cublasStatus_t {
+    return cublasSgemm(p->cublas, CUBLAS_OP_N, CUBLAS_OP_T, K, N, SB, &one, P, lda, D, N, &one, C, ldc);
+  };
+  for (int i = 0; i < L.n_rops; ++i) {
+    const int o = L.rop[i];
+    const DenseOp& op = pg.ops[o];
+    const float* D = bp.dbuf[o];
+    float* gW = grad_blob_dev + op.g_w;
+    for (int part = 0; part < 2; ++part) {
+      const int src = part == 0 ? op.src : op.src2, src_op = part == 0 ? op.src_op : op.src2_op;
+      const int K = part == 0 ? op.K : op.K2, col = part == 0 ? op.g_col : op.g_col2;
+      if (src < 0) continue;
+      const float* P; int lda;
+      if (src_op == SRC_STATE) { P = states_dev; lda = pg.H; }
+      else if (src_op == SRC_CONTROL) { P = bp.xbuf; lda = pg.C; }
+      else { P = bp.pbuf[src_op]; lda = pg.ops[src_op].N; }
+      CUBLAS_TRY(gemm(P, lda, K, D, op.N, gW + col, op.g_ldw));
+    }
+    if (op.tmode == TM_SINCOS) CUBLAS_TRY(gemm(ws + L.aux, 3, 2, D, op.N, gW, op.g_ldw));
+    if (op.g_b >= 0) CUBLAS_TRY(gemm(ws + L.aux + 2, 3, 1, D, op.N, grad_blob_dev + op.g_b, 1));
+  }
+  return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
 
 int snsde_philox_fill(uint64_t seed, uint64_t row_offset, int32_t S, int32_t B, int32_t H,
-                      const float* sqrt_h_host, float* dW_dev, int device, void* stream_v) {
-  if (S < 0 || B < 1 || H < 1 || !dW_dev || (S && !sqrt_h_host)) return fail(SNSDE_ERR_BAD_ARG, "bad philox_fill arguments");
+                      const snsde_step* steps_host, float* dW_dev, float* dU_dev, int device, void* stream_v) {
+  SNSDE_API_BEGIN
+  if (S < 0 || B < 1 || H < 1 || (!dW_dev && !dU_dev) || (S && !steps_host)) return fail(SNSDE_ERR_BAD_ARG, "bad philox_fill arguments");
   if (S == 0) return SNSDE_OK;
   cudaStream_t stream = (cudaStream_t)stream_v;
-  CUDA_TRY(cudaSetDevice(device));
-  float* d_sq = nullptr;
-  CUDA_TRY(cudaMallocAsync(&d_sq, sizeof(float) * S, stream));
-  CUDA_TRY(cudaMemcpyAsync(d_sq, sqrt_h_host, sizeof(float) * S, cudaMemcpyHostToDevice, stream));
-  const size_t n = (size_t)S * B * H;
-  const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-  philox_fill_kernel<<<grid, 256, 0, stream>>>(seed, row_offset, S, B, H, d_sq, dW_dev);
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(d_sq, stream);
-  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "philox_fill launch: %s", cudaGetErrorString(e));
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err));
+  snsde_step* d_st = nullptr;
+  CUDA_TRY(cudaMallocAsync(&d_st, sizeof(snsde_step) * S, stream));
+  cudaError_t e = cudaMemcpyAsync(d_st, steps_host, sizeof(snsde_step) * S, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) {
+    const size_t n = (size_t)S * B * H;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    philox_fill_kernel<<<grid, 256, 0, stream>>>(seed, row_offset, S, B, H, d_st, dW_dev, dU_dev);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(d_st, stream);
+  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "philox_fill: %s", cudaGetErrorString(e));
   return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
 
 }  // extern "C"

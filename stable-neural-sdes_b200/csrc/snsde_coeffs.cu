@@ -7,6 +7,7 @@
 // One pass, HBM-bound: 4 bytes read (+ neighbours from L1/L2) and 16 bytes written per (row, interval, channel).
 #include <cuda_runtime.h>
 #include "../../include/snsde.h"
+#include "snsde_host.cuh"
 
 namespace snsde {
 
@@ -180,11 +181,16 @@ __global__ void __launch_bounds__(128) fill_missing_kernel(const float* __restri
 
 }  // namespace snsde
 
+using snsde::fail;
+
 extern "C" int snsde_hermite_coeffs(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
                                     float* coeffs_dev, int device, void* stream_v) {
-  if (!x_dev || !knots_dev || !coeffs_dev || B < 1 || K < 2 || C < 1) return SNSDE_ERR_BAD_ARG;
-  if (cudaSetDevice(device) != cudaSuccess) return SNSDE_ERR_CUDA;
-  if ((long long)(K - 1) * C > 0x7fffffffLL || B > 65535 * 64) return SNSDE_ERR_BAD_ARG;
+  SNSDE_API_BEGIN
+  if (!x_dev || !knots_dev || !coeffs_dev) return fail(SNSDE_ERR_BAD_ARG, "hermite_coeffs: x/knots/coeffs is NULL");
+  if (B < 1 || K < 2 || C < 1) return fail(SNSDE_ERR_BAD_ARG, "hermite_coeffs: need B >= 1, K >= 2, C >= 1 (got B=%d K=%d C=%d)", B, K, C);
+  if ((long long)(K - 1) * C > 0x7fffffffLL || B > 65535 * 64) return fail(SNSDE_ERR_BAD_ARG, "hermite_coeffs: tensor too large (B=%d K=%d C=%d)", B, K, C);
+  snsde::DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err));
   const int per_row = (K - 1) * C;
   const int gx = (per_row + 255) / 256 < 64 ? (per_row + 255) / 256 : 64;
   for (int b0 = 0; b0 < B; b0 += 65535) {                                  // gridDim.y limit
@@ -192,28 +198,44 @@ extern "C" int snsde_hermite_coeffs(const float* x_dev, const float* knots_dev, 
     snsde::hermite_coeffs_kernel<<<dim3(gx, nb), 256, 0, (cudaStream_t)stream_v>>>(
         x_dev + (size_t)b0 * K * C, knots_dev, coeffs_dev + (size_t)b0 * (K - 1) * 4 * C, nb, K, C);
   }
-  return cudaGetLastError() == cudaSuccess ? SNSDE_OK : SNSDE_ERR_CUDA;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "hermite_coeffs launch: %s", cudaGetErrorString(e));
+  return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
 
 extern "C" int snsde_natural_coeffs(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
                                     float* coeffs_dev, float* scratch_dev, int device, void* stream_v) {
-  if (!x_dev || !knots_dev || !coeffs_dev || !scratch_dev || B < 1 || K < 2 || C < 1) return SNSDE_ERR_BAD_ARG;
-  if (cudaSetDevice(device) != cudaSuccess) return SNSDE_ERR_CUDA;
-  if ((long long)B * C > 0x7fffffffLL * 128LL) return SNSDE_ERR_BAD_ARG;
+  SNSDE_API_BEGIN
+  if (!x_dev || !knots_dev || !coeffs_dev || !scratch_dev) return fail(SNSDE_ERR_BAD_ARG, "natural_coeffs: x/knots/coeffs/scratch is NULL");
+  if (B < 1 || K < 2 || C < 1) return fail(SNSDE_ERR_BAD_ARG, "natural_coeffs: need B >= 1, K >= 2, C >= 1 (got B=%d K=%d C=%d)", B, K, C);
+  if ((long long)B * C > 0x7fffffffLL * 128LL) return fail(SNSDE_ERR_BAD_ARG, "natural_coeffs: tensor too large");
+  snsde::DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err));
   cudaStream_t st = (cudaStream_t)stream_v;
   float *r = scratch_dev, *cp = scratch_dev + K, *w = scratch_dev + 2 * (size_t)K;
   snsde::natural_knot_sweep_kernel<<<1, 32, 0, st>>>(knots_dev, K, r, cp, w);
   const long long n = (long long)B * C;
   snsde::natural_coeffs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(x_dev, r, cp, w, coeffs_dev, B, K, C);
-  return cudaGetLastError() == cudaSuccess ? SNSDE_OK : SNSDE_ERR_CUDA;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "natural_coeffs launch: %s", cudaGetErrorString(e));
+  return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
 
 extern "C" int snsde_fill_missing(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
                                   float* out_dev, int device, void* stream_v) {
-  if (!x_dev || !knots_dev || !out_dev || B < 1 || K < 1 || C < 1) return SNSDE_ERR_BAD_ARG;
-  if (cudaSetDevice(device) != cudaSuccess) return SNSDE_ERR_CUDA;
+  SNSDE_API_BEGIN
+  if (!x_dev || !knots_dev || !out_dev) return fail(SNSDE_ERR_BAD_ARG, "fill_missing: x/knots/out is NULL");
+  if (B < 1 || K < 1 || C < 1) return fail(SNSDE_ERR_BAD_ARG, "fill_missing: need B, K, C >= 1 (got B=%d K=%d C=%d)", B, K, C);
+  if (x_dev == out_dev) return fail(SNSDE_ERR_BAD_ARG, "fill_missing: out must not alias x");
   const long long n = (long long)B * C;
-  if (n > 0x7fffffffLL * 128LL) return SNSDE_ERR_BAD_ARG;
+  if (n > 0x7fffffffLL * 128LL) return fail(SNSDE_ERR_BAD_ARG, "fill_missing: tensor too large");
+  snsde::DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err));
   snsde::fill_missing_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream_v>>>(x_dev, knots_dev, out_dev, B, K, C);
-  return cudaGetLastError() == cudaSuccess ? SNSDE_OK : SNSDE_ERR_CUDA;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "fill_missing launch: %s", cudaGetErrorString(e));
+  return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }

@@ -25,9 +25,17 @@ struct DenseOp {
   int w_off, w2_off, b_off, tw_off;   // float offsets into the weight image (-1: absent)
   int tmode;                          // TimeMode: tw is [2][N] (sin,cos rows) or [1][N] (raw t)
   int act;
-  int vec;                            // 1: row-independent (one row), 0: per batch row
+  int vec;                            // 1: row-independent (one row per evaluation time: tabulated by the
+                                      //    pre-kernel, snsde_fma.cu vec_tables_kernel), 0: per batch row
   int final_drift;                    // 1: result stays in registers and feeds the SDE update
+  int part;                           // 0: drift f, 1: diffusion g (the SRK stages evaluate them at different states)
+  // ---- backward pass (snsde_bwd.cu): where the op's parameters sit in the flat weight blob, and who feeds it
+  int g_w, g_ldw, g_col, g_col2;      // nn.Linear weight [N][g_ldw] at blob offset g_w; src multiplies columns
+                                      // [g_col, g_col+K), src2 columns [g_col2, g_col2+K2); time features columns [0,2)
+  int g_b;                            // bias offset in the blob (-1: none)
+  int src_op, src2_op;                // op that produced src / src2 (SRC_STATE, SRC_CONTROL for the inputs)
 };
+enum : int { SRC_STATE = -1, SRC_CONTROL = -2, SRC_ABSENT = -3 };
 
 // Elementwise diffusion g (neuralsde.py:233-307) and the state update.
 enum CoefSrc : int { CO_NONE = 0, CO_SCALAR, CO_IMG, CO_VBUF, CO_RBUF };
@@ -51,6 +59,8 @@ struct TailOp {
   int vjp_kind;
   int vjp_w1, vjp_w2; // float offsets of the transposed images [in][out] of noise_y.0 (y columns) / noise_y.2
   int vjp_h1;         // buffer holding relu(noise_y.0(...)) (kind 2)
+  // backward pass: blob offsets of theta / sigma / sigma_diag (-1: absent) and the op producing a CO_RBUF coefficient
+  int g_theta, g_sigma, coef_op;
 };
 
 struct Program {
@@ -62,6 +72,11 @@ struct Program {
   TailOp tail;
 };
 
+// Evaluation points per step: Euler/Milstein evaluate f and g at t0 only; SRK (SRID2) evaluates f at
+// t0 + {0, 1, 1/2} h and g at t0 + {0, 1/4, 1} h.  The point table of an SRK step is [t0, t0+h/4, t0+h/2, t0+h].
+constexpr int kSrkPoints = 4;
+constexpr int kSrkGPoints = 3;            // rows of the row-independent coefficient table per SRK step: t0, t0+h/4, t0+h
+
 struct FmaParams {
   Program prog;
   const float* wimg;          // weight image (global)
@@ -70,11 +85,15 @@ struct FmaParams {
   const float* coeffs; long long coeff_row_stride;
   const float* y0; int B;
   const snsde_step* steps; int S;
+  const snsde_point* points;  // SRK: [S][kSrkPoints]; null otherwise
   const snsde_emit* emits; int n_init_emits; int n_out;
   const int* row_slot;
-  const float* dW;
+  const float* dW; const float* dU;
   unsigned long long seed, row_offset;
+  const float* vtab;          // [S][1 or kSrkGPoints][H] row-independent diffusion coefficient (CO_VBUF), or null
   float* out;
+  int groups;                 // row groups per CTA
+  int nw;                     // warps per row group (32*nw >= max(H, HH))
 };
 
 }  // namespace snsde

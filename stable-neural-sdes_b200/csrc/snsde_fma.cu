@@ -1,146 +1,137 @@
-// fp32 FMA kernel: the whole fixed-step SDE solve for R batch rows per CTA in ONE launch.
+// fp32 FMA kernels: the whole fixed-step SDE solve in ONE launch, for every model / shape / method.
 //
-// Replaces the Python step loop of torchsde.sdeint (BaseSDESolver.integrate + Euler/Milstein
-// .step) together with the per-step Diffusion_model.f/g evaluation
+// Replaces the Python step loop of torchsde.sdeint (BaseSDESolver.integrate + Euler / Milstein / SRK .step)
+// together with the per-step Diffusion_model.f/g evaluation
 // (/root/reference/benchmark_classification/models_sde/neuralsde.py:295-307) and
-// torchcde.CubicSpline.evaluate (:296).  Per step, per CTA:
+// torchcde.CubicSpline.evaluate (:296).
 //
-//   cp.async-prefetched spline row  ->  X(t)        (coalesced 16C-byte rows, double buffered)
-//   program of dense ops            ->  drift pre-activation in registers (thread j = feature j)
-//   row-independent noise nets      ->  computed once per CTA, not once per row
-//   Philox/Box-Muller or table dW   ->  y += f*h + g*dW (+ Milstein term), all in registers
-//   emits                           ->  out[slot] (lerp) or fused final_index capture
-//
-// This is the generic path: any (input_option, noise_option), any H/HH/C/L, and the
-// north star's "warp-shuffle/FMA" path for hidden < 64.  Weights are staged once into shared
-// memory (as much of the image as fits); the rest is read through L2.
+// Work decomposition (the north star's "warp-shuffle/FMA path" for hidden < 64, and the general fallback):
+//   * a ROW GROUP = R batch rows integrated by `nw` warps (thread j of the group = feature j).  A group never
+//     talks to another group: its hand-offs are __syncwarp (nw == 1, hidden <= 32) or one named barrier per
+//     group (bar.sync id, 32*nw) - there is no __syncthreads in the time loop.  A CTA packs several groups that
+//     share one shared-memory copy of the weights;
+//   * R is 4 or 8 and groups start at multiples of 4 rows, so ONE Philox4x32 call per (feature, step) yields the
+//     normals of 4 rows (the stream is keyed by global_row >> 2);
+//   * the row-independent noise networks (noise_t(sin t, cos t), the tutorial's g_net(noise_in(t))) are tabulated
+//     per evaluation time by a pre-kernel (vec_tables_kernel) instead of being evaluated on B identical rows;
+//   * per step: cp.async-prefetched spline rows -> X(t); the dense-op program -> drift pre-activation in
+//     registers; Philox or table increments; the state update; emits (lerp / fused final_index capture).
+//   * METHOD 1 = SRK (torchsde SRK.diagonal_or_scalar_step, SRID2 tableau): 3 drift and 4 diffusion evaluations
+//     per step at the stage states H0_s / H1_s.
 #include <cuda_runtime.h>
 #include <math.h>
 
-#include "snsde_common.cuh"
-#include "snsde_math.cuh"
-#include "snsde_rng.cuh"
+#include <algorithm>
+
+#include "snsde_fma.cuh"
 
 namespace snsde {
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-struct SmemMap {
-  float* base;           // [row bufs: kNumRowBufs x R x ld][vec bufs: kNumVecBufs x ld]
-  int row_buf_floats;    // R * ld
-  int ld;
-  float* stage0;         // 2 spline stages of stage_floats each
-  int stage_floats;
-  const float* w;        // staged weights (first smem_w_floats of the image)
-  __device__ __forceinline__ float* buf(int id) const {
-    return id < kNumRowBufs ? base + id * row_buf_floats
-                            : base + kNumRowBufs * row_buf_floats + (id - kNumRowBufs) * ld;
+// ---- row-independent coefficient table ------------------------------------------------------------
+// One CTA per (step, evaluation time): runs the program's vec ops on that single "row" and stores the final
+// coefficient vector.  The reference evaluates these networks on B identical rows (neuralsde.py:281-282).
+__global__ void __launch_bounds__(1024) vec_tables_kernel(const Program pg, const float* __restrict__ wimg,
+                                                          const snsde_step* __restrict__ steps,
+                                                          const snsde_point* __restrict__ points, int npg,
+                                                          float* __restrict__ vtab) {
+  extern __shared__ __align__(16) float vsm[];          // [kNumVecBufs][ld]
+  const int s = blockIdx.x / npg, q = blockIdx.x - s * npg, j = threadIdx.x, ld = pg.ld;
+  TimePoint tp;
+  if (points != nullptr) {
+    const snsde_point pt = points[s * kSrkPoints + (q == 0 ? 0 : (q == 1 ? 1 : 3))];
+    tp.t = pt.t; tp.sin_t = pt.sin_t; tp.cos_t = pt.cos_t;
+  } else {
+    const snsde_step st = steps[s];
+    tp.t = st.t0; tp.sin_t = st.sin_t0; tp.cos_t = st.cos_t0;
   }
-  __device__ __forceinline__ float* stage(int i) const { return stage0 + (i & 1) * stage_floats; }
-};
-
-// acc[r] += sum_k src[r][k] * Wt[k][j]
-template <int ROWS>
-__device__ __forceinline__ void dot_accumulate(float (&acc)[ROWS], const float* __restrict__ src, int ld,
-                                               const float* __restrict__ wt, int K, int N, int j) {
-  const float* w = wt + j;
-  int k = 0;
-  const int K4 = K & ~3;
-  for (; k < K4; k += 4) {
-    const float w0 = w[(size_t)k * N], w1 = w[(size_t)(k + 1) * N];
-    const float w2 = w[(size_t)(k + 2) * N], w3 = w[(size_t)(k + 3) * N];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const float4 a = *reinterpret_cast<const float4*>(src + r * ld + k);
-      acc[r] = fmaf(a.x, w0, acc[r]);
-      acc[r] = fmaf(a.y, w1, acc[r]);
-      acc[r] = fmaf(a.z, w2, acc[r]);
-      acc[r] = fmaf(a.w, w3, acc[r]);
+  for (int o = 0; o < pg.n_ops; ++o) {
+    const DenseOp& op = pg.ops[o];
+    if (!op.vec) continue;
+    if (j < op.N) {
+      float v = op.b_off >= 0 ? wimg[op.b_off + j] : 0.f;
+      if (op.tmode == TM_SINCOS) v = fmaf(tp.cos_t, wimg[op.tw_off + op.N + j], fmaf(tp.sin_t, wimg[op.tw_off + j], v));
+      else if (op.tmode == TM_RAW) v = fmaf(tp.t, wimg[op.tw_off + j], v);
+      if (op.src >= 0) {
+        const float* src = vsm + (op.src - BUF_V0) * ld;
+        const float* w = wimg + op.w_off + j;
+        for (int k = 0; k < op.K; ++k) v = fmaf(src[k], w[(size_t)k * op.N], v);
+      }
+      vsm[(op.dst - BUF_V0) * ld + j] = act_apply(v, op.act);
     }
+    __syncthreads();
   }
-  for (; k < K; ++k) {
-    const float wk = w[(size_t)k * N];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(src[r * ld + k], wk, acc[r]);
-  }
+  if (j < pg.H) vtab[(size_t)blockIdx.x * pg.H + j] = vsm[(pg.tail.coef_ref - BUF_V0) * ld + j];
 }
 
-// acc[r] += sum_k src[r][k] * wrow[k]   - the TRANSPOSED product: thread j walks row j of an [in][out] image
-// (contiguous), used by the Milstein vjp through the noise network; read through L1/L2 (a shared-memory copy
-// would be 32-way bank conflicted at this access pattern).
-template <int ROWS>
-__device__ __forceinline__ void dot_rows_T(float (&acc)[ROWS], const float* __restrict__ src, int ld,
-                                           const float* __restrict__ wrow, int K) {
-  for (int k = 0; k < K; ++k) {
-    const float wk = __ldg(wrow + k);
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(src[r * ld + k], wk, acc[r]);
-  }
-}
-
-template <int ROWS>
-__device__ __forceinline__ void dense_eval(float (&acc)[ROWS], const DenseOp& op, const FmaParams& p,
-                                           const SmemMap& sm, const snsde_step& st, int j) {
-  const int ld = p.prog.ld;
-  auto wptr = [&](int off, int count) -> const float* {
-    return (off + count <= p.smem_w_floats) ? sm.w + off : p.wimg + off;
-  };
-  float init = op.b_off >= 0 ? wptr(op.b_off, op.N)[j] : 0.f;
-  if (op.tmode == TM_SINCOS) {
-    const float* tw = wptr(op.tw_off, 2 * op.N);
-    init = fmaf(st.cos_t0, tw[op.N + j], fmaf(st.sin_t0, tw[j], init));
-  } else if (op.tmode == TM_RAW) {
-    init = fmaf(st.t0, wptr(op.tw_off, op.N)[j], init);
-  }
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r) acc[r] = init;
-  if (op.src >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src), ld, wptr(op.w_off, op.K * op.N), op.K, op.N, j);
-  if (op.src2 >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src2), ld, wptr(op.w2_off, op.K2 * op.N), op.K2, op.N, j);
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r) acc[r] = act_apply(acc[r], op.act);
-}
-
-template <int R, int NTMAX>
+// ---- the solve ---------------------------------------------------------------------------------------
+template <int R, int NTMAX, int METHOD>
 __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
   extern __shared__ __align__(16) float smem[];
   const Program& pg = p.prog;
-  const int tid = threadIdx.x, NT = blockDim.x;
+  const TailOp& t = pg.tail;
   const int H = pg.H, C = pg.C, ld = pg.ld;
-  const int row0 = blockIdx.x * R;
+  const int nw = p.nw, GT = nw * 32;                        // threads per group
+  const int gid = threadIdx.x / GT, tid = threadIdx.x - gid * GT;
+  constexpr int NP = METHOD == 1 ? 3 : 1;                   // drift evaluation points per step
+  constexpr int NPG = METHOD == 1 ? kSrkGPoints : 1;
 
-  // ---- shared memory carve-up: [row bufs][vec bufs][2 spline stages][weights] ----
-  SmemMap sm;
-  {
-    sm.base = smem;
-    sm.row_buf_floats = R * ld;
-    sm.ld = ld;
-    sm.stage0 = smem + kNumRowBufs * R * ld + kNumVecBufs * ld;
-    sm.stage_floats = pg.uses_control ? R * 4 * C : 0;
-    float* w = sm.stage0 + 2 * sm.stage_floats;
-    for (int i = tid; i < p.smem_w_floats; i += NT) w[i] = p.wimg[i];
-    sm.w = w;
-  }
+  // ---- shared memory: [weights][group 0: row bufs, spline stages][group 1 ...] ----
+  const int stage_floats = pg.uses_control ? R * 4 * C : 0;
+  const int group_floats = kNumRowBufs * R * ld + 2 * NP * stage_floats;
+  for (int i = threadIdx.x; i < p.smem_w_floats; i += blockDim.x) smem[i] = p.wimg[i];
+  __syncthreads();                                          // the only CTA-wide barrier
+  GroupSmem sm;
+  sm.w = smem;
+  sm.base = smem + p.smem_w_floats + gid * group_floats;
+  sm.row_buf_floats = R * ld;
+  sm.stage0 = sm.base + kNumRowBufs * R * ld;
+  sm.stage_floats = stage_floats;
+
+  const int row0 = (blockIdx.x * p.groups + gid) * R;
+  if (row0 >= p.B) return;                                  // whole group idle (groups never sync with each other)
   float* const sY = sm.buf(BUF_Y);
   float* const sX = sm.buf(BUF_X);
   auto grow = [&](int r) { return min(row0 + r, p.B - 1); };   // clamped row (local to this shard)
+  auto gsync = [&]() { group_sync(gid, nw); };
 
+  // which interval a drift evaluation point reads: Euler/Milstein -> the step's own; SRK -> points 0, 3, 2
+  auto f_point = [&](int s, int i, TimePoint& tp, int& interval, float& frac) {
+    if (METHOD == 1) {
+      const snsde_point pt = p.points[s * kSrkPoints + (i == 0 ? 0 : (i == 1 ? 3 : 2))];
+      tp.t = pt.t; tp.sin_t = pt.sin_t; tp.cos_t = pt.cos_t; interval = pt.interval; frac = pt.frac;
+    } else {
+      const snsde_step st = p.steps[s];
+      tp.t = st.t0; tp.sin_t = st.sin_t0; tp.cos_t = st.cos_t0; interval = st.interval; frac = st.frac;
+    }
+  };
+  auto stage_buf = [&](int s, int i) { return sm.stage0 + (((s & 1) * NP) + i) * stage_floats; };
   auto prefetch_spline = [&](int s) {
     if (!pg.uses_control || s >= p.S) return;
-    const int interval = p.steps[s].interval;
-    float* dst = sm.stage(s);
-    for (int i = tid; i < R * C; i += NT) {
-      const int r = i / C, q = i - r * C;
-      const float* src = p.coeffs + (size_t)grow(r) * p.coeff_row_stride + (size_t)interval * 4 * C + 4 * q;
-      cp_async16(dst + r * 4 * C + 4 * q, src);
+    for (int i = 0; i < NP; ++i) {
+      TimePoint tp; int interval; float frac;
+      f_point(s, i, tp, interval, frac);
+      float* dst = stage_buf(s, i);
+      for (int q = tid; q < R * C; q += GT) {
+        const int r = q / C, c = q - r * C;
+        const float* src = p.coeffs + (size_t)grow(r) * p.coeff_row_stride + (size_t)interval * 4 * C + 4 * c;
+        cp_async16(dst + r * 4 * C + 4 * c, src);
+      }
     }
     cp_async_commit();
   };
   prefetch_spline(0);
+
+  // X(t) of drift point i of step s: a + (b + (two_c/2 + three_d*frac/3)*frac)*frac  (torchcde op order)
+  auto eval_control = [&](int s, int i, float frac) {
+    const float* stg = stage_buf(s, i);
+    for (int q = tid; q < R * C; q += GT) {
+      const int r = q / C, c = q - r * C;
+      const float* row = stg + r * 4 * C;
+      float inner = 0.5f * row[2 * C + c] + __fdiv_rn(row[3 * C + c] * frac, 3.0f);
+      inner = row[C + c] + inner * frac;
+      sX[r * ld + c] = row[c] + inner * frac;
+    }
+  };
 
   // ---- state in registers: thread j owns y[.][j] ----
   const bool jact = tid < H;
@@ -173,167 +164,299 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
     emit(em);
   }
 
+  // Runs the per-row ops of one part (0 drift, 1 diffusion, 2 both) on the state currently in sY (and sX);
+  // the drift pre-activation stays in `acc`.  Every op is preceded by a group hand-off.
+  float acc[R];
+  auto run_ops = [&](int part, const TimePoint& tp) {
+    for (int o = 0; o < pg.n_ops; ++o) {
+      const DenseOp& op = pg.ops[o];
+      if (op.vec || (part != 2 && op.part != part)) continue;
+      gsync();                              // op o reads what an earlier op (or the state writer) wrote
+      if (tid < op.N) {
+        if (op.final_drift) {
+          dense_eval<R>(acc, op, p.wimg, sm.w, p.smem_w_floats, sm, ld, tp, tid);
+        } else {
+          float a[R];
+          dense_eval<R>(a, op, p.wimg, sm.w, p.smem_w_floats, sm, ld, tp, tid);
+          float* dst = sm.buf(op.dst);
+#pragma unroll
+          for (int r = 0; r < R; ++r) dst[r * ld + tid] = a[r];
+        }
+      }
+    }
+    if (part != 0 && t.coef_src == CO_RBUF) gsync();       // the tail reads the coefficient buffer
+  };
+  auto drift_value = [&](float d, float ycur) {
+    if (t.geometric) d = d * tanhf(ycur);
+    if (t.clip_drift) d = tanhf(d);
+    return d;
+  };
+  // coefficient entering the elementwise diffusion for row r (table / image / scalar / per-row network output)
+  auto coef_of = [&](int r, float vcoef) {
+    return t.coef_src == CO_RBUF ? sm.buf(t.coef_ref)[r * ld + tid] : vcoef;
+  };
+  auto vcoef_at = [&](int s, int q) {
+    float v = t.coef_scalar;
+    if (t.coef_src == CO_IMG) v = p.wimg[t.coef_ref + tid];
+    else if (t.coef_src == CO_VBUF) v = p.vtab[((size_t)s * NPG + q) * H + tid];
+    return v;
+  };
+  // Brownian increment (and, for SRK, the space-time Levy integral U) of row r at step s
+  float nrm[4], nrmu[4];
+  auto draw = [&](int s, int r, float h, float sqrt_h, float& w, float& u) {
+    if (p.dW != nullptr) {
+      w = p.dW[((size_t)s * p.B + grow(r)) * H + tid];
+      u = (METHOD == 1) ? p.dU[((size_t)s * p.B + grow(r)) * H + tid] : 0.f;
+      return;
+    }
+    const unsigned long long gb = p.row_offset + (unsigned long long)(row0 + r);
+    if (r == 0 || (gb & 3ull) == 0ull) {
+      philox_normals4(p.seed, (uint32_t)tid, (uint32_t)(gb >> 2), (uint32_t)s, nrm);
+      if (METHOD == 1) philox_normals4_u(p.seed, (uint32_t)tid, (uint32_t)(gb >> 2), (uint32_t)s, nrmu);
+    }
+    w = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), sqrt_h);
+    u = (METHOD == 1) ? levy_U(w, pick4(nrmu, (int)(gb & 3ull)), h, sqrt_h) : 0.f;
+  };
+
   for (int s = 0; s < p.S; ++s) {
     const snsde_step st = p.steps[s];
 
-    // explicit increments (parity mode): issue the loads now, consume at the end of the step
-    float dw[R];
-    if (p.dW != nullptr && jact) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) dw[r] = p.dW[((size_t)s * p.B + grow(r)) * H + tid];
-    }
+    if (METHOD == 0) {
+      // =============================== Euler / Milstein ===============================================
+      TimePoint tp{st.t0, st.sin_t0, st.cos_t0};
+      float vcoef = 0.f;
+      if (jact) vcoef = vcoef_at(s, 0);                       // issued early: consumed after the dense program
+      if (pg.uses_control) {
+        cp_async_wait_all();
+        gsync();
+        eval_control(s, 0, st.frac);
+        prefetch_spline(s + 1);
+      }
+      run_ops(2, tp);
 
-    // ---- control path X(t0): a + (b + (two_c/2 + three_d*frac/3)*frac)*frac ----
-    if (pg.uses_control) {
-      cp_async_wait_all();
-      __syncthreads();
-      const float* stg = sm.stage(s);
-      for (int i = tid; i < R * C; i += NT) {
-        const int r = i / C, c = i - r * C;
-        const float* row = stg + r * 4 * C;
-        float inner = 0.5f * row[2 * C + c] + __fdiv_rn(row[3 * C + c] * st.frac, 3.0f);
-        inner = row[C + c] + inner * st.frac;
-        sX[r * ld + c] = row[c] + inner * st.frac;
-      }
-      prefetch_spline(s + 1);
-    }
-    __syncthreads();
-
-    // ---- dense program ----
-    float acc[R];
-    for (int o = 0; o < pg.n_ops; ++o) {
-      const DenseOp& op = pg.ops[o];
-      if (o > 0) __syncthreads();      // op o reads what op o-1 wrote (dst != src by construction)
-      if (tid < op.N) {
-        if (op.vec) {
-          float a1[1];
-          dense_eval<1>(a1, op, p, sm, st, tid);
-          sm.buf(op.dst)[tid] = a1[0];
-        } else {
-          dense_eval<R>(acc, op, p, sm, st, tid);
-          if (!op.final_drift) {
-            float* dst = sm.buf(op.dst);
-#pragma unroll
-            for (int r = 0; r < R; ++r) dst[r * ld + tid] = acc[r];
-          }
-        }
-      }
-    }
-
-    // ---- SDE update (torchsde Euler.step / Milstein.step) ----
-    const TailOp& t = pg.tail;
-    const bool net_vjp = t.milstein && t.vjp_kind != 0;       // block-uniform
-    float* const sA = sm.buf(BUF_X);                            // scratch of the vjp (dead since the first ops)
-    float* const sB = sm.buf(BUF_U);
-    if (jact) {
-      float vcoef = t.coef_scalar;
-      if (t.coef_src == CO_IMG) vcoef = p.wimg[t.coef_ref + tid];
-      else if (t.coef_src == CO_VBUF) vcoef = sm.buf(t.coef_ref)[tid];
-      const float* rcoef = (t.coef_src == CO_RBUF) ? sm.buf(t.coef_ref) : nullptr;
-      float nrm[4];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float d = acc[r];
-        if (t.geometric) d = d * tanhf(y[r]);
-        if (t.clip_drift) d = tanhf(d);
-        const float coef = rcoef ? rcoef[r * ld + tid] : vcoef;
-        float g, dgdy;
-        diffusion_eval<false>(t, coef, y[r], st.t0, g, dgdy);
-        float w;
-        if (p.dW != nullptr) {
-          w = dw[r];
-        } else {
-          const unsigned long long gb = p.row_offset + (unsigned long long)(row0 + r);
-          if (r == 0 || (gb & 3ull) == 0ull) philox_normals4(p.seed, (uint32_t)tid, (uint32_t)(gb >> 2), (uint32_t)s, nrm);
-          w = __fmul_rn(pick4(nrm, (int)(gb & 3ull)), st.sqrt_h);
-        }
-        float yn = __fadd_rn(__fadd_rn(y[r], __fmul_rn(d, st.h)), __fmul_rn(g, w));
-        if (t.milstein) {
-          const float v = __fmul_rn(w, w) - st.h;
-          yn = __fadd_rn(yn, 0.5f * ((g * v) * dgdy));          // direct (diagonal) part of d g_j / d y_j
-          if (net_vjp) {
-            // cotangent reaching q_j:  (g v) * tanh' * s_theta * [nan_to_num passes] * d raw / d q  (* relu' for kind 2)
-            const float raw = (t.mult == MU_Y) ? coef * y[r] : coef;
-            float a = (g * v) * ((1.f - g * g) * t.s_theta) * (is_finite_f(raw) ? 1.f : 0.f);
-            if (t.mult == MU_Y) a *= y[r];
-            if (t.vjp_kind == 2 && !(coef > 0.f)) a = 0.f;
-            sA[r * ld + tid] = a;
-          }
-        }
-        yprev[r] = y[r];
-        y[r] = yn;
-        if (!net_vjp) sY[r * ld + tid] = yn;
-      }
-    }
-    if (net_vjp) {
-      // torchsde: + 0.5 * vjp_y(g; g * (dW^2 - h)); the path through noise_y is W1y^T [relu'] W2^T [relu'] a
-      __syncthreads();
-      const float* src = sA;
-      if (t.vjp_kind == 2) {
-        if (jact) {
-          float b[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) b[r] = 0.f;
-          dot_rows_T<R>(b, sA, ld, p.wimg + t.vjp_w2 + (size_t)tid * H, H);
-          const float* h1 = sm.buf(t.vjp_h1);
-#pragma unroll
-          for (int r = 0; r < R; ++r) sB[r * ld + tid] = (h1[r * ld + tid] > 0.f) ? b[r] : 0.f;
-        }
-        __syncthreads();
-        src = sB;
-      }
+      const bool net_vjp = t.milstein && t.vjp_kind != 0;       // block-uniform
+      float* const sA = sm.buf(BUF_X);                            // scratch of the vjp (dead since the first ops)
+      float* const sB = sm.buf(BUF_U);
       if (jact) {
-        float c[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) c[r] = 0.f;
-        dot_rows_T<R>(c, src, ld, p.wimg + t.vjp_w1 + (size_t)tid * H, H);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          y[r] = __fadd_rn(y[r], 0.5f * c[r]);
-          sY[r * ld + tid] = y[r];
+          const float d = drift_value(acc[r], y[r]);
+          const float coef = coef_of(r, vcoef);
+          float g, dgdy;
+          diffusion_eval<false>(t, coef, y[r], st.t0, g, dgdy);
+          float w, u;
+          draw(s, r, st.h, st.sqrt_h, w, u);
+          float yn = __fadd_rn(__fadd_rn(y[r], __fmul_rn(d, st.h)), __fmul_rn(g, w));
+          if (t.milstein) {
+            const float v = __fmul_rn(w, w) - st.h;
+            yn = __fadd_rn(yn, 0.5f * ((g * v) * dgdy));          // direct (diagonal) part of d g_j / d y_j
+            if (net_vjp) {
+              // cotangent reaching q_j:  (g v) * tanh' * s_theta * [nan_to_num passes] * d raw / d q  (* relu' for kind 2)
+              const float raw = (t.mult == MU_Y) ? coef * y[r] : coef;
+              float a = (g * v) * ((1.f - g * g) * t.s_theta) * (is_finite_f(raw) ? 1.f : 0.f);
+              if (t.mult == MU_Y) a *= y[r];
+              if (t.vjp_kind == 2 && !(coef > 0.f)) a = 0.f;
+              sA[r * ld + tid] = a;
+            }
+          }
+          yprev[r] = y[r];
+          y[r] = yn;
+          if (!net_vjp) sY[r * ld + tid] = yn;
         }
+      }
+      if (net_vjp) {
+        // torchsde: + 0.5 * vjp_y(g; g * (dW^2 - h)); the path through noise_y is W1y^T [relu'] W2^T [relu'] a
+        gsync();
+        const float* src = sA;
+        if (t.vjp_kind == 2) {
+          if (jact) {
+            float b[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) b[r] = 0.f;
+            dot_rows_T<R>(b, sA, ld, p.wimg + t.vjp_w2 + (size_t)tid * H, H);
+            const float* h1 = sm.buf(t.vjp_h1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) sB[r * ld + tid] = (h1[r * ld + tid] > 0.f) ? b[r] : 0.f;
+          }
+          gsync();
+          src = sB;
+        }
+        if (jact) {
+          float c[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) c[r] = 0.f;
+          dot_rows_T<R>(c, src, ld, p.wimg + t.vjp_w1 + (size_t)tid * H, H);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            y[r] = __fadd_rn(y[r], 0.5f * c[r]);
+            sY[r * ld + tid] = y[r];
+          }
+        }
+      }
+    } else {
+      // =============================== SRK (SRID2, diagonal noise) ====================================
+      // torchsde SRK.diagonal_or_scalar_step; tableau (tableaus/srid2.py, Roessler 2010 SRI2):
+      //   C0 = (0, 1, 1/2, 0)   A0 = [[], [1], [1/4, 1/4], [0, 0, 0]]      B0 = [[], [0], [1, 1/2], [0, 0, 0]]
+      //   C1 = (0, 1/4, 1, 1/4) A1 = [[], [1/4], [1, 0], [0, 0, 1/4]]      B1 = [[], [-1/2], [1, 0], [2, -1, 1/2]]
+      //   alpha = (1/6, 1/6, 2/3, 0)   beta1 = (-1, 4/3, 2/3, 0)   beta2 = (1, -4/3, 1/3, 0)
+      //   beta3 = (2, -4/3, -2/3, 0)   beta4 = (-2, 5/3, -2/3, 1)
+      // Stage 3 of the drift (H0_3 = y0, alpha_3 = 0) contributes nothing and is skipped.
+      const float h = st.h, sqrt_h = st.sqrt_h, rdt = __fdiv_rn(1.0f, h);
+      const snsde_point* pts = p.points + s * kSrkPoints;
+      TimePoint tp0{pts[0].t, pts[0].sin_t, pts[0].cos_t}, tpq{pts[1].t, pts[1].sin_t, pts[1].cos_t};
+      TimePoint tph{pts[2].t, pts[2].sin_t, pts[2].cos_t}, tp1{pts[3].t, pts[3].sin_t, pts[3].cos_t};
+      float vc0 = 0.f, vcq = 0.f, vc1 = 0.f;
+      if (jact) { vc0 = vcoef_at(s, 0); vcq = vcoef_at(s, 1); vc1 = vcoef_at(s, 2); }
+      float y0r[R], w[R], ik0[R], f0[R], g0[R], f1[R], g1[R], f2[R], g2[R], tmp[R];
+      const bool per_row_g = t.coef_src == CO_RBUF;
+      if (pg.uses_control) { cp_async_wait_all(); gsync(); eval_control(s, 0, pts[0].frac); }
+      // stage 0: f0 = f(t0, y0), g0 = g(t0, y0)            (sY holds y0)
+      run_ops(2, tp0);
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          y0r[r] = y[r];
+          float u, dg;
+          draw(s, r, h, sqrt_h, w[r], u);
+          ik0[r] = u;
+          f0[r] = drift_value(acc[r], y[r]);
+          diffusion_eval<false>(t, coef_of(r, vc0), y[r], tp0.t, g0[r], dg);
+        }
+      }
+      // stage 1: H0_1 = y0 + f0 h (+ 0 g0 I_k0/h);  H1_1 = y0 + f0 h/4 - g0 sqrt(h)/2
+      gsync();
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          sY[r * ld + tid] = y0r[r] + (1.0f * f0[r]) * h + ((0.0f * g0[r]) * ik0[r]) * rdt;
+          tmp[r] = y0r[r] + (0.25f * f0[r]) * h + (-0.5f * g0[r]) * sqrt_h;
+        }
+      }
+      if (pg.uses_control) { gsync(); eval_control(s, 1, pts[3].frac); }
+      run_ops(0, tp1);                                       // f1 = f(t0 + h, H0_1)
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) f1[r] = drift_value(acc[r], sY[r * ld + tid]);
+      }
+      gsync();
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) sY[r * ld + tid] = tmp[r];
+      }
+      if (per_row_g) run_ops(1, tpq);                        // g1 = g(t0 + h/4, H1_1)
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { float dg; diffusion_eval<false>(t, coef_of(r, vcq), tmp[r], tpq.t, g1[r], dg); }
+      }
+      // stage 2: H0_2 = y0 + f0 h/4 + g0 I_k0/h + f1 h/4 + g1 I_k0/(2h);  H1_2 = y0 + f0 h + g0 sqrt(h) (+ 0 f1 h + 0 g1 sqrt(h))
+      gsync();
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float a = y0r[r] + (0.25f * f0[r]) * h + ((1.0f * g0[r]) * ik0[r]) * rdt;
+          a = a + (0.25f * f1[r]) * h + ((0.5f * g1[r]) * ik0[r]) * rdt;
+          sY[r * ld + tid] = a;
+          float b = y0r[r] + (1.0f * f0[r]) * h + (1.0f * g0[r]) * sqrt_h;
+          b = b + (0.0f * f1[r]) * h + (0.0f * g1[r]) * sqrt_h;
+          tmp[r] = b;
+        }
+      }
+      if (pg.uses_control) { gsync(); eval_control(s, 2, pts[2].frac); prefetch_spline(s + 1); }
+      run_ops(0, tph);                                       // f2 = f(t0 + h/2, H0_2)
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) f2[r] = drift_value(acc[r], sY[r * ld + tid]);
+      }
+      gsync();
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) sY[r * ld + tid] = tmp[r];
+      }
+      if (per_row_g) run_ops(1, tp1);                        // g2 = g(t0 + h, H1_2)
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { float dg; diffusion_eval<false>(t, coef_of(r, vc1), tmp[r], tp1.t, g2[r], dg); }
+      }
+      // stage 3: H1_3 = y0 (+0 f0 h) + 2 g0 sqrt(h) (+0 f1 h) - g1 sqrt(h) + f2 h/4 + g2 sqrt(h)/2
+      gsync();
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float b = y0r[r] + (0.0f * f0[r]) * h + (2.0f * g0[r]) * sqrt_h;
+          b = b + (0.0f * f1[r]) * h + (-1.0f * g1[r]) * sqrt_h;
+          b = b + (0.25f * f2[r]) * h + (0.5f * g2[r]) * sqrt_h;
+          tmp[r] = b;
+          sY[r * ld + tid] = b;
+        }
+      }
+      if (per_row_g) run_ops(1, tpq);                        // g3 = g(t0 + h/4, H1_3)
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float g3, dg;
+          diffusion_eval<false>(t, coef_of(r, vcq), tmp[r], tpq.t, g3, dg);
+          const float I_k = w[r];
+          const float I_kk = (I_k * I_k - h) * 0.5f;
+          const float I_kkk = (I_k * I_k * I_k - 3.0f * h * I_k) * (1.0f / 6.0f);
+          const float a0 = I_kk / sqrt_h, a1 = ik0[r] * rdt, a2 = I_kkk * rdt;
+          const float gw0 = -1.0f * I_k + 1.0f * a0 + 2.0f * a1 + -2.0f * a2;
+          const float gw1 = (4.0f / 3.0f) * I_k + (-4.0f / 3.0f) * a0 + (-4.0f / 3.0f) * a1 + (5.0f / 3.0f) * a2;
+          const float gw2 = (2.0f / 3.0f) * I_k + (1.0f / 3.0f) * a0 + (-2.0f / 3.0f) * a1 + (-2.0f / 3.0f) * a2;
+          const float gw3 = a2;
+          float yn = y0r[r] + ((1.0f / 6.0f) * f0[r]) * h + gw0 * g0[r];
+          yn = yn + ((1.0f / 6.0f) * f1[r]) * h + gw1 * g1[r];
+          yn = yn + ((2.0f / 3.0f) * f2[r]) * h + gw2 * g2[r];
+          yn = yn + gw3 * g3;
+          yprev[r] = y0r[r];
+          y[r] = yn;
+        }
+      }
+      if (jact) {                                            // (every reader of sY is behind a hand-off by now)
+#pragma unroll
+        for (int r = 0; r < R; ++r) sY[r * ld + tid] = y[r];
       }
     }
     for (int e = st.emit_begin; e < st.emit_end; ++e) emit(p.emits[e]);
   }
 }
 
-// ---- host-side launcher --------------------------------------------------------------------
+// ---- host-side launchers -----------------------------------------------------------------------
 
-size_t fma_smem_bytes(const Program& pg, int R, int smem_w_floats) {
-  size_t f = (size_t)kNumRowBufs * R * pg.ld + (size_t)kNumVecBufs * pg.ld;
-  if (pg.uses_control) f += (size_t)2 * R * 4 * pg.C;
-  f += smem_w_floats;
-  return f * sizeof(float);
+size_t fma_group_smem_floats(const Program& pg, int R, int method) {
+  const int np = method == SNSDE_METHOD_SRK ? 3 : 1;
+  size_t f = (size_t)kNumRowBufs * R * pg.ld;
+  if (pg.uses_control) f += (size_t)2 * np * R * 4 * pg.C;
+  return f;
 }
 
-template <int R, int NTMAX>
+template <int R, int NTMAX, int METHOD>
 static cudaError_t launch_one(const FmaParams& p, int grid, int nt, size_t smem, cudaStream_t stream) {
-  auto kern = snsde_fma_kernel<R, NTMAX>;
+  auto kern = snsde_fma_kernel<R, NTMAX, METHOD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, nt, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t fma_launch(const FmaParams& p, int R, int nt, size_t smem, cudaStream_t stream) {
-  const int grid = (p.B + R - 1) / R;
-  if (nt <= 256) {
-    switch (R) {
-      case 1: return launch_one<1, 256>(p, grid, nt, smem, stream);
-      case 2: return launch_one<2, 256>(p, grid, nt, smem, stream);
-      case 4: return launch_one<4, 256>(p, grid, nt, smem, stream);
-      case 8: return launch_one<8, 256>(p, grid, nt, smem, stream);
-      case 16: return launch_one<16, 256>(p, grid, nt, smem, stream);
-    }
-  } else {
-    switch (R) {
-      case 1: return launch_one<1, 1024>(p, grid, nt, smem, stream);
-      case 2: return launch_one<2, 1024>(p, grid, nt, smem, stream);
-      case 4: return launch_one<4, 1024>(p, grid, nt, smem, stream);
-    }
+cudaError_t fma_launch(const FmaParams& p, int R, int method, size_t smem, cudaStream_t stream) {
+  const int nt = p.groups * p.nw * 32;
+  const int n_groups = (p.B + R - 1) / R;
+  const int grid = (n_groups + p.groups - 1) / p.groups;
+  const bool srk = method == SNSDE_METHOD_SRK;
+  if (nt <= 512) {
+    if (R == 8) return srk ? launch_one<8, 512, 1>(p, grid, nt, smem, stream) : launch_one<8, 512, 0>(p, grid, nt, smem, stream);
+    if (R == 4) return srk ? launch_one<4, 512, 1>(p, grid, nt, smem, stream) : launch_one<4, 512, 0>(p, grid, nt, smem, stream);
+  } else if (R == 4) {
+    return srk ? launch_one<4, 1024, 1>(p, grid, nt, smem, stream) : launch_one<4, 1024, 0>(p, grid, nt, smem, stream);
   }
   return cudaErrorInvalidValue;
+}
+
+cudaError_t vec_tables_launch(const Program& pg, const float* wimg, const snsde_step* steps, const snsde_point* points,
+                              int S, int npg, float* vtab, cudaStream_t stream) {
+  const int nt = std::max(32, (std::max(pg.H, pg.HH) + 31) & ~31);
+  vec_tables_kernel<<<S * npg, nt, sizeof(float) * kNumVecBufs * pg.ld, stream>>>(pg, wimg, steps, points, npg, vtab);
+  return cudaGetLastError();
 }
 
 }  // namespace snsde

@@ -1,0 +1,99 @@
+// Device helpers shared by the fp32 FMA forward kernels (snsde_fma.cu) and the reverse sweep (snsde_bwd.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "snsde_common.cuh"
+#include "snsde_math.cuh"
+#include "snsde_rng.cuh"
+
+namespace snsde {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Hand-off inside one row group.
+__device__ __forceinline__ void group_sync(int gid, int nw) {
+  if (nw == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(nw * 32) : "memory");
+}
+
+struct GroupSmem {
+  float* base;           // [kNumRowBufs][R][ld]
+  int row_buf_floats;    // R * ld
+  float* stage0;         // 2 x NP spline stages of stage_floats each
+  int stage_floats;
+  const float* w;        // staged weights (first smem_w_floats of the image), shared by the CTA
+  __device__ __forceinline__ float* buf(int id) const { return base + id * row_buf_floats; }
+};
+
+// acc[r] += sum_k src[r][k] * w[k * stride + j]      (w already offset by j)
+template <int ROWS>
+__device__ __forceinline__ void dot_accumulate(float (&acc)[ROWS], const float* __restrict__ src, int ld,
+                                               const float* __restrict__ w, int K, int stride) {
+  int k = 0;
+  const int K4 = K & ~3;
+#pragma unroll 2
+  for (; k < K4; k += 4) {
+    const float w0 = w[(size_t)k * stride], w1 = w[(size_t)(k + 1) * stride];
+    const float w2 = w[(size_t)(k + 2) * stride], w3 = w[(size_t)(k + 3) * stride];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(src + r * ld + k);
+      acc[r] = fmaf(a.x, w0, acc[r]);
+      acc[r] = fmaf(a.y, w1, acc[r]);
+      acc[r] = fmaf(a.z, w2, acc[r]);
+      acc[r] = fmaf(a.w, w3, acc[r]);
+    }
+  }
+  for (; k < K; ++k) {
+    const float wk = w[(size_t)k * stride];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(src[r * ld + k], wk, acc[r]);
+  }
+}
+
+// acc[r] += sum_k src[r][k] * wrow[k]   - the TRANSPOSED product: thread j walks row j of an [in][out] image
+// (contiguous), used by the Milstein vjp through the noise network.
+template <int ROWS>
+__device__ __forceinline__ void dot_rows_T(float (&acc)[ROWS], const float* __restrict__ src, int ld,
+                                           const float* __restrict__ wrow, int K) {
+  for (int k = 0; k < K; ++k) {
+    const float wk = __ldg(wrow + k);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(src[r * ld + k], wk, acc[r]);
+  }
+}
+
+struct TimePoint { float t, sin_t, cos_t; };
+
+// Pre-activation (ACT = false) or activated output of one dense op for the R rows of a group, feature j.
+template <int ROWS, bool ACT = true>
+__device__ __forceinline__ void dense_eval(float (&acc)[ROWS], const DenseOp& op, const float* wimg,
+                                           const float* wsm, int smem_w_floats,
+                                           const GroupSmem& sm, int ld, const TimePoint& tp, int j) {
+  auto wptr = [&](int off, int count) -> const float* {
+    return (off + count <= smem_w_floats) ? wsm + off : wimg + off;
+  };
+  float init = op.b_off >= 0 ? wptr(op.b_off, op.N)[j] : 0.f;
+  if (op.tmode == TM_SINCOS) {
+    const float* tw = wptr(op.tw_off, 2 * op.N);
+    init = fmaf(tp.cos_t, tw[op.N + j], fmaf(tp.sin_t, tw[j], init));
+  } else if (op.tmode == TM_RAW) {
+    init = fmaf(tp.t, wptr(op.tw_off, op.N)[j], init);
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) acc[r] = init;
+  if (op.src >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src), ld, wptr(op.w_off, op.K * op.N) + j, op.K, op.N);
+  if (op.src2 >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src2), ld, wptr(op.w2_off, op.K2 * op.N) + j, op.K2, op.N);
+  if (ACT) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = act_apply(acc[r], op.act);
+  }
+}
+
+}  // namespace snsde

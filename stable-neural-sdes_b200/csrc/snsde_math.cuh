@@ -61,4 +61,45 @@ __device__ __forceinline__ void diffusion_eval(const TailOp& t, float coef, floa
   }
 }
 
+// Cotangents of the elementwise diffusion g(coef, y, t) (what autograd propagates through neuralsde.py:233-307):
+// given a_g = dL/dg returns dL/dy (direct path only), dL/dcoef, and dL/d sigmoid(theta).
+// nan_to_num passes a gradient only where its input is finite; relu where its output is positive.
+__device__ __forceinline__ void diffusion_backward(const TailOp& t, float coef, float y, float tt, float g, float a_g,
+                                                   float& a_y, float& a_coef, float& a_sth) {
+  float raw, dy, dc;
+  switch (t.special) {
+    case SP_ZERO: raw = 0.f; dy = 0.f; dc = 0.f; break;
+    case SP_SQRT: raw = sqrtf(y); dy = 0.5f / raw; dc = 0.f; break;
+    case SP_CUBE: raw = y * y * y; dy = 3.f * y * y; dc = 0.f; break;
+    case SP_SIGMOID: raw = 1.f / (1.f + expf(-y)); dy = raw * (1.f - raw); dc = 0.f; break;
+    case SP_RELU: raw = y < 0.f ? 0.f : y; dy = y > 0.f ? 1.f : 0.f; dc = 0.f; break;
+    default:
+      if (t.mult == MU_Y) { raw = coef * y; dy = coef; dc = y; }
+      else if (t.mult == MU_TY) { raw = tt * y; dy = tt; dc = 0.f; }
+      else if (t.mult == MU_T) { raw = coef * tt; dy = 0.f; dc = tt; }
+      else { raw = coef; dy = 0.f; dc = 1.f; }
+  }
+  float a_raw;
+  if (t.bounded) {
+    const float a_arg = a_g * (1.f - g * g);
+    a_sth = a_arg * nan_to_num_f(raw);
+    a_raw = is_finite_f(raw) ? a_arg * t.s_theta : 0.f;
+  } else {
+    a_sth = 0.f;
+    a_raw = a_g;
+  }
+  a_y = a_raw * dy;
+  a_coef = a_raw * dc;
+}
+
+// d act(v) / dv given the pre-activation v (LipSwish) or the activated output (ReLU: out > 0).
+__device__ __forceinline__ float act_grad(float pre, float post, int act) {
+  if (act == ACT_RELU) return post > 0.f ? 1.f : 0.f;
+  if (act == ACT_LIPSWISH) {
+    const float sg = 1.f / (1.f + expf(-pre));
+    return 0.909f * (sg + pre * sg * (1.f - sg));
+  }
+  return 1.f;
+}
+
 }  // namespace snsde

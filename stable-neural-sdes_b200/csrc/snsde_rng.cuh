@@ -17,7 +17,8 @@ namespace snsde {
 
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
-constexpr uint32_t kStreamTag = 0x534E5344u;
+constexpr uint32_t kStreamTag = 0x534E5344u;      // 'SNSD': Brownian increments W
+constexpr uint32_t kStreamTagU = 0x534E5355u;     // 'SNSU': space-time Levy areas of the SRK method
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -51,6 +52,22 @@ __device__ __forceinline__ void philox_normals4(unsigned long long seed, uint32_
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   box_muller(r.x, r.y, n[0], n[1]);
   box_muller(r.z, r.w, n[2], n[3]);
+}
+
+// Second, independent stream for the SRK method: standard normals behind the space-time Levy area.
+__device__ __forceinline__ void philox_normals4_u(unsigned long long seed, uint32_t j, uint32_t p, uint32_t s,
+                                                  float n[4]) {
+  const uint4 r = philox4x32_10(make_uint4(j, p, s, kStreamTagU),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  box_muller(r.x, r.y, n[0], n[1]);
+  box_muller(r.z, r.w, n[2], n[3]);
+}
+
+// torchsde `bm(t0, t1, return_U=True)` for the space-time Levy area approximation:
+//   U = h (W/2 + Hst),  Hst ~ N(0, h/12) independent of W   (brownian_interval.py _H_to_U)
+__device__ __forceinline__ float levy_U(float W, float n2, float h, float sqrt_h) {
+  const float hst = __fmul_rn(n2, __fmul_rn(sqrt_h, 0.28867513459481287f));
+  return __fmul_rn(h, __fadd_rn(__fmul_rn(0.5f, W), hst));
 }
 
 // n[lane] without a dynamically indexed (local-memory) array

@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(256) snsde_tc_tables_kernel(const float* __res
 }
 
 // =================================== host side ===================================================
-static std::string g_reason = "";
+static thread_local std::string g_reason = "";
 const char* tc_unsupported_reason() { return g_reason.c_str(); }
 
 static bool is_time_opt(int io) { return io >= 3 && io <= 6; }

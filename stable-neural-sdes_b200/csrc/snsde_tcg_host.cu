@@ -18,7 +18,7 @@ namespace snsde {
 __global__ void snsde_tc_tables_kernel(const float* __restrict__ vec, TcNoiseNet nn, int H,
                                        const snsde_step* __restrict__ steps, float* __restrict__ a_tab);
 
-static std::string g_greason = "";
+static thread_local std::string g_greason = "";
 const char* tcg_unsupported_reason() { return g_greason.c_str(); }
 
 static bool g_is_time_opt(int io) { return io >= 3 && io <= 6; }

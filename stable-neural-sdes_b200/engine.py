@@ -3,13 +3,24 @@
 ``sdeint`` has the keyword surface of ``torchsde.sdeint`` as the reference calls it
 (/root/reference/benchmark_classification/models_sde/neuralsde.py:78-82 and the tutorial
 notebooks' cell 7) and returns the same ``[len(ts), B, H]`` tensor; ``patch`` swaps it into
-a reference ``NeuralSDE`` at the ``_solve_sde_path`` seam (neuralsde.py:71-82; torch-ists
-variant nsde_model.py:63-74) and fuses the ``final_index`` gather of ``forward`` (:91-116).
+the reference's three wrappers at the ``_solve_sde_path`` seam:
 
-PyTorch is plumbing here (device memory, streams); all arithmetic of the path runs in the
-CUDA kernels behind include/snsde.h.  There is no CPU/eager fallback.
+* classification ``NeuralSDE`` (neuralsde.py:51-120): ``forward`` additionally fuses the
+  ``final_index`` gather (:91-116) into the kernel;
+* ``NeuralSDE_forecasting`` (benchmark_forecasting/models_sde/neuralsde.py:123-186): ``forward``
+  streams only the last ``output_time`` knots the head reads (:184-185);
+* torch-ists ``NeuralSDE`` (torch-ists/torch_ists/diff_module/NSDE/nsde_model.py:45-84): only
+  ``_solve_sde_path`` (signature ``(times, y0, kwargs)``, default method ``'srk'``) is replaced.
+
+Training: under autograd the solve saves every solver state and the backward pass runs the
+reverse-sweep kernel behind ``snsde_backward`` (the reference back-propagates through
+torchsde's step loop, benchmark_classification/common_sde.py:156-162).
+
+PyTorch is plumbing here (device memory, streams, the autograd hook); all arithmetic of the path
+runs in the CUDA kernels behind include/snsde.h.  There is no CPU/eager fallback.
 """
 import ctypes
+import inspect
 import types
 import warnings
 import weakref
@@ -21,18 +32,20 @@ from . import _lib, packing, stepplan
 
 
 class BrownianIncrements:
-    """Explicit Brownian increments ``dW[S, B, H]`` (parity mode).  Also satisfies torchsde's
-    ``bm(t0, t1)`` protocol (sequential replay), so the same object can be handed to real
-    torchsde through the reference's ``**kwargs`` pass-through (neuralsde.py:84,105,82)."""
+    """Explicit Brownian increments ``dW[S, B, H]`` (parity mode); for ``method='srk'`` also the
+    space-time Levy integrals ``dU[S, B, H]`` torchsde obtains from ``bm(t0, t1, return_U=True)``.
+    Satisfies torchsde's ``bm(t0, t1)`` protocol (sequential replay), so the same object can be handed
+    to real torchsde through the reference's ``**kwargs`` pass-through (neuralsde.py:84,105,82)."""
 
-    def __init__(self, dW):
-        self.dW = dW
+    def __init__(self, dW, dU=None):
+        self.dW, self.dU = dW, dU
         self._k = 0
 
-    def __call__(self, t0, t1):
+    def __call__(self, t0, t1, return_U=False):
         w = self.dW[self._k]
+        u = self.dU[self._k] if return_U else None
         self._k += 1
-        return w
+        return (w, u) if return_U else w
 
 
 def _ptr(t):
@@ -44,7 +57,7 @@ _HOST_COPIES = {}
 
 def _host_array(t):
     """fp32 numpy copy of a small tensor; device tensors are cached per (object, version) so
-    steady-state calls do not synchronise."""
+    steady-state calls do not synchronise (the weak reference guards against ``id`` reuse)."""
     if isinstance(t, np.ndarray):
         return np.ascontiguousarray(t, dtype=np.float32)
     if not t.is_cuda:
@@ -65,12 +78,12 @@ class Plan:
 
     def __init__(self, desc, method="euler", precision="auto", device=None):
         self.lib = _lib.load()
-        if not torch.cuda.is_available():
-            raise _lib.EngineError("snsde: no CUDA device - this engine has no CPU fallback")
         if method not in _lib.METHOD:
-            raise ValueError(f"snsde: method {method!r} not implemented (euler, milstein; 'srk' is future work)")
+            raise ValueError(f"snsde: method {method!r} not implemented (euler, milstein, srk)")
         if precision not in _lib.PRECISION:
             raise ValueError(f"snsde: precision {precision!r} not in {sorted(_lib.PRECISION)}")
+        if not torch.cuda.is_available():
+            raise _lib.EngineError("snsde: no CUDA device - this engine has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.desc = dict(desc)
         self.method, self.precision = method, precision
@@ -80,6 +93,7 @@ class Plan:
         self._h = h
         self._plans = {}
         self.weights_version = None
+        self.n_weights = int(self.lib.snsde_weight_count(ctypes.byref(self._cdesc)))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -108,8 +122,19 @@ class Plan:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         return _lib.check(self.lib.snsde_plan_status(self._h, ctypes.c_void_p(stream)))
 
+    def poll_status(self):
+        """Non-blocking: raises if a solve that has completed since the last poll saturated its fp16 operands
+        (the latents it returned are outside the parity tolerance).  Called at the start of every solve."""
+        if _lib.check(self.lib.snsde_plan_status_nowait(self._h)) & 1:
+            raise _lib.EngineError(
+                "snsde: an earlier solve of this model on the tensor-core kernel met a state or control value beyond "
+                "the fp16 range (|v| > 65504) of its split-precision operands and saturated it; its result is not "
+                "within tolerance.  Re-run with precision='fp32' (or check_range=True to do so automatically).")
+
     def set_weights(self, blob):
         blob = blob.detach().to(torch.float32).contiguous()
+        if blob.numel() != self.n_weights:
+            raise ValueError(f"snsde: weight blob has {blob.numel()} floats, model needs {self.n_weights}")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.snsde_plan_set_weights(self._h, _ptr(blob), blob.numel(), int(blob.is_cuda),
                                                    ctypes.c_void_p(stream)))
@@ -120,16 +145,12 @@ class Plan:
             self.set_weights(packing.pack(sde, self.desc))
             self.weights_version = ver
 
-    def forward(self, y0, plan, coeffs=None, row_slot=None, dW=None, seed=0, row_offset=0, out=None):
-        """Enqueue one solve on the current stream.  Returns ``[n_out, B, H]`` or, with
-        ``row_slot`` (int32 ``[B]``), the fused ``[B, H]`` gather."""
-        dev = self.device
-        H = self.hidden
+    def _check_inputs(self, y0, plan, coeffs):
+        dev, H = self.device, self.hidden
         if y0.dim() != 2 or y0.shape[1] != H:
             raise ValueError(f"snsde: y0 must be [B, {H}], got {tuple(y0.shape)}")
         if y0.device != dev:
             raise ValueError(f"snsde: y0 is on {y0.device}, plan is on {dev}")
-        y0 = y0.detach().to(torch.float32).contiguous()
         B = y0.shape[0]
         stride = 0
         if self.uses_control:
@@ -146,10 +167,32 @@ class Plan:
             stride = coeffs.stride(0)
         else:
             coeffs = None
+        return coeffs, stride
+
+    def forward(self, y0, plan, coeffs=None, row_slot=None, dW=None, dU=None, seed=0, row_offset=0, out=None):
+        """Enqueue one solve on the current stream.  Returns ``[n_out, B, H]`` or, with
+        ``row_slot`` (int32 ``[B]``), the fused ``[B, H]`` gather."""
+        dev, H = self.device, self.hidden
+        self.poll_status()
+        coeffs, stride = self._check_inputs(y0, plan, coeffs)
+        y0 = y0.detach().to(torch.float32).contiguous()
+        B = y0.shape[0]
         if dW is not None:
             if tuple(dW.shape) != (plan.n_steps, B, H):
                 raise ValueError(f"snsde: dW must be [S={plan.n_steps}, B={B}, H={H}], got {tuple(dW.shape)}")
             dW = dW.detach().to(device=dev, dtype=torch.float32).contiguous()
+        points = None
+        if self.method == "srk":
+            if plan.points is None:
+                raise ValueError("snsde: method 'srk' needs a step plan built with method='srk'")
+            points = ctypes.c_void_p(plan.points.ctypes.data)
+            if dW is not None:
+                if dU is None or tuple(dU.shape) != (plan.n_steps, B, H):
+                    raise ValueError("snsde: method 'srk' with explicit increments needs dU [S, B, H] (space-time Levy "
+                                     "integrals, torchsde bm(t0, t1, return_U=True)) beside dW")
+                dU = dU.detach().to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            dU = None
         if row_slot is not None:
             row_slot = row_slot.to(device=dev, dtype=torch.int32).contiguous()
             if tuple(row_slot.shape) != (B,):
@@ -166,9 +209,36 @@ class Plan:
             self._h, _ptr(coeffs), stride, plan.n_knots, _ptr(y0), B,
             ctypes.c_void_p(plan.steps.ctypes.data), plan.n_steps,
             ctypes.c_void_p(plan.emits.ctypes.data), len(plan.emits), plan.n_init_emits, plan.n_out,
-            _ptr(row_slot), _ptr(dW), ctypes.c_uint64(seed & (2 ** 64 - 1)), ctypes.c_uint64(row_offset),
+            points, _ptr(row_slot), _ptr(dW), _ptr(dU if dW is not None else None),
+            ctypes.c_uint64(seed & (2 ** 64 - 1)), ctypes.c_uint64(row_offset),
             _ptr(out), ctypes.c_void_p(stream)))
         return out
+
+    def backward(self, states, grad_states, plan, coeffs=None, dW=None, seed=0, row_offset=0):
+        """Reverse sweep (``snsde_backward``): ``states``/``grad_states`` are ``[S+1, B, H]``.  Returns
+        ``(grad_y0 [B, H], grad_blob [n_weights])``."""
+        dev, H = self.device, self.hidden
+        S = plan.n_steps
+        if states.dim() != 3 or states.shape[0] != S + 1 or states.shape[2] != H:
+            raise ValueError(f"snsde: states must be [S+1={S + 1}, B, {H}], got {tuple(states.shape)}")
+        B = states.shape[1]
+        coeffs, stride = self._check_inputs(states[0], plan, coeffs)
+        states = states.detach().to(torch.float32).contiguous()
+        grad_states = grad_states.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if grad_states.shape != states.shape:
+            raise ValueError("snsde: grad_states must have the shape of states")
+        if dW is not None:
+            dW = dW.detach().to(device=dev, dtype=torch.float32).contiguous()
+        nbytes = _lib.check(self.lib.snsde_backward_workspace_bytes(self._h, B, S))
+        ws = torch.empty((nbytes + 3) // 4, device=dev, dtype=torch.float32)
+        gy0 = torch.empty((B, H), device=dev, dtype=torch.float32)
+        gblob = torch.empty(self.n_weights, device=dev, dtype=torch.float32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.snsde_backward(
+            self._h, _ptr(coeffs), stride, plan.n_knots, B, ctypes.c_void_p(plan.steps.ctypes.data), S,
+            _ptr(states), _ptr(grad_states), _ptr(dW), ctypes.c_uint64(seed & (2 ** 64 - 1)),
+            ctypes.c_uint64(row_offset), _ptr(gy0), _ptr(gblob), _ptr(ws), ws.numel() * 4, ctypes.c_void_p(stream)))
+        return gy0, gblob
 
     def step_plan(self, ts, dt, knots):
         ts_h = _host_array(ts)
@@ -178,25 +248,33 @@ class Plan:
         if sp is None:
             if len(self._plans) > 64:
                 self._plans.clear()
-            sp = self._plans[key] = stepplan.build_step_plan(ts_h, dt, kn_h)
+            sp = self._plans[key] = stepplan.build_step_plan(ts_h, dt, kn_h, method=self.method)
         return sp
 
 
-def philox_increments(seed, plan, B, H, device, row_offset=0):
-    """``dW[S, B, H]`` exactly as the kernels draw them for ``seed`` (for the oracle)."""
+def philox_increments(seed, plan, B, H, device, row_offset=0, with_U=False):
+    """``dW[S, B, H]`` exactly as the kernels draw them for ``seed`` (for the oracle); with ``with_U`` also
+    the SRK kernels' space-time Levy integrals ``dU[S, B, H]``."""
     lib = _lib.load()
     dev = torch.device(device)
     dW = torch.empty((plan.n_steps, B, H), device=dev, dtype=torch.float32)
-    sq = np.ascontiguousarray(plan.steps["sqrt_h"])
+    dU = torch.empty_like(dW) if with_U else None
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(lib.snsde_philox_fill(ctypes.c_uint64(seed), ctypes.c_uint64(row_offset), plan.n_steps, B, H,
-                                     ctypes.c_void_p(sq.ctypes.data), _ptr(dW), dev.index or 0,
+                                     ctypes.c_void_p(plan.steps.ctypes.data), _ptr(dW), _ptr(dU), dev.index or 0,
                                      ctypes.c_void_p(stream)))
-    return dW
+    return (dW, dU) if with_U else dW
+
+
+# Plans live beside the module they serve, NOT inside it: they hold ctypes handles, which must not travel through
+# copy.deepcopy / torch.save of the model (the reference harness deep-copies its best model, common_sde.py:181).
+_PLANS = weakref.WeakKeyDictionary()
 
 
 def _plan_for(sde, method, precision, device):
-    cache = sde.__dict__.setdefault("_snsde_plans", {})
+    cache = _PLANS.get(sde)
+    if cache is None:
+        cache = _PLANS[sde] = {}
     key = (method, precision, str(device))
     plan = cache.get(key)
     if plan is None:
@@ -205,50 +283,163 @@ def _plan_for(sde, method, precision, device):
     return plan
 
 
-def _check_sde(sde, y0):
+def plans_of(sde):
+    """The engine plans currently cached for ``sde`` (``{(method, precision, device): Plan}``)."""
+    return dict(_PLANS.get(sde, {}))
+
+
+def _check_sde(sde):
     if getattr(sde, "sde_type", "ito") != "ito" or getattr(sde, "noise_type", "diagonal") != "diagonal":
         raise ValueError("snsde: only Ito SDEs with diagonal noise are supported (neuralsde.py:137-138)")
-    if torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in sde.parameters())):
-        raise RuntimeError("snsde: the engine is forward-only (SURVEY 8f1); call it under torch.no_grad() "
-                           "- refusing to silently drop gradients")
 
 
-def _increments(bm, plan, B, H, device):
+def _wants_grad(sde, y0):
+    return torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in sde.parameters()))
+
+
+def _increments(bm, plan, B, H, device, srk):
+    """(dW, dU) tables from a ``bm`` object: a BrownianIncrements / oracle table is used as is, any other
+    torchsde-protocol callable is replayed step by step."""
     if bm is None:
-        return None
+        return None, None
     if hasattr(bm, "dW"):
-        return bm.dW
-    rows = [bm(torch.tensor(float(s["t0"])), torch.tensor(float(s["t0"]) + float(s["h"]))) for s in plan.steps]
-    return torch.stack(rows).to(device) if rows else torch.empty((0, B, H), device=device)
+        return bm.dW, getattr(bm, "dU", None)
+    rows, urows = [], []
+    for s in plan.steps:
+        t0, t1 = torch.tensor(float(s["t0"])), torch.tensor(float(s["t0"]) + float(s["h"]))
+        if srk:
+            w, u = bm(t0, t1, return_U=True)
+            urows.append(u)
+        else:
+            w = bm(t0, t1)
+        rows.append(w)
+    if not rows:
+        e = torch.empty((0, B, H), device=device)
+        return e, (e if srk else None)
+    return torch.stack(rows).to(device), (torch.stack(urows).to(device) if srk else None)
 
 
 def _random_seed():
     return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
+class _SolveStates(torch.autograd.Function):
+    """Every solver state ``[S+1, B, H]`` with a backward through the reverse-sweep kernel.  The requested
+    outputs are formed from the states by differentiable indexing (lerp / per-row capture) outside."""
+
+    @staticmethod
+    def forward(ctx, plan, sp, coeffs, dW, seed, row_offset, keys, y0, *params):
+        states = plan.forward(y0, sp.dense(), coeffs=coeffs, dW=dW, seed=seed, row_offset=row_offset)
+        ctx.plan, ctx.sp, ctx.coeffs, ctx.dW, ctx.seed, ctx.row_offset = plan, sp, coeffs, dW, seed, row_offset
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.dtypes = [p.dtype for p in params]
+        ctx.save_for_backward(states)
+        return states
+
+    @staticmethod
+    def backward(ctx, grad_states):
+        (states,) = ctx.saved_tensors
+        gy0, gblob = ctx.plan.backward(states, grad_states, ctx.sp, coeffs=ctx.coeffs, dW=ctx.dW, seed=ctx.seed,
+                                       row_offset=ctx.row_offset)
+        grads, off = [], 0
+        for shape, dtype in zip(ctx.shapes, ctx.dtypes):
+            n = int(np.prod(shape)) if shape else 1
+            grads.append(gblob[off:off + n].view(shape).to(dtype))
+            off += n
+        return (None, None, None, None, None, None, None, gy0, *grads)
+
+
+def _states_with_grad(sde, plan, sp, y0, dW, seed, row_offset):
+    if plan.method != "euler":
+        raise RuntimeError(f"snsde: the backward pass is implemented for method='euler' (the reference's training "
+                           f"default, neuralsde.py:75), not {plan.method!r}; call under torch.no_grad() for inference")
+    keys = packing.blob_keys(plan.desc)
+    named = dict(sde.named_parameters())
+    missing = [k for k in keys if k not in named]
+    if missing:
+        raise ValueError(f"snsde: parameters {missing} not found on the SDE module")
+    params = [named[k] for k in keys]
+    return _SolveStates.apply(plan, sp, getattr(sde, "coeffs", None), dW, seed, row_offset, keys, y0, *params)
+
+
+def _select_outputs(states, sp):
+    """``[n_out, B, H]`` from the dense states: out[slot] = w_prev * Y[k] + w_curr * Y[k+1] (torchsde linear_interp)."""
+    slot, k, w_prev, w_curr = sp.output_map()
+    order = np.argsort(slot, kind="stable")
+    assert np.array_equal(slot[order], np.arange(sp.n_out)), "every output slot is produced exactly once"
+    k, w_prev, w_curr = k[order], w_prev[order], w_curr[order]
+    dev = states.device
+    hi = torch.as_tensor(k + 1, device=dev)
+    out = states.index_select(0, hi)
+    if np.any(w_prev != 0.0):
+        lo = torch.as_tensor(np.maximum(k, 0), device=dev)
+        wp = torch.as_tensor(w_prev, device=dev).view(-1, 1, 1)
+        wc = torch.as_tensor(w_curr, device=dev).view(-1, 1, 1)
+        out = wp * states.index_select(0, lo) + wc * out
+    return out
+
+
+def _select_rows(states, sp, row_slot):
+    """Fused-gather equivalent on the dense states: row b keeps output slot ``row_slot[b]``."""
+    slot, k, w_prev, w_curr = sp.output_map()
+    order = np.argsort(slot, kind="stable")
+    k, w_prev, w_curr = k[order], w_prev[order], w_curr[order]
+    dev = states.device
+    rs = row_slot.to(device=dev, dtype=torch.long)
+    rows = torch.arange(states.shape[1], device=dev)
+    hi = torch.as_tensor(k + 1, device=dev)[rs]
+    out = states[hi, rows]
+    if np.any(w_prev != 0.0):
+        lo = torch.as_tensor(np.maximum(k, 0), device=dev)[rs]
+        wp = torch.as_tensor(w_prev, device=dev)[rs].unsqueeze(-1)
+        wc = torch.as_tensor(w_curr, device=dev)[rs].unsqueeze(-1)
+        out = wp * states[lo, rows] + wc * out
+    return out
+
+
+def _solve(sde, plan, sp, y0, row_slot, bm, seed, row_offset, out, check_range):
+    srk = plan.method == "srk"
+    dW, dU = _increments(bm, sp, y0.shape[0], plan.hidden, y0.device, srk)
+    if dW is None and seed is None:
+        seed = _random_seed()
+    seed = seed or 0
+    coeffs = getattr(sde, "coeffs", None)
+    if _wants_grad(sde, y0):
+        states = _states_with_grad(sde, plan, sp, y0, dW, seed, row_offset)
+        res = _select_outputs(states, sp) if row_slot is None else _select_rows(states, sp, row_slot)
+        if out is not None:
+            raise ValueError("snsde: out= is not supported under autograd")
+        return res
+    res = plan.forward(y0, sp, coeffs=coeffs, row_slot=row_slot, dW=dW, dU=dU, seed=seed, row_offset=row_offset, out=out)
+    if check_range and plan.kernel != "fma_fp32" and plan.status() & 1:
+        p32 = _plan_for(sde, plan.method, "fp32", y0.device)
+        res = p32.forward(y0, sp, coeffs=coeffs, row_slot=row_slot, dW=dW, dU=dU, seed=seed, row_offset=row_offset, out=out)
+    return res
+
+
 def sdeint(sde, y0, ts, dt=1e-3, method=None, options=None, bm=None, seed=None, precision="auto",
-           row_offset=0, names=None, out=None, **unused_kwargs):
+           row_offset=0, names=None, out=None, check_range=False, **unused_kwargs):
     """Drop-in for ``torchsde.sdeint(sde, y0, ts, dt=..., method=...)`` on this path.
 
     ``sde`` is a reference ``Diffusion_model`` (or the tutorial ``NeuralLSDEFunc``) on which
-    ``set_X(coeffs, times)`` has been called; the engine reads ``sde.coeffs``, ``sde.times`` and
-    ``state_dict()`` and never calls Python ``f``/``g``.  ``options`` is accepted and ignored, as
-    torchsde's Euler ignores ``options['dt']`` (neuralsde.py:39-46).  ``bm=None`` draws
-    increments in-kernel (Philox, ``seed``); ``bm=BrownianIncrements(dW)`` replays a table.
+    ``set_X(coeffs, times)`` has been called; the engine reads ``sde.coeffs``, ``sde.times`` and the
+    parameters and never calls Python ``f``/``g``.  ``method``: ``'euler'`` (default), ``'milstein'``,
+    ``'srk'``.  ``options`` is accepted and ignored, as torchsde's fixed-step solvers ignore ``options['dt']``
+    (neuralsde.py:39-46).  ``bm=None`` draws increments in-kernel (Philox, ``seed``);
+    ``bm=BrownianIncrements(dW[, dU])`` replays a table.  Under autograd (``method='euler'``) the result
+    carries a backward through the reverse-sweep kernel.  The tensor-core kernels flag operands beyond the
+    fp16 range: the flag is polled (and raised) on the next call, or at once with ``check_range=True``
+    (one stream synchronisation; the solve is then re-run on the fp32 kernel).
     """
     if unused_kwargs:
         warnings.warn(f"Unexpected arguments {sorted(unused_kwargs)}")          # torchsde does the same
     if names is not None:
         raise ValueError("snsde: `names` remapping is not supported")
     method = "euler" if method is None else method
-    _check_sde(sde, y0)
+    _check_sde(sde)
     plan = _plan_for(sde, method, precision, y0.device)
     sp = plan.step_plan(ts, dt, getattr(sde, "times", None))
-    dW = _increments(bm, sp, y0.shape[0], plan.hidden, y0.device)
-    if dW is None and seed is None:
-        seed = _random_seed()
-    return plan.forward(y0, sp, coeffs=getattr(sde, "coeffs", None), dW=dW, seed=seed or 0,
-                        row_offset=row_offset, out=out)
+    return _solve(sde, plan, sp, y0, None, bm, seed, row_offset, out, check_range)
 
 
 def final_index_slots(times, final_index):
@@ -264,72 +455,120 @@ def final_index_slots(times, final_index):
 
 
 def solve_final(sde, times, final_index, z0, method=None, bm=None, seed=None, precision="auto",
-                row_offset=0, out=None, dt=None):
+                row_offset=0, out=None, dt=None, check_range=False):
     """``z`` at each row's own final knot, ``[B, H]``: sdeint + gather of neuralsde.py:105-116 fused
     (each row keeps only its own slot; the ``[n_unique, B, H]`` intermediate is never written)."""
     method = "euler" if method is None else method
-    _check_sde(sde, z0)
+    _check_sde(sde)
     plan = _plan_for(sde, method, precision, z0.device)
     ts, slots = final_index_slots(times, final_index)
     sp = plan.step_plan(ts, stepplan.solver_dt(_host_array(times)) if dt is None else dt, times)
-    dW = _increments(bm, sp, z0.shape[0], plan.hidden, z0.device)
-    if dW is None and seed is None:
-        seed = _random_seed()
-    return plan.forward(z0, sp, coeffs=getattr(sde, "coeffs", None), row_slot=slots, dW=dW, seed=seed or 0,
-                        row_offset=row_offset, out=out)
+    return _solve(sde, plan, sp, z0, slots, bm, seed, row_offset, out, check_range)
 
 
-_ENGINE_KW = ("bm", "seed", "precision", "row_offset")
+# ---- patching the reference wrappers ----------------------------------------------------------------
+_ENGINE_KW = ("bm", "seed", "precision", "row_offset", "check_range")
 
 
-def patch(model, fuse_final_index=True):
-    """Swap the engine into a reference ``NeuralSDE``-style module, in place.
+def _cat_coeffs(coeffs):
+    if isinstance(coeffs, (tuple, list)):
+        return coeffs[0] if len(coeffs) == 1 else torch.cat(list(coeffs), dim=-1)
+    return coeffs
 
-    * ``model._solve_sde_path`` (both signatures: ``(times, ts, z0, kwargs)`` of the benchmark
-      classes and ``(times, y0, kwargs)`` of torch-ists) calls :func:`sdeint`;
-    * with ``fuse_final_index`` and a classification-style ``forward(times, coeffs,
-      final_index, z0=None, stream=False, **kw)``, the non-stream branch calls
-      :func:`solve_final` so the gather happens in the kernel.
-    Returns ``model``.
+
+def _solve_sde_path_benchmark(self, times, ts, z0, kwargs):
+    """Replacement for ``NeuralSDE._solve_sde_path(times, ts, z0, kwargs)`` (neuralsde.py:71-82; default 'euler')."""
+    kwargs = dict(kwargs)
+    kwargs.setdefault("method", "euler")
+    return sdeint(self.func, z0, ts, dt=stepplan.solver_dt(_host_array(times)), **kwargs)
+
+
+def _solve_sde_path_torch_ists(self, times, y0, kwargs):
+    """Replacement for torch-ists ``NeuralSDE._solve_sde_path(times, y0, kwargs)`` (nsde_model.py:63-74; default
+    'srk', outputs at every knot)."""
+    kwargs = dict(kwargs)
+    kwargs.setdefault("method", "srk")
+    return sdeint(self.func, y0, times, dt=stepplan.solver_dt(_host_array(times)), **kwargs)
+
+
+def _forward_classification(self, times, coeffs, final_index, z0=None, stream=False, **kwargs):
+    """``NeuralSDE.forward`` (neuralsde.py:84-120) with the final_index gather fused into the solve."""
+    self.func.set_X(_cat_coeffs(coeffs), times)
+    z0 = self._prepare_initial_state(times, z0)
+    eng = {k: kwargs.pop(k) for k in _ENGINE_KW if k in kwargs}
+    method = kwargs.pop("method", None)
+    kwargs.pop("options", None)
+    if stream:
+        z_t = sdeint(self.func, z0, times, dt=stepplan.solver_dt(_host_array(times)), method=method, **eng, **kwargs)
+        z_t = z_t.transpose(0, 1)
+    else:
+        if kwargs:
+            warnings.warn(f"Unexpected arguments {sorted(kwargs)}")
+        z_t = solve_final(self.func, times, final_index, z0, method=method, **eng)
+    return self.linear(z_t)
+
+
+def _forward_forecasting(self, times, coeffs, final_index, z0=None, stream=False, **kwargs):
+    """``NeuralSDE_forecasting.forward`` (benchmark_forecasting/models_sde/neuralsde.py:158-186): the reference
+    streams every knot and heads the last ``output_time`` of them (:184-185); only those are written here."""
+    self.func.set_X(_cat_coeffs(coeffs), times)
+    z0 = self._prepare_initial_state(times, z0)
+    eng = {k: kwargs.pop(k) for k in _ENGINE_KW if k in kwargs}
+    method = kwargs.pop("method", None)
+    kwargs.pop("options", None)
+    K, ot = len(times), int(self.output_time)
+    dt = stepplan.solver_dt(_host_array(times))
+    if 0 < ot < K:
+        ts = torch.cat([times[:1], times[K - ot:]])
+        z_t = sdeint(self.func, z0, ts, dt=dt, method=method, **eng, **kwargs)[1:]
+    else:                                   # the reference's slice z_t[:, K - ot:] with ot >= K (or 0) on the full stream
+        z_t = sdeint(self.func, z0, times, dt=dt, method=method, **eng, **kwargs)
+        z_t = z_t[K - ot:] if ot else z_t[K:]
+    return self.linear(z_t.transpose(0, 1))
+
+
+# pickling a bound method stores (getattr, (instance, __name__)): name the replacements after the attributes they fill
+# so that torch.save(model) works (the loaded copy comes back with the class's own methods: patch() it again)
+_solve_sde_path_benchmark.__name__ = _solve_sde_path_torch_ists.__name__ = "_solve_sde_path"
+_forward_classification.__name__ = _forward_forecasting.__name__ = "forward"
+
+
+def wrapper_kind(model):
+    """Which of the reference's three wrappers ``model`` is, from its own ``forward`` signature."""
+    try:
+        names = list(inspect.signature(type(model).forward).parameters)
+    except (TypeError, ValueError):
+        return "unknown"
+    if names[:4] == ["self", "times", "coeffs", "final_index"] and hasattr(model, "_prepare_initial_state"):
+        return "forecasting" if hasattr(model, "output_time") else "classification"
+    if names[:3] == ["self", "coeffs", "times"]:
+        return "torch_ists"
+    return "unknown"
+
+
+def patch(model, fuse=True):
+    """Swap the engine into one of the reference's ``NeuralSDE`` wrappers, in place; returns ``model``.
+
+    * always: ``model._solve_sde_path`` calls :func:`sdeint` on ``self.func`` (benchmark signature
+      ``(times, ts, z0, kwargs)``, default ``'euler'``; torch-ists signature ``(times, y0, kwargs)``, default ``'srk'``);
+    * ``fuse`` and a classification ``NeuralSDE``: ``forward`` fuses the ``final_index`` gather;
+    * ``fuse`` and ``NeuralSDE_forecasting``: ``forward`` writes only the last ``output_time`` knots;
+    * torch-ists ``NeuralSDE`` or an unrecognised wrapper: ``forward`` is left alone.
+    The replacements are module-level functions bound to the instance, so ``copy.deepcopy`` and ``torch.save`` of a
+    patched model work and a copy drives its own ``func``.
     """
-    func = model.func
-
-    def _solve(self, times, *rest):
-        if len(rest) == 3:
-            ts, z0, kwargs = rest
-        else:
-            z0, kwargs = rest
-            ts = times
-        kwargs = dict(kwargs)
-        if "method" not in kwargs:
-            if len(rest) == 2:
-                # torch-ists NeuralSDE defaults to 'srk' (nsde_model.py:67), which the engine does not implement:
-                # refuse rather than silently integrating with a different scheme
-                raise ValueError("snsde: this wrapper's default method is 'srk' (not implemented); pass method='euler' "
-                                 "or method='milstein' explicitly")
-            kwargs["method"] = "euler"                       # benchmark wrappers' default (neuralsde.py:75)
-        if kwargs["method"] == "srk":
-            raise ValueError("snsde: method 'srk' is not implemented (SURVEY 8f2); use 'euler' or 'milstein'")
-        dt = stepplan.solver_dt(_host_array(times))
-        return sdeint(func, z0, ts, dt=dt, **kwargs)
-
-    model._solve_sde_path = types.MethodType(_solve, model)
-
-    if fuse_final_index and hasattr(model, "_prepare_initial_state") and hasattr(model, "linear"):
-        def _forward(self, times, coeffs, final_index, z0=None, stream=False, **kwargs):
-            if isinstance(coeffs, (tuple, list)):
-                coeffs = coeffs[0] if len(coeffs) == 1 else torch.cat(list(coeffs), dim=-1)
-            func.set_X(coeffs, times)
-            z0 = self._prepare_initial_state(times, z0)
-            eng = {k: kwargs.pop(k) for k in _ENGINE_KW if k in kwargs}
-            method = kwargs.pop("method", None)
-            kwargs.pop("options", None)
-            if stream:
-                z_t = sdeint(func, z0, times, dt=stepplan.solver_dt(_host_array(times)), method=method, **eng, **kwargs)
-                z_t = z_t.transpose(0, 1)
-            else:
-                z_t = solve_final(func, times, final_index, z0, method=method, **eng)
-            return self.linear(z_t)
-
-        model.forward = types.MethodType(_forward, model)
+    if not hasattr(model, "func") or not hasattr(model, "_solve_sde_path"):
+        raise ValueError("snsde: patch() expects a NeuralSDE-style wrapper with `.func` and `._solve_sde_path`")
+    kind = wrapper_kind(model)
+    n_args = len(inspect.signature(type(model)._solve_sde_path).parameters)
+    if n_args == 5:
+        model._solve_sde_path = types.MethodType(_solve_sde_path_benchmark, model)
+    elif n_args == 4:
+        model._solve_sde_path = types.MethodType(_solve_sde_path_torch_ists, model)
+    else:
+        raise ValueError("snsde: unrecognised _solve_sde_path signature (expected (times, ts, z0, kwargs) or (times, y0, kwargs))")
+    if fuse and kind == "classification":
+        model.forward = types.MethodType(_forward_classification, model)
+    elif fuse and kind == "forecasting":
+        model.forward = types.MethodType(_forward_forecasting, model)
     return model

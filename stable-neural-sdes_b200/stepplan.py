@@ -14,19 +14,47 @@ STEP_DTYPE = np.dtype([("t0", "<f4"), ("h", "<f4"), ("sqrt_h", "<f4"), ("sin_t0"
                        ("interval", "<i4"), ("frac", "<f4"), ("emit_begin", "<i4"), ("emit_end", "<i4"),
                        ("reserved", "<i4")])
 EMIT_DTYPE = np.dtype([("slot", "<i4"), ("w_prev", "<f4"), ("w_curr", "<f4")])
-assert STEP_DTYPE.itemsize == 40 and EMIT_DTYPE.itemsize == 12
+POINT_DTYPE = np.dtype([("t", "<f4"), ("sin_t", "<f4"), ("cos_t", "<f4"), ("frac", "<f4"), ("interval", "<i4")])
+assert STEP_DTYPE.itemsize == 40 and EMIT_DTYPE.itemsize == 12 and POINT_DTYPE.itemsize == 20
+SRK_POINT_FRACTIONS = (0.0, 0.25, 0.5, 1.0)      # SRID2: f at t0 + {0, 1, 1/2} h, g at t0 + {0, 1/4, 1} h
 
 
 class StepPlan:
-    __slots__ = ("steps", "emits", "n_init_emits", "n_out", "n_knots")
+    __slots__ = ("steps", "emits", "n_init_emits", "n_out", "n_knots", "points", "_dense")
 
-    def __init__(self, steps, emits, n_init_emits, n_out, n_knots):
+    def __init__(self, steps, emits, n_init_emits, n_out, n_knots, points=None):
         self.steps, self.emits = steps, emits
         self.n_init_emits, self.n_out, self.n_knots = n_init_emits, n_out, n_knots
+        self.points = points                     # [S, 4] snsde_point (method 'srk') or None
+        self._dense = None
 
     @property
     def n_steps(self):
         return len(self.steps)
+
+    def dense(self):
+        """The same steps, emitting EVERY solver state: slot s+1 = state after step s (``[S+1, B, H]``).
+        The training path saves these states for the reverse sweep and forms the requested outputs from them."""
+        if self._dense is None:
+            S = self.n_steps
+            steps = self.steps.copy()
+            steps["emit_begin"] = np.arange(1, S + 1, dtype=np.int32)
+            steps["emit_end"] = np.arange(2, S + 2, dtype=np.int32)
+            em = np.zeros(S + 1, dtype=EMIT_DTYPE)
+            em["slot"] = np.arange(S + 1, dtype=np.int32)
+            em["w_curr"] = 1.0
+            self._dense = StepPlan(steps, em, 1, S + 1, self.n_knots, self.points)
+        return self._dense
+
+    def output_map(self):
+        """How the requested outputs read the dense states: ``out[slot] = w_prev * Y[k] + w_curr * Y[k + 1]``
+        with ``k`` the step that produced the emit (``k = -1``: the initial state, out = Y[0]).
+        Returns (slot, k, w_prev, w_curr) arrays over the emits."""
+        E = len(self.emits)
+        k = np.full(E, -1, dtype=np.int64)
+        for s in range(self.n_steps):
+            k[self.steps["emit_begin"][s]:self.steps["emit_end"][s]] = s
+        return self.emits["slot"].astype(np.int64), k, self.emits["w_prev"].copy(), self.emits["w_curr"].copy()
 
 
 def solver_dt(knots):
@@ -35,7 +63,26 @@ def solver_dt(knots):
     return max(float((knots[1:] - knots[:-1]).min()), 1e-3)
 
 
-def build_step_plan(ts, dt, knots=None):
+def srk_points(steps, knots=None):
+    """Evaluation points of the SRID2 stages per step, ``[S, 4]``: ``t0 + c * h`` for c in (0, 1/4, 1/2, 1) in
+    float32 arithmetic (torchsde forms ``t0 + C[j] * dt`` with 0-d float32 tensors), their time features and
+    spline interval / fraction."""
+    S = len(steps)
+    pts = np.zeros((S, len(SRK_POINT_FRACTIONS)), dtype=POINT_DTYPE)
+    for i, c in enumerate(SRK_POINT_FRACTIONS):
+        t = (steps["t0"] + (np.float32(c) * steps["h"]).astype(np.float32)).astype(np.float32)
+        pts["t"][:, i] = t
+        pts["sin_t"][:, i] = np.sin(t)
+        pts["cos_t"][:, i] = np.cos(t)
+        if knots is not None and S:
+            kn = np.ascontiguousarray(knots, dtype=np.float32).reshape(-1)
+            idx = np.clip(np.searchsorted(kn, t, side="left") - 1, 0, kn.size - 2)
+            pts["interval"][:, i] = idx
+            pts["frac"][:, i] = t - kn[idx]
+    return np.ascontiguousarray(pts)
+
+
+def build_step_plan(ts, dt, knots=None, method="euler"):
     ts = np.ascontiguousarray(ts, dtype=np.float32).reshape(-1)
     if ts.size < 1:
         raise ValueError("ts must hold at least one time")
@@ -82,4 +129,5 @@ def build_step_plan(ts, dt, knots=None):
     em["slot"] = [e[0] for e in emits]
     em["w_prev"] = [e[1] for e in emits]
     em["w_curr"] = [e[2] for e in emits]
-    return StepPlan(steps, em, 1, int(ts.size), 0 if knots is None else int(np.size(knots)))
+    points = srk_points(steps, knots) if method == "srk" else None
+    return StepPlan(steps, em, 1, int(ts.size), 0 if knots is None else int(np.size(knots)), points)

@@ -19,6 +19,9 @@ What is real reference code here and what is shim:
   in-tree spline, and ``forward_golden.pt`` pins the reference's output-time
   selection/gather given the oracle solver.
 
+  ``forward_golden.pt`` also holds the torch-ists wrapper (nsde_model.py, loaded by file path as the
+  reference's own test does), whose default method is 'srk'.
+
 Outputs: fg_golden.pt, spline_golden.pt, forward_golden.pt (a few hundred KB in total).
 """
 import importlib
@@ -47,6 +50,8 @@ def install_shims():
     def sdeint(sde, y0, ts, dt, bm=None, method="euler", options=None, **kw):
         return osolver.sdeint(sde, y0, ts, dt, bm, method=method, options=options)
 
+    tsde.sdeint_adjoint = sdeint
+
     tsde.sdeint = sdeint
     tdiff = types.ModuleType("torchdiffeq")
     tdiff.odeint = tdiff.odeint_adjoint = None
@@ -74,6 +79,16 @@ def load_reference_module(root, real_cde=True):
         return mod, sys.modules["controldiffeq"]
     finally:
         sys.path.pop(0)
+
+
+def load_torch_ists_module():
+    """torch-ists' copy of the wrapper + vector field, loaded by file path the way the reference's own test does
+    (/root/reference/tests/test_neuralsde_core_alignment.py:48-53): the torch_ists package itself is not importable."""
+    path = REF / "torch-ists" / "torch_ists" / "diff_module" / "NSDE" / "nsde_model.py"
+    spec = importlib.util.spec_from_file_location("ref_torch_ists_nsde_model", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def make_inputs(seed, B, K, C, H):
@@ -141,7 +156,7 @@ def spline_golden(cde):
     print("spline_golden.pt:", len(out), "cases")
 
 
-def forward_golden(ref_c, ref_f):
+def forward_golden(ref_c, ref_f, ref_t=None):
     out = []
     with torch.no_grad():
         # classification wrapper: final_index gather
@@ -176,6 +191,27 @@ def forward_golden(ref_c, ref_f):
                         state_dict={k: v.clone() for k, v in func.state_dict().items()},
                         initial_network={k: v.clone() for k, v in model.initial_network.state_dict().items()},
                         times=times, coeffs=torch.cat(coeffs4, -1), dW=dW, z=z))
+        # torch-ists wrapper (nsde_model.py:45-84): forward(coeffs, times) -> (head(z), z), every knot, default method
+        # 'srk' (needs the space-time Levy integrals beside the increments), linspace grid with a sliver step
+        if ref_t is not None:
+            for method, io, no in ((None, 4, 17), ("euler", 6, 17), ("srk", 2, 16)):
+                B, K, C, H, L = 4, 9, 3, 8, 2
+                torch.manual_seed(321 + io)
+                func = ref_t.Diffusion_model(C, H, H, L, input_option=io, noise_option=no)
+                model = ref_t.NeuralSDE(func, C, H, 2, initial=True)
+                times = torch.linspace(0, 1, K)
+                x = torch.randn(B, K, C).cumsum(1) * 0.3
+                coeffs = ospline.hermite_cubic_coefficients_with_backward_differences(x, times)
+                S = len(osolver.step_times(times, osolver.solver_dt(times)))
+                dW = torch.randn(S, B, H) * (1.0 / (K - 1)) ** 0.5
+                dU = torch.randn(S, B, H) * (1.0 / (K - 1)) ** 1.5 / 3 ** 0.5
+                kw = {} if method is None else {"method": method}
+                pred, z = model(coeffs, times, bm=osolver.BrownianTable(dW, dU=dU), **kw)
+                out.append(dict(kind="torch_ists", method=method, input_option=io, noise_option=no,
+                                dims=(B, K, C, H, H, L), n_steps=S,
+                                state_dict={k: v.clone() for k, v in func.state_dict().items()},
+                                model_state={k: v.clone() for k, v in model.state_dict().items()},
+                                times=times, coeffs=coeffs, dW=dW, dU=dU, z=z, pred=pred))
     torch.save(out, HERE / "forward_golden.pt")
     print("forward_golden.pt:", len(out), "cases")
 
@@ -187,4 +223,4 @@ if __name__ == "__main__":
     spline_golden(cde)
     ref_f, _ = load_reference_module(REF / "benchmark_forecasting", real_cde=False)
     ref_c, _ = load_reference_module(REF / "benchmark_classification")
-    forward_golden(ref_c, ref_f)
+    forward_golden(ref_c, ref_f, load_torch_ists_module())

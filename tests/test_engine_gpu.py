@@ -195,6 +195,9 @@ def test_patch_drop_in_on_reference_style_wrapper(dev):
         def _solve_sde_path(self, times, ts, z0, kwargs):
             raise AssertionError("must be replaced by patch()")
 
+        def forward(self, times, coeffs, final_index, z0=None, stream=False, **kwargs):
+            raise AssertionError("must be replaced by patch()")
+
     B, H, C, L, K = 12, 32, 4, 1, 17
     func, times, coeffs, _ = make_problem(4, 17, B, H, C, L, K, seed=31)
     model = RefStyleNeuralSDE(func, C, H, 3)
@@ -222,7 +225,7 @@ def test_in_kernel_philox_equals_table_replay_and_matches_numpy_reference(dev):
     dt = solver.solver_dt(times)
     with torch.no_grad():
         a = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=dt, seed=1234, precision="fp32")
-        plan = mg._snsde_plans[("euler", "fp32", str(dev))]
+        plan = snsde_b200.plans_of(mg)[("euler", "fp32", str(dev))]
         sp = plan.step_plan(times, dt, times)
         dW = snsde_b200.philox_increments(1234, sp, B, H, dev)
         b = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=dt, bm=snsde_b200.BrownianIncrements(dW), precision="fp32")
@@ -255,7 +258,7 @@ def test_batch_sharding_is_bit_invariant(dev):
             mg.set_X(cg[lo:hi], tg)
             # every shard must use the GLOBAL output-time set so slots agree
             ts, slots = snsde_b200.final_index_slots(tg, fi)
-            plan = mg._snsde_plans[("euler", "fp32", str(dev))]
+            plan = snsde_b200.plans_of(mg)[("euler", "fp32", str(dev))]
             sp = plan.step_plan(ts, 1.0, tg)
             parts.append(plan.forward(yg[lo:hi], sp, coeffs=cg[lo:hi], row_slot=slots[lo:hi], seed=99, row_offset=lo))
     assert torch.equal(full, torch.cat(parts))
@@ -277,15 +280,18 @@ def test_edge_shapes_and_errors(dev):
     m.to("cpu"); m.set_X(coeffs, times)
     close(got, solver.sdeint(m, y0, times, 1.0, solver.BrownianTable(dW)))
     mg = m.to(dev); mg.set_X(coeffs.to(dev), times.to(dev))
-    with pytest.raises(RuntimeError, match="forward-only"):
-        snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0)
+    with pytest.raises(RuntimeError, match="backward pass is implemented for method='euler'"):
+        snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, method="milstein")      # never drops gradients silently
     with torch.no_grad():
         with pytest.raises(ValueError):
             snsde_b200.sdeint(mg, torch.zeros(1, 5, device=dev), times.to(dev), dt=1.0)
         with pytest.raises(ValueError):
             snsde_b200.sdeint(mg, y0.to(dev), times.flip(0).to(dev), dt=1.0)
         with pytest.raises(ValueError):
-            snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, method="srk")
+            snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, method="heun")
+        with pytest.raises(ValueError, match="dU"):
+            snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, method="srk",
+                              bm=snsde_b200.BrownianIncrements(torch.zeros(4, 1, 4)))
         with pytest.raises(ValueError):
             snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, bm=snsde_b200.BrownianIncrements(torch.zeros(3, 1, 4)))
 
@@ -330,7 +336,7 @@ def test_tc_kernel_matches_oracle(io, no, H, C, L, B, method, dev):
     ts = times[[0, 1, 2, 11, 24]]
     dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(1)) * dt ** 0.5
     got, want = run_both(m, times, coeffs, y0, ts, dt, dW, method, dev, precision="tc")
-    assert m._snsde_plans[(method, "tc", str(dev))].kernel == "tcgen05"
+    assert snsde_b200.plans_of(m)[(method, "tc", str(dev))].kernel == "tcgen05"
     close(got, want)
 
 
@@ -344,7 +350,7 @@ def test_tc_kernel_long_trajectory_c2_shape_and_philox(dev):
     with torch.no_grad():
         z_tc = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=77, precision="tc")
         z_fma = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=77, precision="fp32")
-        plan = mg._snsde_plans[("euler", "tc", str(dev))]
+        plan = snsde_b200.plans_of(mg)[("euler", "tc", str(dev))]
         assert plan.kernel == "tcgen05"
         sp = plan.step_plan(times, 1.0, times)
         dW = snsde_b200.philox_increments(77, sp, B, H, dev).cpu()
@@ -361,7 +367,7 @@ def test_tc_auto_falls_back_to_fma_when_unsupported(dev):
     mg.set_X(coeffs.to(dev), times.to(dev))
     with torch.no_grad():
         snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=1)
-        assert mg._snsde_plans[("euler", "auto", str(dev))].kernel == "fma_fp32"
+        assert snsde_b200.plans_of(mg)[("euler", "auto", str(dev))].kernel == "fma_fp32"
         with pytest.raises(ValueError, match="tensor-core"):
             snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=1, precision="tc")
 
@@ -391,7 +397,7 @@ def test_general_tc_kernel_matches_oracle(io, no, H, C, L, B, method, dev, monke
     ts = times[[0, 1, 2, 9, 20]]
     dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(1)) * dt ** 0.5
     got, want = run_both(m, times, coeffs, y0, ts, dt, dW, method, dev, precision="tc")
-    assert m._snsde_plans[(method, "tc", str(dev))].kernel == "tcgen05_general"
+    assert snsde_b200.plans_of(m)[(method, "tc", str(dev))].kernel == "tcgen05_general"
     close(got, want)
 
 
@@ -404,11 +410,11 @@ def test_general_kernel_agrees_with_resident_kernel(dev, monkeypatch):
     mg.set_X(coeffs.to(dev), times.to(dev))
     with torch.no_grad():
         a = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
-        assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05"
-        del mg._snsde_plans
+        assert snsde_b200.plans_of(mg)[("euler", "tc", str(dev))].kernel == "tcgen05"
+        snsde_b200.engine._PLANS.pop(mg, None)
         monkeypatch.setenv("SNSDE_FORCE_TCG", "1")
         b = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
-        assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05_general"
+        assert snsde_b200.plans_of(mg)[("euler", "tc", str(dev))].kernel == "tcgen05_general"
     close(b, a, rtol=1e-5)
 
 
@@ -421,7 +427,7 @@ def test_weights_in_tmem_agree_with_weights_in_smem(dev, monkeypatch):
     mg.set_X(coeffs.to(dev), times.to(dev))
     with torch.no_grad():
         a = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
-        assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05"
+        assert snsde_b200.plans_of(mg)[("euler", "tc", str(dev))].kernel == "tcgen05"
         monkeypatch.setenv("SNSDE_TC_NO_TMEM", "1")
         b = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=21, precision="tc")
         monkeypatch.delenv("SNSDE_TC_NO_TMEM")
@@ -437,7 +443,7 @@ def test_fp16_range_overflow_is_flagged_not_silent(dev):
     mg.set_X(coeffs.to(dev), times.to(dev))
     with torch.no_grad():
         snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=1, precision="tc")
-        plan = mg._snsde_plans[("euler", "tc", str(dev))]
+        plan = snsde_b200.plans_of(mg)[("euler", "tc", str(dev))]
         assert plan.status() == 0
         big = y0.clone()
         big[2, 5] = 1.0e5                                   # beyond the split-fp16 operand range

@@ -74,12 +74,12 @@ def test_c2_full_size(dev):
         mg.set_X(cg, tg)
         z_tc = snsde_b200.solve_final(mg, tg, fg, zg, seed=5, precision="tc")
         z_fma = snsde_b200.solve_final(mg, tg, fg, zg, seed=5, precision="fp32")
-        assert mg._snsde_plans[("euler", "tc", str(dev))].kernel == "tcgen05"
+        assert snsde_b200.plans_of(mg)[("euler", "tc", str(dev))].kernel == "tcgen05"
         # (1) two independent kernels, identical Philox stream
         assert rel_err(z_tc, z_fma) <= RTOL
         # (2) sharding invariance, bit for bit (4 shards, as in BASELINE config c4's 4-GPU split)
         ts, slots = snsde_b200.final_index_slots(tg, fg)
-        plan = mg._snsde_plans[("euler", "tc", str(dev))]
+        plan = snsde_b200.plans_of(mg)[("euler", "tc", str(dev))]
         sp = plan.step_plan(ts, 1.0, tg)
         parts = [plan.forward(zg[lo:lo + 256], sp, coeffs=cg[lo:lo + 256], row_slot=slots[lo:lo + 256], seed=5, row_offset=lo)
                  for lo in range(0, B, 256)]
@@ -104,7 +104,7 @@ def test_c3_full_size_milstein(dev):
         z_tc = snsde_b200.solve_final(mg, tg, fg, zg, method="milstein", seed=9, precision="tc")
         z_fma = snsde_b200.solve_final(mg, tg, fg, zg, method="milstein", seed=9, precision="fp32")
         z_eul = snsde_b200.solve_final(mg, tg, fg, zg, method="euler", seed=9, precision="tc")
-        plan = mg._snsde_plans[("milstein", "tc", str(dev))]
+        plan = snsde_b200.plans_of(mg)[("milstein", "tc", str(dev))]
         dW = snsde_b200.philox_increments(9, plan.step_plan(tg, 1.0, tg), B, H, dev).cpu()
     # ill-conditioned workload (see quantile_err): two fp32-class kernels agree on all but a sliver of elements
     assert quantile_err(z_tc, z_fma, 0.5) <= 1e-6 and quantile_err(z_tc, z_fma, 0.99) <= RTOL
@@ -127,7 +127,7 @@ def test_c4_shape_state_network_noise(dev):
     with torch.no_grad():
         mg.set_X(coeffs.to(dev), tg)
         z = snsde_b200.sdeint(mg, zg, ts.to(dev), dt=1.0, seed=3, row_offset=2048)
-        plan = next(iter(mg._snsde_plans.values()))
+        plan = next(iter(snsde_b200.plans_of(mg).values()))
         sp = plan.step_plan(ts, 1.0, tg)
         halves = [plan.forward(zg[lo:lo + 512], sp, coeffs=None, seed=3, row_offset=2048 + lo) for lo in (0, 512)]
         assert torch.equal(torch.cat(halves, dim=1), z)
@@ -154,7 +154,7 @@ def test_c5_shape_slice_natural_spline_tail(dev):
     with torch.no_grad():
         mg.set_X(coeffs.to(dev), times.to(dev))
         z = snsde_b200.sdeint(mg, z0.to(dev), ts.to(dev), dt=1.0, seed=4)
-        plan = next(iter(mg._snsde_plans.values()))
+        plan = next(iter(snsde_b200.plans_of(mg).values()))
         dW = snsde_b200.philox_increments(4, plan.step_plan(ts, 1.0, times), B, H, dev).cpu()
     o = oracle_model(m.cpu(), io, no, C, H)
     o.set_X(coeffs, times)

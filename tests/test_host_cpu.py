@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.snsde_abi_version() == 1
+    assert lib.snsde_abi_version() == 2
     nm = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", nm), name
@@ -35,6 +35,9 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Step) == 40 == snsde_b200.stepplan.STEP_DTYPE.itemsize
     assert ctypes.sizeof(_lib.Emit) == 12 == snsde_b200.stepplan.EMIT_DTYPE.itemsize
     assert ctypes.sizeof(_lib.ModelDesc) == 36
+    assert ctypes.sizeof(_lib.Point) == 20 == snsde_b200.stepplan.POINT_DTYPE.itemsize
+    for (n, _), (m, _t) in zip(_lib.Point._fields_, snsde_b200.stepplan.POINT_DTYPE.descr):
+        assert n == m
     for (n, _), (m, _t) in zip(_lib.Step._fields_, snsde_b200.stepplan.STEP_DTYPE.descr):
         assert n == m
 
@@ -66,8 +69,10 @@ def test_weight_count_tutorial_and_validation_errors():
     assert b"Unknown noise_option 20" in lib.snsde_last_error()
     bad.noise_option, bad.hidden_hidden = 17, 8          # emb needs HH == H
     assert lib.snsde_weight_count(ctypes.byref(bad)) == _lib.ERR_BAD_ARG
-    bad.hidden_hidden, bad.method = 4, 2                 # srk
+    bad.hidden_hidden, bad.method = 4, 3                 # unknown method id
     assert lib.snsde_weight_count(ctypes.byref(bad)) == _lib.ERR_UNSUPPORTED
+    bad.method = 2                                       # srk (torch-ists default) is implemented
+    assert lib.snsde_weight_count(ctypes.byref(bad)) > 0
     bad.method, bad.noise_option = 1, 18                 # milstein through the noise network (full vjp) is supported
     assert lib.snsde_weight_count(ctypes.byref(bad)) > 0
     with pytest.raises(ValueError):
@@ -188,18 +193,28 @@ def test_two_rank_gloo_all_gather_of_latents(tmp_path):
 REF = pathlib.Path("/root/reference")
 
 
-@pytest.mark.skipif(not REF.exists(), reason="reference tree not mounted (GPU box)")
-@pytest.mark.parametrize("bench_dir,io,no", [("benchmark_classification", 4, 17), ("benchmark_classification", 1, 18),
-                                              ("benchmark_forecasting", 6, 17), ("benchmark_classification", 2, 5)])
-def test_packing_and_patch_accept_the_reference_own_modules(bench_dir, io, no):
+def _golden_tools():
     sys.path.insert(0, str(ROOT / "tests" / "golden"))
     try:
         import make_golden
     finally:
         sys.path.pop(0)
-    make_golden.install_shims()
+    return make_golden
+
+
+def _drop_shims():
+    for name in ("torchcde", "torchsde", "torchdiffeq", "controldiffeq"):
+        sys.modules.pop(name, None)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("bench_dir,io,no", [("benchmark_classification", 4, 17), ("benchmark_classification", 1, 18),
+                                              ("benchmark_forecasting", 6, 17), ("benchmark_classification", 2, 5)])
+def test_packing_accepts_the_reference_own_modules(bench_dir, io, no):
+    mg = _golden_tools()
+    mg.install_shims()
     try:
-        ref, _ = make_golden.load_reference_module(REF / bench_dir, real_cde=(bench_dir == "benchmark_classification"))
+        ref, _ = mg.load_reference_module(REF / bench_dir, real_cde=(bench_dir == "benchmark_classification"))
         torch.manual_seed(0)
         func = ref.Diffusion_model(input_channels=5, hidden_channels=32, hidden_hidden_channels=32, num_hidden_layers=2,
                                    input_option=io, noise_option=no)
@@ -211,28 +226,97 @@ def test_packing_and_patch_accept_the_reference_own_modules(bench_dir, io, no):
         assert torch.equal(blob, packing.pack(own, packing.describe(own)))        # same bytes from either module
         cd = _lib.ModelDesc(method=0, precision=0, **desc)
         assert _lib.load().snsde_weight_count(ctypes.byref(cd)) == blob.numel()
-        model = ref.NeuralSDE(func, 5, 32, 3, initial=False)
-        assert snsde_b200.patch(model) is model and model._solve_sde_path.__func__.__name__ == "_solve"
+        assert all(k in dict(func.named_parameters()) for k in packing.blob_keys(desc))   # the backward returns one grad per key
+    finally:
+        _drop_shims()
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not mounted (GPU box)")
+def test_patch_dispatches_on_each_of_the_three_reference_wrappers():
+    """patch() must be correct for the classification NeuralSDE, NeuralSDE_forecasting and the torch-ists NeuralSDE
+    (the forecasting / torch-ists forwards were replaced by the classification one)."""
+    import copy
+    import io as _io
+    mg = _golden_tools()
+    mg.install_shims()
+    try:
+        ref_c, _ = mg.load_reference_module(REF / "benchmark_classification")
+        ref_f, _ = mg.load_reference_module(REF / "benchmark_forecasting", real_cde=False)
+        ref_t = mg.load_torch_ists_module()
+        mk = lambda ref: ref.Diffusion_model(5, 32, 32, 1, input_option=4, noise_option=17)       # noqa: E731
+        cls = snsde_b200.patch(ref_c.NeuralSDE(mk(ref_c), 5, 32, 3, initial=False))
+        fore = snsde_b200.patch(ref_f.NeuralSDE_forecasting(mk(ref_f), 5, 4, 32, 3, initial=True))
+        ists = snsde_b200.patch(ref_t.NeuralSDE(mk(ref_t), 5, 32, 3, initial=True))
+        assert [snsde_b200.wrapper_kind(m) for m in (cls, fore, ists)] == ["classification", "forecasting", "torch_ists"]
+        from snsde_b200 import engine
+        assert cls.forward.__func__ is engine._forward_classification
+        assert fore.forward.__func__ is engine._forward_forecasting
+        assert "forward" not in ists.__dict__                                   # torch-ists forward(coeffs, times) untouched
+        assert cls._solve_sde_path.__func__ is engine._solve_sde_path_benchmark
+        assert fore._solve_sde_path.__func__ is engine._solve_sde_path_benchmark
+        assert ists._solve_sde_path.__func__ is engine._solve_sde_path_torch_ists
+        # a deep copy drives ITS OWN func; plans (ctypes handles) are not part of the module
+        dup = copy.deepcopy(cls)
+        assert dup._solve_sde_path.__self__ is dup and dup.forward.__self__ is dup and dup.func is not cls.func
+        assert not any("snsde" in k for k in cls.func.__dict__)
+        torch.save(cls.state_dict(), _io.BytesIO())
         times = torch.arange(6.0)
         coeffs = torch.zeros(2, 5, 20)
-        if not torch.cuda.is_available():
-            with torch.no_grad(), pytest.raises(snsde_b200.EngineError):       # reaches the engine, which refuses without a GPU
-                model(times, [coeffs], torch.tensor([5, 3]), z0=torch.zeros(2, 32))
+        if not torch.cuda.is_available():       # every wrapper reaches the engine, which refuses without a GPU
+            with torch.no_grad():
+                with pytest.raises(snsde_b200.EngineError):
+                    cls(times, [coeffs], torch.tensor([5, 3]), z0=torch.zeros(2, 32))
+                with pytest.raises(snsde_b200.EngineError):
+                    dup(times, [coeffs], torch.tensor([5, 3]), z0=torch.zeros(2, 32))
+                with pytest.raises(snsde_b200.EngineError):
+                    fore(times, (coeffs[..., :5], coeffs[..., 5:10], coeffs[..., 10:15], coeffs[..., 15:]), None)
+                with pytest.raises(snsde_b200.EngineError):
+                    ists(coeffs, times)                                        # default method 'srk'
     finally:
-        for name in ("torchcde", "torchsde", "torchdiffeq", "controldiffeq"):
-            sys.modules.pop(name, None)
+        _drop_shims()
 
 
-def test_torch_ists_style_wrapper_requires_an_explicit_method():
+def test_torch_ists_style_wrapper_defaults_to_srk():
     class IstsStyle(torch.nn.Module):                      # signature of torch-ists NeuralSDE._solve_sde_path (nsde_model.py:63)
         def __init__(self):
             super().__init__()
             self.func = vector_field.DiffusionModel(3, 8, 8, 1, input_option=4, noise_option=17)
-    m = snsde_b200.patch(IstsStyle(), fuse_final_index=False)
-    with pytest.raises(ValueError, match="srk"):
-        m._solve_sde_path(torch.arange(4.0), torch.zeros(2, 8), {})
-    with pytest.raises(ValueError, match="srk"):
-        m._solve_sde_path(torch.arange(4.0), torch.zeros(2, 8), {"method": "srk"})
+
+        def _solve_sde_path(self, times, y0, kwargs):
+            raise AssertionError("replaced by patch()")
+
+        def forward(self, coeffs, times, **kwargs):
+            return self._solve_sde_path(times, torch.zeros(coeffs.shape[0], 8), kwargs)
+    m = snsde_b200.patch(IstsStyle())
+    assert snsde_b200.wrapper_kind(m) == "torch_ists" and "forward" not in m.__dict__
+    if not torch.cuda.is_available():
+        with torch.no_grad(), pytest.raises(snsde_b200.EngineError):
+            m(torch.zeros(2, 3, 12), torch.arange(4.0))
+    with pytest.raises(ValueError, match="not implemented"):
+        with torch.no_grad():
+            m(torch.zeros(2, 3, 12), torch.arange(4.0), method="heun")
+
+
+def test_step_plan_dense_states_and_srk_points():
+    sp = snsde_b200.build_step_plan(np.array([0.0, 0.25, 1.0], dtype=np.float32), 0.4, np.linspace(0, 1, 5, dtype=np.float32),
+                                    method="srk")
+    S = sp.n_steps
+    assert S == 3 and sp.points.shape == (S, 4)
+    h, t0 = sp.steps["h"], sp.steps["t0"]
+    for i, c in enumerate((0.0, 0.25, 0.5, 1.0)):
+        t = (t0 + np.float32(c) * h).astype(np.float32)
+        assert np.array_equal(sp.points["t"][:, i], t)
+        assert np.allclose(sp.points["sin_t"][:, i], np.sin(t))
+        kn = np.linspace(0, 1, 5, dtype=np.float32)
+        idx = np.clip(np.searchsorted(kn, t, side="left") - 1, 0, 3)
+        assert np.array_equal(sp.points["interval"][:, i], idx)
+    d = sp.dense()
+    assert d.n_out == S + 1 and len(d.emits) == S + 1 and np.array_equal(d.emits["slot"], np.arange(S + 1))
+    assert np.array_equal(d.steps["emit_begin"], np.arange(1, S + 1)) and np.all(d.emits["w_curr"] == 1)
+    slot, k, wp, wc = sp.output_map()
+    # ts[1] = 0.25 falls inside step 0 (0 -> 0.4): lerp of Y[0], Y[1]; ts[2] = 1.0 is the end of the last step
+    assert list(slot) == [0, 1, 2] and list(k) == [-1, 0, S - 1]
+    assert abs(wp[1] - 0.375) < 1e-6 and abs(wc[1] - 0.625) < 1e-6 and wp[2] == 0 and wc[2] == 1
 
 
 def test_bench_algorithmic_costs_match_the_survey_contract():

@@ -102,6 +102,14 @@ def test_forward_wrappers_match_reference(golden_dir):
         bm = solver.BrownianTable(c["dW"])
         if c["kind"] == "classification":
             z = wrapper.classification_latent(m, c["times"], c["coeffs"], c["final_index"], c["z0"], bm)
+        elif c["kind"] == "torch_ists":          # nsde_model.py:76-84: every knot, default method 'srk'
+            m.set_X(c["coeffs"], c["times"])
+            init = torch.nn.Linear(c["dims"][2], c["dims"][3])
+            init.load_state_dict({k.split(".", 1)[1]: v for k, v in c["model_state"].items() if k.startswith("initial_network.")})
+            with torch.no_grad():
+                z0 = init(m.X.evaluate(c["times"][0]))
+            bm = solver.BrownianTable(c["dW"], dU=c["dU"])
+            z = wrapper.streamed_latent(m, c["times"], c["coeffs"], z0, bm, method=c["method"] or "srk")
         else:
             m.set_X(c["coeffs"], c["times"])
             init = torch.nn.Linear(c["dims"][2], c["dims"][3])
@@ -177,6 +185,75 @@ def test_milstein_matches_closed_form_for_gbm():
     for k in range(5):
         y = y + 0.1 * y * 0.1 + 0.4 * y * dW[k] + 0.5 * 0.4 * 0.4 * y * (dW[k] ** 2 - 0.1)
     assert torch.allclose(out[-1], y, atol=1e-12)
+
+
+class _Lin(torch.nn.Module):
+    sde_type, noise_type = "ito", "diagonal"
+
+    def f(self, t, y):
+        return -0.8 * y
+
+    def g(self, t, y):
+        return torch.zeros_like(y)
+
+
+def test_srk_without_noise_is_the_third_order_taylor_step():
+    # SRID2 drift part: H0_1 = y + f0 h, H0_2 = y + (f0 + f1) h/4, y1 = y + h (f0 + f1 + 4 f2)/6; for f = a y this is
+    # y (1 + z + z^2/2 + z^3/6), z = a h
+    ts = torch.tensor([0.0, 0.3], dtype=torch.float64)
+    y0 = torch.rand(3, 2, dtype=torch.float64) + 0.5
+    z = torch.zeros(1, 3, 2, dtype=torch.float64)
+    out = solver.sdeint(_Lin(), y0, ts, 0.3, solver.BrownianTable(z, dU=z), method="srk")
+    zz = -0.8 * 0.3
+    assert torch.allclose(out[-1], y0 * (1 + zz + zz ** 2 / 2 + zz ** 3 / 6), atol=1e-14)
+
+
+def _coarsen(Wf, hf, n):
+    """(dW, U) of n coarse steps from a fine Brownian path Wf [n_fine+1, P, 1]: U_k = int (W_s - W_t0) ds over the
+    coarse step (trapezoid on the fine path)."""
+    n_fine, P = Wf.shape[0] - 1, Wf.shape[1]
+    m = n_fine // n
+    Wc = Wf[::m]
+    lo, hi = Wf[:-1].reshape(n, m, P, 1), Wf[1:].reshape(n, m, P, 1)
+    U = (0.5 * (lo + hi) - Wc[:-1].unsqueeze(1)).sum(1) * hf
+    return Wc[1:] - Wc[:-1], U
+
+
+def test_srk_has_strong_order_1p5_and_needs_the_space_time_levy_integral():
+    """Pins the SRID2 tableau and the U convention (I_k0 = int_t0^t1 (W_s - W_t0) ds) structurally.
+    GBM (exact solution known): strong error falls ~2^1.5 per halving of h, Milstein ~2^1.  GBM cannot see U
+    (L0 b = L1 a there), so an OU process (additive noise, L1 a = -theta sigma, L0 b = 0) checks it: with the true
+    U the error keeps order 1.5, with Hst = 0 (U = h W/2) it degrades to order 1."""
+    torch.manual_seed(3)
+    n_fine, P = 2 ** 13, 600
+    hf = 1.0 / n_fine
+    dWf = torch.randn(n_fine, P, 1, dtype=torch.float64) * hf ** 0.5
+    Wf = torch.cat([torch.zeros(1, P, 1, dtype=torch.float64), dWf.cumsum(0)])
+    y0 = torch.ones(P, 1, dtype=torch.float64)
+    ts = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    exact = torch.exp((0.1 - 0.5 * 0.4 ** 2) * 1.0 + 0.4 * Wf[-1])
+    errs, errs_mil = [], []
+    for n in (8, 32):
+        dW, U = _coarsen(Wf, hf, n)
+        y = solver.sdeint(_GBM(), y0, ts, 1.0 / n, solver.BrownianTable(dW, dU=U), method="srk")[-1]
+        errs.append(float((y - exact).abs().mean()))
+        y = solver.sdeint(_GBM(), y0, ts, 1.0 / n, solver.BrownianTable(dW), method="milstein")[-1]
+        errs_mil.append(float((y - exact).abs().mean()))
+    order, order_mil = np.log2(errs[0] / errs[1]) / 2, np.log2(errs_mil[0] / errs_mil[1]) / 2
+    assert order > 1.3 and 0.8 < order_mil < 1.2 and errs[1] < 0.2 * errs_mil[1], (errs, errs_mil)
+
+    ou = _OU(1.5, 0.0, 0.5)
+    dW, U = _coarsen(Wf, hf, 1024)
+    ref = solver.sdeint(ou, y0, ts, 1.0 / 1024, solver.BrownianTable(dW, dU=U), method="srk")[-1]
+    e_true, e_wrong = [], []
+    for n in (8, 32):
+        dW, U = _coarsen(Wf, hf, n)
+        y = solver.sdeint(ou, y0, ts, 1.0 / n, solver.BrownianTable(dW, dU=U), method="srk")[-1]
+        e_true.append(float((y - ref).abs().mean()))
+        y = solver.sdeint(ou, y0, ts, 1.0 / n, solver.BrownianTable(dW, dU=0.5 * dW / n), method="srk")[-1]
+        e_wrong.append(float((y - ref).abs().mean()))
+    o_true, o_wrong = np.log2(e_true[0] / e_true[1]) / 2, np.log2(e_wrong[0] / e_wrong[1]) / 2
+    assert o_true > 1.3 and o_wrong < 1.15 and e_true[1] < 0.2 * e_wrong[1], (e_true, e_wrong, o_true, o_wrong)
 
 
 def test_philox_known_answers():
