@@ -426,31 +426,38 @@ struct PlanStreamGuard {
   }
 };
 
-// Row groups per CTA, warps per group and the staged share of the weight image for the FMA-style kernels.
+// Rows per group, row groups per CTA, warps per group and whether the weight image is staged in shared memory, for
+// the FMA-style kernels.  group_floats(R) = shared-memory floats one group needs.
 struct GroupConfig { int R, nw, groups, smem_w_floats; size_t smem; };
-static bool pick_group_config(const snsde_plan* p, int B, size_t group_floats_r4, size_t group_floats_r8, bool allow_r8,
-                              GroupConfig& g) {
+template <typename F>
+static bool pick_group_config(const snsde_plan* p, int B, F group_floats, bool allow_r8, GroupConfig& g) {
   const Program& pg = p->prog;
   g.nw = (std::max(pg.H, pg.HH) + 31) / 32;
   const int max_threads = g.nw > 16 ? 1024 : 512;
-  // 8 rows per group amortise each weight read over twice the FMAs; keep 4 while that still fills the machine
-  g.R = (allow_r8 && g.nw <= 16 && (B + 3) / 4 > 4 * p->num_sms) ? 8 : 4;
-  const size_t gf = (g.R == 8 ? group_floats_r8 : group_floats_r4) * sizeof(float);
-  if (gf > (size_t)p->smem_optin) {
-    if (g.R == 8 && group_floats_r4 * sizeof(float) <= (size_t)p->smem_optin) { g.R = 4; return pick_group_config(p, B, group_floats_r4, group_floats_r8, false, g); }
-    return false;
+  const size_t optin = (size_t)p->smem_optin, img = (size_t)p->wimg_floats * sizeof(float);
+  const bool img_fits = img + group_floats(4) * sizeof(float) <= optin;
+  // Parallelism first: the chain of dependent ops makes every group latency-bound, so small batches take fewer rows per
+  // group (down to one) until there is about a warp per scheduler; 8 rows per group amortise each weight read over
+  // twice the FMAs and pay when the image is read through L2 or the batch is large.
+  const int want_warps = 4 * p->num_sms;
+  int R = 1;
+  if (g.nw > 16) R = 4;
+  else if (allow_r8 && (B / 8) * g.nw >= (img_fits ? want_warps : p->num_sms / 2)) R = 8;
+  else if ((B / 4) * g.nw >= p->num_sms / 2) R = 4;
+  for (;; R = (R == 8 ? 4 : 1)) {
+    if (group_floats(R) * sizeof(float) <= optin) break;
+    if (R == 1 || (R == 4 && g.nw > 16)) return false;
   }
-  const int n_groups = (B + g.R - 1) / g.R;
-  int G = std::max(1, n_groups / std::max(1, p->num_sms));           // one wave of CTAs first
-  G = std::min(G, std::min(15, max_threads / (g.nw * 32)));           // 15 named barriers, thread limit
+  g.R = R;
+  const size_t gf = group_floats(R) * sizeof(float);
+  const int n_groups = (B + R - 1) / R;
+  int G = std::max(1, n_groups / std::max(1, p->num_sms));             // one wave of CTAs first
+  G = std::min(G, std::min(15, max_threads / (g.nw * 32)));             // 15 named barriers, thread limit
   G = std::max(G, 1);
-  while (G > 1 && (size_t)G * gf > (size_t)p->smem_optin) --G;
-  // trade groups for staged weights while the whole image does not fit beside them
-  const size_t img = (size_t)p->wimg_floats * sizeof(float);
-  while (G > 1 && (size_t)G * gf + img > (size_t)p->smem_optin && (size_t)(G - 1) * gf + img <= (size_t)p->smem_optin) --G;
+  while (G > 1 && (size_t)G * gf > optin) --G;
+  while (G > 1 && (size_t)G * gf + img > optin && gf + img <= optin) --G;   // trade groups for the staged image
   g.groups = G;
-  const size_t room = ((size_t)p->smem_optin - (size_t)G * gf) / sizeof(float);
-  g.smem_w_floats = (int)std::min<size_t>((size_t)p->wimg_floats, room) & ~3;
+  g.smem_w_floats = ((size_t)G * gf + img <= optin) ? p->wimg_floats : 0;   // all or nothing
   g.smem = (size_t)g.smem_w_floats * sizeof(float) + (size_t)G * gf;
   return true;
 }
@@ -684,7 +691,8 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
   fp.vtab = nullptr;
 
   GroupConfig gc;
-  if (!pick_group_config(p, B, fma_group_smem_floats(pg, 4, p->desc.method), fma_group_smem_floats(pg, 8, p->desc.method), !srk, gc))
+  const int method_ = p->desc.method;
+  if (!pick_group_config(p, B, [&](int R) { return fma_group_smem_floats(pg, R, method_); }, !srk, gc))
     return fail(SNSDE_ERR_UNSUPPORTED, "activation buffers do not fit in shared memory");
   fp.groups = gc.groups; fp.nw = gc.nw; fp.smem_w_floats = gc.smem_w_floats;
   if (pg.tail.coef_src == CO_VBUF && S > 0) {
@@ -811,9 +819,9 @@ int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_str
     p->launches += 1;
   }
   GroupConfig gc;
-  const size_t gf = bwd_group_smem_floats(pg, L.n_rops, 4, L.has_lipswish);
-  if (!pick_group_config(p, B, gf, gf, false, gc))
-    return fail(SNSDE_ERR_UNSUPPORTED, "the backward pass keeps every activation of a step in shared memory: hidden size too large (%zu bytes per row group)", gf * sizeof(float));
+  if (!pick_group_config(p, B, [&](int R) { return bwd_group_smem_floats(pg, L.n_rops, R, L.has_lipswish); }, false, gc))
+    return fail(SNSDE_ERR_UNSUPPORTED, "the backward pass keeps every activation of a step in shared memory: hidden size too large (%zu bytes per row group)",
+                bwd_group_smem_floats(pg, L.n_rops, 1, L.has_lipswish) * sizeof(float));
   bp.groups = gc.groups; bp.nw = gc.nw; bp.smem_w_floats = gc.smem_w_floats;
   cudaError_t e = bwd_fill_aux(p->d_steps, S, B, ws + L.aux, stream);
   if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "aux kernel launch: %s", cudaGetErrorString(e));

@@ -27,7 +27,7 @@
 
 namespace snsde {
 
-template <int R, int NTMAX>
+template <int R, int NTMAX, bool WS>
 __global__ void __launch_bounds__(NTMAX) snsde_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) float smem[];
   const Program& pg = p.prog;
@@ -41,9 +41,12 @@ __global__ void __launch_bounds__(NTMAX) snsde_bwd_kernel(const BwdParams p) {
   // ---- shared memory: [weights][group: Y X D | post[n_rops] | cot[n_rops] | pre[n_rops]? | 2 spline stages] ----
   const int stage_floats = pg.uses_control ? R * 4 * C : 0;
   const int group_floats = (3 + n_rops * (p.has_lipswish ? 3 : 2)) * slot + 2 * stage_floats;
-  for (int i = threadIdx.x; i < p.smem_w_floats; i += blockDim.x) smem[i] = p.wimg[i];
-  __syncthreads();
-  float* const gbase = smem + p.smem_w_floats + gid * group_floats;
+  if (WS) {
+    stage_weights(smem, p.wimg, p.smem_w_floats);
+    __syncthreads();
+  }
+  const float* __restrict__ const W = WS ? smem : p.wimg;
+  float* const gbase = smem + (WS ? p.smem_w_floats : 0) + gid * group_floats;
   float* const sY = gbase;
   float* const sX = gbase + slot;
   float* const sD = gbase + 2 * slot;
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(NTMAX) snsde_bwd_kernel(const BwdParams p) {
     float y[R], w[R];
     float vcoef = t.coef_scalar;
     if (jact) {
-      if (t.coef_src == CO_IMG) vcoef = p.wimg[t.coef_ref + tid];
+      if (t.coef_src == CO_IMG) vcoef = W[t.coef_ref + tid];
       else if (t.coef_src == CO_VBUF) vcoef = p.vtab[(size_t)s * H + tid];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -146,18 +149,15 @@ __global__ void __launch_bounds__(NTMAX) snsde_bwd_kernel(const BwdParams p) {
         // dense_eval reads sm.buf(id): resolve the producing slots by hand
         float a[R];
         {
-          auto wptr = [&](int off, int count) -> const float* {
-            return (off + count <= p.smem_w_floats) ? smem + off : p.wimg + off;
-          };
-          float init = op.b_off >= 0 ? wptr(op.b_off, op.N)[tid] : 0.f;
+          float init = op.b_off >= 0 ? W[op.b_off + tid] : 0.f;
           if (op.tmode == TM_SINCOS) {
-            const float* tw = wptr(op.tw_off, 2 * op.N);
+            const float* tw = W + op.tw_off;
             init = fmaf(tp.cos_t, tw[op.N + tid], fmaf(tp.sin_t, tw[tid], init));
           }
 #pragma unroll
           for (int r = 0; r < R; ++r) a[r] = init;
-          if (op.src >= 0) dot_accumulate<R>(a, buf_of(op.src_op, op.src), ld, wptr(op.w_off, op.K * op.N) + tid, op.K, op.N);
-          if (op.src2 >= 0) dot_accumulate<R>(a, buf_of(op.src2_op, op.src2), ld, wptr(op.w2_off, op.K2 * op.N) + tid, op.K2, op.N);
+          if (op.src >= 0) dot_accumulate<R>(a, buf_of(op.src_op, op.src), ld, W + op.w_off + tid, op.K, op.N);
+          if (op.src2 >= 0) dot_accumulate<R>(a, buf_of(op.src2_op, op.src2), ld, W + op.w2_off + tid, op.K2, op.N);
         }
         if (op.final_drift) {
 #pragma unroll
@@ -351,9 +351,9 @@ size_t bwd_group_smem_floats(const Program& pg, int n_rops, int R, int has_lipsw
   return f;
 }
 
-template <int R, int NTMAX>
+template <int R, int NTMAX, bool WS>
 static cudaError_t bwd_launch_one(const BwdParams& p, int grid, int nt, size_t smem, cudaStream_t stream) {
-  auto kern = snsde_bwd_kernel<R, NTMAX>;
+  auto kern = snsde_bwd_kernel<R, NTMAX, WS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, nt, smem, stream>>>(p);
@@ -364,8 +364,10 @@ cudaError_t bwd_launch(const BwdParams& p, int R, size_t smem, cudaStream_t stre
   const int nt = p.groups * p.nw * 32;
   const int n_groups = (p.B + R - 1) / R;
   const int grid = (n_groups + p.groups - 1) / p.groups;
-  if (R == 4 && nt <= 512) return bwd_launch_one<4, 512>(p, grid, nt, smem, stream);
-  if (R == 4) return bwd_launch_one<4, 1024>(p, grid, nt, smem, stream);
+  const bool ws = p.smem_w_floats > 0;
+  if (R == 4 && nt <= 512) return ws ? bwd_launch_one<4, 512, true>(p, grid, nt, smem, stream) : bwd_launch_one<4, 512, false>(p, grid, nt, smem, stream);
+  if (R == 1 && nt <= 512) return ws ? bwd_launch_one<1, 512, true>(p, grid, nt, smem, stream) : bwd_launch_one<1, 512, false>(p, grid, nt, smem, stream);
+  if (R == 4) return ws ? bwd_launch_one<4, 1024, true>(p, grid, nt, smem, stream) : bwd_launch_one<4, 1024, false>(p, grid, nt, smem, stream);
   return cudaErrorInvalidValue;
 }
 

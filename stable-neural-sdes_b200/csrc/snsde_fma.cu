@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(1024) vec_tables_kernel(const Program pg, cons
 }
 
 // ---- the solve ---------------------------------------------------------------------------------------
-template <int R, int NTMAX, int METHOD>
+// WS: the whole weight image is staged in shared memory (true) or read through L1/L2 (false: it does not fit).
+template <int R, int NTMAX, int METHOD, bool WS>
 __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
   extern __shared__ __align__(16) float smem[];
   const Program& pg = p.prog;
@@ -78,11 +79,13 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
   // ---- shared memory: [weights][group 0: row bufs, spline stages][group 1 ...] ----
   const int stage_floats = pg.uses_control ? R * 4 * C : 0;
   const int group_floats = kNumRowBufs * R * ld + 2 * NP * stage_floats;
-  for (int i = threadIdx.x; i < p.smem_w_floats; i += blockDim.x) smem[i] = p.wimg[i];
-  __syncthreads();                                          // the only CTA-wide barrier
+  if (WS) {
+    stage_weights(smem, p.wimg, p.smem_w_floats);
+    __syncthreads();                                        // the only CTA-wide barrier
+  }
+  const float* __restrict__ const W = WS ? smem : p.wimg;
   GroupSmem sm;
-  sm.w = smem;
-  sm.base = smem + p.smem_w_floats + gid * group_floats;
+  sm.base = smem + (WS ? p.smem_w_floats : 0) + gid * group_floats;
   sm.row_buf_floats = R * ld;
   sm.stage0 = sm.base + kNumRowBufs * R * ld;
   sm.stage_floats = stage_floats;
@@ -174,10 +177,10 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
       gsync();                              // op o reads what an earlier op (or the state writer) wrote
       if (tid < op.N) {
         if (op.final_drift) {
-          dense_eval<R>(acc, op, p.wimg, sm.w, p.smem_w_floats, sm, ld, tp, tid);
+          dense_eval<R>(acc, op, W, sm, ld, tp, tid);
         } else {
           float a[R];
-          dense_eval<R>(a, op, p.wimg, sm.w, p.smem_w_floats, sm, ld, tp, tid);
+          dense_eval<R>(a, op, W, sm, ld, tp, tid);
           float* dst = sm.buf(op.dst);
 #pragma unroll
           for (int r = 0; r < R; ++r) dst[r * ld + tid] = a[r];
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
   };
   auto vcoef_at = [&](int s, int q) {
     float v = t.coef_scalar;
-    if (t.coef_src == CO_IMG) v = p.wimg[t.coef_ref + tid];
+    if (t.coef_src == CO_IMG) v = W[t.coef_ref + tid];
     else if (t.coef_src == CO_VBUF) v = p.vtab[((size_t)s * NPG + q) * H + tid];
     return v;
   };
@@ -429,25 +432,33 @@ size_t fma_group_smem_floats(const Program& pg, int R, int method) {
   return f;
 }
 
-template <int R, int NTMAX, int METHOD>
+template <int R, int NTMAX, int METHOD, bool WS>
 static cudaError_t launch_one(const FmaParams& p, int grid, int nt, size_t smem, cudaStream_t stream) {
-  auto kern = snsde_fma_kernel<R, NTMAX, METHOD>;
+  auto kern = snsde_fma_kernel<R, NTMAX, METHOD, WS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, nt, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
+template <int R, int NTMAX>
+static cudaError_t launch_rn(const FmaParams& p, int method, int grid, int nt, size_t smem, cudaStream_t stream) {
+  const bool ws = p.smem_w_floats > 0;
+  if (method == SNSDE_METHOD_SRK)
+    return ws ? launch_one<R, NTMAX, 1, true>(p, grid, nt, smem, stream) : launch_one<R, NTMAX, 1, false>(p, grid, nt, smem, stream);
+  return ws ? launch_one<R, NTMAX, 0, true>(p, grid, nt, smem, stream) : launch_one<R, NTMAX, 0, false>(p, grid, nt, smem, stream);
+}
+
 cudaError_t fma_launch(const FmaParams& p, int R, int method, size_t smem, cudaStream_t stream) {
   const int nt = p.groups * p.nw * 32;
   const int n_groups = (p.B + R - 1) / R;
   const int grid = (n_groups + p.groups - 1) / p.groups;
-  const bool srk = method == SNSDE_METHOD_SRK;
   if (nt <= 512) {
-    if (R == 8) return srk ? launch_one<8, 512, 1>(p, grid, nt, smem, stream) : launch_one<8, 512, 0>(p, grid, nt, smem, stream);
-    if (R == 4) return srk ? launch_one<4, 512, 1>(p, grid, nt, smem, stream) : launch_one<4, 512, 0>(p, grid, nt, smem, stream);
+    if (R == 8 && method != SNSDE_METHOD_SRK) return launch_rn<8, 512>(p, method, grid, nt, smem, stream);
+    if (R == 4) return launch_rn<4, 512>(p, method, grid, nt, smem, stream);
+    if (R == 1) return launch_rn<1, 512>(p, method, grid, nt, smem, stream);
   } else if (R == 4) {
-    return srk ? launch_one<4, 1024, 1>(p, grid, nt, smem, stream) : launch_one<4, 1024, 0>(p, grid, nt, smem, stream);
+    return launch_rn<4, 1024>(p, method, grid, nt, smem, stream);
   }
   return cudaErrorInvalidValue;
 }

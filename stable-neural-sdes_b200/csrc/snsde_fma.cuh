@@ -27,20 +27,31 @@ struct GroupSmem {
   int row_buf_floats;    // R * ld
   float* stage0;         // 2 x NP spline stages of stage_floats each
   int stage_floats;
-  const float* w;        // staged weights (first smem_w_floats of the image), shared by the CTA
   __device__ __forceinline__ float* buf(int id) const { return base + id * row_buf_floats; }
 };
 
-// acc[r] += sum_k src[r][k] * w[k * stride + j]      (w already offset by j)
+// Copies the weight image into shared memory (whole CTA, 16-byte accesses); the caller synchronises.
+__device__ __forceinline__ void stage_weights(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const int n4 = n_floats >> 2;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = s4[i];
+}
+
+// acc[r] += sum_k src[r][k] * w[k * stride]      (w already offset by the thread's output feature)
+// The weight pointer walks by `stride`; its address space (shared when the image is staged, global otherwise) is a
+// compile-time property of the calling kernel, so these are plain LDS / LDG with immediate offsets.
 template <int ROWS>
 __device__ __forceinline__ void dot_accumulate(float (&acc)[ROWS], const float* __restrict__ src, int ld,
                                                const float* __restrict__ w, int K, int stride) {
-  int k = 0;
   const int K4 = K & ~3;
+  const int s2 = 2 * stride, s3 = 3 * stride, s4 = 4 * stride;
+  const float* wk = w;
+  int k = 0;
 #pragma unroll 2
-  for (; k < K4; k += 4) {
-    const float w0 = w[(size_t)k * stride], w1 = w[(size_t)(k + 1) * stride];
-    const float w2 = w[(size_t)(k + 2) * stride], w3 = w[(size_t)(k + 3) * stride];
+  for (; k < K4; k += 4, wk += s4) {
+    const float w0 = wk[0], w1 = wk[stride], w2 = wk[s2], w3 = wk[s3];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const float4 a = *reinterpret_cast<const float4*>(src + r * ld + k);
@@ -50,10 +61,10 @@ __device__ __forceinline__ void dot_accumulate(float (&acc)[ROWS], const float* 
       acc[r] = fmaf(a.w, w3, acc[r]);
     }
   }
-  for (; k < K; ++k) {
-    const float wk = w[(size_t)k * stride];
+  for (; k < K; ++k, wk += stride) {
+    const float wv = wk[0];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(src[r * ld + k], wk, acc[r]);
+    for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(src[r * ld + k], wv, acc[r]);
   }
 }
 
@@ -72,24 +83,21 @@ __device__ __forceinline__ void dot_rows_T(float (&acc)[ROWS], const float* __re
 struct TimePoint { float t, sin_t, cos_t; };
 
 // Pre-activation (ACT = false) or activated output of one dense op for the R rows of a group, feature j.
+// W = base of the weight image in the address space the kernel was compiled for.
 template <int ROWS, bool ACT = true>
-__device__ __forceinline__ void dense_eval(float (&acc)[ROWS], const DenseOp& op, const float* wimg,
-                                           const float* wsm, int smem_w_floats,
+__device__ __forceinline__ void dense_eval(float (&acc)[ROWS], const DenseOp& op, const float* __restrict__ W,
                                            const GroupSmem& sm, int ld, const TimePoint& tp, int j) {
-  auto wptr = [&](int off, int count) -> const float* {
-    return (off + count <= smem_w_floats) ? wsm + off : wimg + off;
-  };
-  float init = op.b_off >= 0 ? wptr(op.b_off, op.N)[j] : 0.f;
+  float init = op.b_off >= 0 ? W[op.b_off + j] : 0.f;
   if (op.tmode == TM_SINCOS) {
-    const float* tw = wptr(op.tw_off, 2 * op.N);
+    const float* tw = W + op.tw_off;
     init = fmaf(tp.cos_t, tw[op.N + j], fmaf(tp.sin_t, tw[j], init));
   } else if (op.tmode == TM_RAW) {
-    init = fmaf(tp.t, wptr(op.tw_off, op.N)[j], init);
+    init = fmaf(tp.t, W[op.tw_off + j], init);
   }
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) acc[r] = init;
-  if (op.src >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src), ld, wptr(op.w_off, op.K * op.N) + j, op.K, op.N);
-  if (op.src2 >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src2), ld, wptr(op.w2_off, op.K2 * op.N) + j, op.K2, op.N);
+  if (op.src >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src), ld, W + op.w_off + j, op.K, op.N);
+  if (op.src2 >= 0) dot_accumulate<ROWS>(acc, sm.buf(op.src2), ld, W + op.w2_off + j, op.K2, op.N);
   if (ACT) {
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] = act_apply(acc[r], op.act);
