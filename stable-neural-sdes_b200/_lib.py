@@ -3,7 +3,8 @@ import ctypes
 import pathlib
 
 HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = HERE / "libsnsde.so"
+import os
+LIB_PATH = HERE / ("libsnsde_trace.so" if os.environ.get("SNSDE_TRACE_BUILD") else "libsnsde.so")
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_WEIGHTS, ERR_INTERNAL = 0, -1, -2, -3, -4, -5
 ABI_VERSION = 2

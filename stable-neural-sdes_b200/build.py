@@ -20,8 +20,10 @@ import os
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
-if os.environ.get("SNSDE_TRACE_BUILD"):       # debug build: compiles the clock64 trace events into the tcgen05 kernels
-    NVCC_FLAGS.append("-DSNSDE_TC_TRACE_BUILD")
+if os.environ.get("SNSDE_TRACE_BUILD"):       # debug build: compiles the clock64 trace events into the tcgen05 kernels;
+    NVCC_FLAGS.append("-DSNSDE_TC_TRACE_BUILD")   # a separate library (loaded when SNSDE_TRACE_BUILD is set), own object cache
+    OBJ = HERE / "build_trace"
+    LIB = HERE / "libsnsde_trace.so"
 
 
 def _headers_hash():
@@ -53,7 +55,7 @@ def build(force=False, verbose=False):
     # whole-library fingerprint next to the .so: lets a snapshot without the object cache (GPU box) skip the build
     lib_fp = hashlib.sha256("".join(hashlib.sha256(s.read_bytes()).hexdigest() for s in sources).encode()
                             + hdr_hash.encode()).hexdigest()
-    lib_stamp = HERE / ".libsnsde.stamp"
+    lib_stamp = HERE / ("." + LIB.stem + ".stamp")
     if not force and LIB.exists() and lib_stamp.exists() and lib_stamp.read_text() == lib_fp:
         return LIB
     OBJ.mkdir(exist_ok=True)
