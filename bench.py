@@ -259,7 +259,9 @@ def bind_to_gpu_numa(local_rank):
         if allowed:
             os.sched_setaffinity(0, allowed)
         return node
-    except Exception:                                    # noqa: BLE001
+    except Exception as exc:                             # noqa: BLE001
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"[bench] NUMA binding skipped: {exc!r}", file=sys.stderr)
         return None
 
 

@@ -76,7 +76,7 @@ constexpr int kBarPEmpty = 5;                       // +slot: epilogue warps arr
 
 
 struct TcSmem {
-  int w, b, x, stg, prep, bias, bars, total;
+  int w, b, x, stg, prep, bias, outst, bars, total;
   int lbo_b;            // bytes between K chunks (8 columns) of a B operand
   int x_slot_bytes, stg_bytes, prep_bytes;
 };
@@ -95,7 +95,8 @@ __host__ __device__ inline TcSmem tc_smem_layout(int wimg_bytes, int H, int C, i
   s.prep = (s.stg + nstg * s.stg_bytes + 15) & ~15;
   s.prep_bytes = (NR + 2) * 128 * 4 + 32;
   s.bias = s.prep + 2 * s.prep_bytes;                // [kTcMaxLayers][128] per-layer bias vectors
-  s.bars = s.bias + kTcMaxLayers * 512;
+  s.outst = s.bias + kTcMaxLayers * 512;             // output staging ring: 2 x ([NR][H] floats + 16-byte header)
+  s.bars = s.outst + 2 * (NR * H * 4 + 16);
   s.total = s.bars + 8 * (2 + 2 * nx + nstg + 4) + 16;
   return s;
 }
@@ -274,6 +275,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* bact = smem + L.b + (h >> 3) * L.lbo_b + (h & 7) * 2;       // + (r/8)*128 + (r%8)*16 ; lo: + (N/8)*128
     float vmax = 0.f;
+    // (A 4x4 lane transpose that turns the four 2-byte operand stores of a thread into one 8-byte store was measured:
+    //  the two dependent shuffles cost more than the stores they save - layer epilogues +170..190 cycles.)
     auto write_operand = [&](int r, float v) {
       __half hi, lo;
       split_f16(v, hi, lo);
@@ -443,6 +446,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
               yn[i] = __fadd_rn(yn[i], 0.5f * ((g[i] * v2) * dgy[i]));
             }
           }
+          // Output of this step (torchsde linear_interp between the two states) -> staging ring; the MMA warp sends it
+          // to HBM with TMA bulk stores once this hand-over has made it visible to the async proxy.  The epilogue issues
+          // no global store in the time loop: its hand-over fence (fence.proxy.async = MEMBAR.ALL.CTA) would wait for the
+          // store's round trip to L2 (clock trace: ~430 cycles per step when the emits were plain stores here).
+          {
+            float* ost = reinterpret_cast<float*>(smem + L.outst + (s & 1) * (NR * H * 4 + 16));
+            if (si.n_emits > 0) {
+              // per-row final_index capture: only the rows whose slot this is are staged (a handful per step; every
+              // shared-memory store in flight lengthens the hand-over fence by ~50 cycles)
+#pragma unroll
+              for (int i = 0; i < RT; ++i)
+                if (p.row_slot == nullptr || myslot[i] == si.first.slot)
+                  ost[4 + (rbase + i) * H + h] = si.first.w_prev * y[i] + si.first.w_curr * yn[i];
+            }
+          }
 #pragma unroll
           for (int i = 0; i < RT; ++i) {
             yprev[i] = y[i];
@@ -458,8 +476,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       }
       // ---- in the shadow of the next step's layer-0 MMAs ----
       named_arrive(kBarPEmpty + (s & 1), kCntPrep);                     // slot consumed
-      if (si.n_emits > 0) emit(si.first);
-      for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);
+      for (int e = 1; e < si.n_emits; ++e) emit(p.emits[si.emit_begin + e]);      // several output times inside one step: rare
       TC_TRACE(tid == 0, s, EV_EPI_SHADOW_END);
     }
     if (vmax > 65504.f) *p.status = 1;              // an operand beyond the fp16 range was saturated (sticky flag)
@@ -484,6 +501,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
       return seg_ops(ts, ((ts & 1) ? tmem : w_base) + p.hx_hi, ((ts & 2) ? tmem : w_base) + p.hx_lo,
                      x_base + slot * L.x_slot_bytes, Cpad / 16, L.lbo_b, tmem + dcol(0), true);
     };
+    // Outputs of step s: staged by the epilogue before the hand-over that woke this warp; sent with bulk async copies
+    // (lane r = row r for the per-row final_index capture, one copy of the whole [rows][H] block for streamed outputs).
+    const int my_row_slot = (p.row_slot != nullptr && lane < NR) ? p.row_slot[min(row0 + lane, p.B - 1)] : -1;
+    const int valid_rows = min(NR, p.B - row0);
+    // first output slot of a step (-1: the step emits nothing), read from the global step / emit tables one step ahead
+    auto load_eslot = [&](int s) -> int {
+      if (s >= p.S) return -1;
+      const int eb = p.steps[s].emit_begin, ee = p.steps[s].emit_end;
+      return ee > eb ? p.emits[eb].slot : -1;
+    };
+    int eslot_next = load_eslot(0);
+    auto send_outputs = [&](int s) {
+      const uint8_t* ost = smem + L.outst + (s & 1) * (NR * H * 4 + 16);
+      const int eslot = eslot_next;
+      eslot_next = load_eslot(s + 1);                    // consumed one step later: its latency is never waited for
+      if (eslot >= 0) {
+        if (p.row_slot != nullptr) {
+          if (lane < valid_rows && my_row_slot == eslot)
+            bulk_s2g(p.out + (size_t)(row0 + lane) * H, smem_u32(ost + 16 + lane * H * 4), (uint32_t)(H * 4));
+        } else if (lane == 0) {
+          bulk_s2g(p.out + ((size_t)eslot * p.B + row0) * H, smem_u32(ost + 16), (uint32_t)(valid_rows * H * 4));
+        }
+      }
+      bulk_commit_group();
+      bulk_wait_group_read<1>();          // the copies of step s-1 have read their staging slot: the epilogue may reuse it
+    };
     auto run_segment = [&](const SegOps& o, uint32_t wait_bar, uint32_t wait_par, uint32_t commit_bar, int s = -1, int ev = -1) {
       if (wait_bar == 0) named_sync(kBarIn, kCntIn);        // operands from the epilogue warps
       else mbar_wait(wait_bar, wait_par);                   // X(t) operand ring
@@ -505,6 +548,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         if (s >= 0) {
           run_segment(o0, 0, 0, bar_acc, s, EV_MMA_WAKE0);
           TC_TRACE(lane == 0, s, EV_MMA_COMMIT0);
+          if (s > 0) send_outputs(s - 1);                // in the shadow of the layer-0 MMAs
           run_segment(o1, 0, 0, bar_acc, s, EV_MMA_WAKE1);
           TC_TRACE(lane == 0, s, EV_MMA_COMMIT1);
         }
@@ -531,10 +575,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
             const SegOps o = layer_ops(seg);
             asm volatile("" ::"r"(o.ts), "r"(o.nk), "r"(o.a_hi), "r"(o.a_lo), "r"(o.d), "l"(o.db), "r"(o.acc0));
             run_segment(o, 0, 0, bar_acc);
+            if (seg == 0 && s > 0) send_outputs(s - 1);
           }
         }
       }
     }
+    if (p.S > 0) {                                       // outputs of the last step: its hand-over has no MMA segment behind it
+      named_sync(kBarIn, kCntIn);
+      send_outputs(p.S - 1);
+    }
+    bulk_wait_all();
   } else if (warp < kPrepWarp0) {
     // =========================== CONTROL PRODUCER ===========================
     // This role has to deliver one X(t) operand per solver step; measured (clock64 trace) at 3500 cycles per
