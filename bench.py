@@ -388,6 +388,65 @@ class Workload:
             torch.cuda.current_stream(self.dev).wait_stream(self.side)
 
 
+def train_block(w, wl, steps, warmup, precision, dev, rows=16):
+    """one training step of the workload through the public API - forward solve that saves the solver
+    states, reverse-sweep kernel, weight-gradient GEMMs - timed on the device, plus a gradient parity gate:
+    dL/dz0 of the first `rows` rows (L = sum z^2 is row-separable) against fp64 autograd through the oracle on the
+    materialised increments."""
+    import snsde_b200
+    from oracle import solver
+    B, H, S = w["B"], w["H"], w["S"]
+    times, coeffs, z0, fi = wl.sets_host[0]
+    times_d, coeffs_d, z0_d, fi_d = wl.sets_dev[0]
+    model = wl.model
+    model.set_X(coeffs_d, times_d)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-6)
+
+    def one(i, with_opt):
+        zz = z0_d.clone().requires_grad_(True)
+        z = snsde_b200.solve_final(model, times, fi, zz, method="euler", seed=i, precision=precision, row_offset=wl.row_offset, dt=wl.dt)
+        (z * z).sum().backward()
+        if with_opt:
+            opt.step()
+        opt.zero_grad(set_to_none=True)
+        return zz.grad
+
+    out = {}
+    for key, with_opt in (("fwd_bwd_ms", False), ("fwd_bwd_optimizer_ms", True)):
+        for i in range(warmup):
+            one(i, with_opt)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            one(i, with_opt)
+        b.record()
+        torch.cuda.synchronize()
+        out[key] = a.elapsed_time(b) / steps
+    # gradient parity (weights as they are now)
+    seed = 777
+    zz = z0_d.clone().requires_grad_(True)
+    z = snsde_b200.solve_final(model, times, fi, zz, method="euler", seed=seed, precision=precision, row_offset=wl.row_offset, dt=wl.dt)
+    (z * z).sum().backward()
+    opt.zero_grad(set_to_none=True)
+    got = zz.grad[:rows].cpu().double()
+    plan = snsde_b200.plan_for(model, "euler", precision, dev)
+    ts, _ = snsde_b200.final_index_slots(times, fi)
+    dW = snsde_b200.philox_increments(seed, plan.step_plan(ts, wl.dt, times), rows, H, dev, row_offset=wl.row_offset).cpu().double()
+    m = oracle_model_for(w, model).double()
+    m.set_X(coeffs[:rows].double(), times.double())
+    y0 = z0[:rows].double().requires_grad_(True)
+    z_all = solver.sdeint_with_grad(m, y0, times.double(), wl.dt, solver.BrownianTable(dW))
+    zo = z_all[fi[:rows], torch.arange(rows)]
+    (zo * zo).sum().backward()
+    err = float((got - y0.grad).abs().max()) / max(float(y0.grad.abs().max()), 1e-6)
+    out.update({"value": B * S / (out["fwd_bwd_ms"] * 1e-3), "unit": "SDE-steps/s (forward + backward)", "rows_per_gpu": B, "solver_steps": S,
+                "forward_kernel": plan.kernel, "backward_kernel": "fp32 reverse sweep + cuBLAS weight-gradient GEMMs",
+                "grad_parity": {"what": "dL/dz0, L = sum z^2", "rel_err": err, "tol": 1e-4, "ok": bool(err <= 1e-4), "rows": rows,
+                                "oracle": "fp64 autograd through oracle.solver (CPU), same Philox increments"}})
+    return out
+
+
 def roofline_block(name, w, plan, kern_ms, n_out_rows):
     hbm_peak, tf_peak, peak_src = peaks()
     B, S = w["B"], w["S"]
@@ -621,6 +680,11 @@ def main():
             del cwl
             torch.cuda.empty_cache()
 
+    train = None
+    if args.workload == "c2" and not args.no_configs and not args.solver_steps and w["method"] == "euler":
+        tb = train_block(w, wl, max(3, args.steps // 4), 2, args.precision, dev)      # every rank trains its shard; rank 0 reports
+        train = tb if rank == 0 else None
+
     if rank == 0:
         n_out_rows = 1 if w["out"] == "final_index" else n_out
         roof = roofline_block(args.workload, w, plan, kern_ms, n_out_rows)
@@ -653,8 +717,11 @@ def main():
                                     "note": "host buffers = raw path x[B,K,C]; coefficients built on device per step"}
         if configs:
             line["configs"] = configs
+        if train:
+            line["train"] = train
         print(json.dumps(line), flush=True)
-    bad = rank == 0 and ((parity and not parity["ok"]) or any(c["parity"] and not c["parity"]["ok"] for c in configs.values()))
+    bad = rank == 0 and ((parity and not parity["ok"]) or any(c["parity"] and not c["parity"]["ok"] for c in configs.values())
+                         or (train is not None and not train["grad_parity"]["ok"]))
     if world > 1:
         dist.destroy_process_group()
     if bad:

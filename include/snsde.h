@@ -220,6 +220,24 @@ int snsde_natural_coeffs(const float* x_dev, const float* knots_dev, int32_t B, 
 int snsde_fill_missing(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
                        float* out_dev, int device, void* stream);
 
+/* ---- the seam's neighbours, eval mode ----------------------------------------------------------------
+ * z0 = initial_network(X(times[0])): `_prepare_initial_state`, benchmark_classification/models_sde/neuralsde.py:63-69
+ * (= benchmark_forecasting/models_sde/neuralsde.py:137-143).  coeffs_dev as in snsde_forward; (interval, frac) locate
+ * times[0] in the knots (0, 0.0f when times[0] is the first knot); W_dev [H, C], b_dev [H] = initial_network; z0_dev [B, H]. */
+int snsde_initial_state(const float* coeffs_dev, int64_t coeff_row_stride, int32_t B, int32_t C, int32_t n_knots,
+                        int32_t interval, float frac, const float* W_dev, const float* b_dev, int32_t H,
+                        float* z0_dev, int device, void* stream);
+
+/* pred = Linear2(relu(bn(Linear1(pre(z))))) for R rows: the read-out heads of the three wrappers in EVAL mode
+ * (neuralsde.py:59-61,119: Linear, BatchNorm1d, ReLU, Dropout, Linear; forecasting :133-136,185: Linear, ReLU, Linear;
+ * torch-ists nsde_model.py:52-55,83: Tanh, Linear, ReLU, Linear).  pre_tanh: apply tanh to z first.  bn_scale_dev /
+ * bn_shift_dev [H1] (both or neither): BatchNorm1d in eval mode as  x * scale + shift  with
+ * scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale.  W1 [H1, H], W2 [O, H1] (nn.Linear layout). */
+int snsde_readout_head(const float* z_dev, int64_t R, int32_t H, int32_t pre_tanh,
+                       const float* W1_dev, const float* b1_dev, const float* bn_scale_dev, const float* bn_shift_dev,
+                       int32_t H1, const float* W2_dev, const float* b2_dev, int32_t O, float* out_dev,
+                       int device, void* stream);
+
 /* Number of engine kernels launched by this plan so far (for bench.py's gpu_launches). */
 int64_t snsde_plan_launch_count(const snsde_plan* plan);
 

@@ -136,9 +136,19 @@ def step_times(ts, dt):
     return out
 
 
+def sdeint_with_grad(sde, y0, ts, dt, bm, method="euler", options=None, **unused):
+    """``sdeint`` with autograd left on: what the reference does when it trains through ``torchsde.sdeint``
+    (benchmark_classification/common_sde.py:156-162) - the oracle for the engine's backward pass."""
+    return _integrate(sde, y0, ts, dt, bm, method)
+
+
 @torch.no_grad()
 def sdeint(sde, y0, ts, dt, bm, method="euler", options=None, **unused):
     """Returns ``[len(ts), B, H]`` like ``torchsde.sdeint``.  ``bm`` is mandatory here."""
+    return _integrate(sde, y0, ts, dt, bm, method)
+
+
+def _integrate(sde, y0, ts, dt, bm, method):
     if getattr(sde, "noise_type", "diagonal") != "diagonal" or getattr(sde, "sde_type", "ito") != "ito":
         raise ValueError("oracle supports Ito SDEs with diagonal noise only")
     if method not in _STEPPERS:

@@ -9,10 +9,10 @@ Public surface (mirrors the reference's operator interface for this path):
 """
 from . import dist, packing, stepplan                                    # noqa: F401
 from ._lib import EngineError, LIB_PATH                                  # noqa: F401
-from .engine import (BrownianIncrements, Plan, final_index_slots, patch, philox_increments,  # noqa: F401
-                     plans_of, sdeint, solve_final, wrapper_kind)
+from .engine import (BrownianIncrements, Plan, final_index_slots, initial_state, patch, philox_increments,  # noqa: F401
+                     plans_of, readout_head, sdeint, solve_final, wrapper_kind)
 from .engine import _plan_for as plan_for                                # noqa: F401
 from .stepplan import build_step_plan, solver_dt                          # noqa: F401
 
-__all__ = ["sdeint", "solve_final", "patch", "Plan", "BrownianIncrements", "philox_increments", "plans_of", "plan_for", "wrapper_kind",
+__all__ = ["sdeint", "solve_final", "patch", "Plan", "BrownianIncrements", "philox_increments", "plans_of", "plan_for", "wrapper_kind", "initial_state", "readout_head",
            "final_index_slots", "build_step_plan", "solver_dt", "dist", "EngineError"]

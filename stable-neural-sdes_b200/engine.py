@@ -466,6 +466,117 @@ def solve_final(sde, times, final_index, z0, method=None, bm=None, seed=None, pr
     return _solve(sde, plan, sp, z0, slots, bm, seed, row_offset, out, check_range)
 
 
+# ---- the seam's neighbours in eval mode -------------------------------------------------
+def _f32c(t):
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def initial_state(initial_network, coeffs, times):
+    """``z0 = initial_network(X(times[0]))`` (``_prepare_initial_state``, neuralsde.py:63-69) in one engine kernel;
+    ``coeffs`` is the packed ``[B, K-1, 4C]`` tensor ``set_X`` received."""
+    lib = _lib.load()
+    if not coeffs.is_cuda:
+        raise _lib.EngineError("snsde: no CUDA tensors - this engine has no CPU fallback")
+    coeffs = _f32c(coeffs)
+    B, K1, C4 = coeffs.shape
+    kn = _host_array(times)
+    t0 = kn[0]
+    idx = int(np.clip(np.searchsorted(kn, t0, side="left") - 1, 0, kn.size - 2))
+    W, b = _f32c(initial_network.weight), _f32c(initial_network.bias)
+    H, C = W.shape
+    if C4 != 4 * C:
+        raise ValueError(f"snsde: coeffs have {C4 // 4} channels, initial_network expects {C}")
+    z0 = torch.empty((B, H), device=coeffs.device, dtype=torch.float32)
+    stream = torch.cuda.current_stream(coeffs.device).cuda_stream
+    _lib.check(lib.snsde_initial_state(_ptr(coeffs), coeffs.stride(0), B, C, K1 + 1, idx, ctypes.c_float(float(t0 - kn[idx])),
+                                       _ptr(W), _ptr(b), H, _ptr(z0), coeffs.device.index or 0, ctypes.c_void_p(stream)))
+    return z0
+
+
+_BN_FOLDS = weakref.WeakKeyDictionary()
+
+
+def _bn_affine(bn):
+    """BatchNorm1d in eval mode as ``x * scale + shift``; cached until one of its tensors changes."""
+    ver = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+    hit = _BN_FOLDS.get(bn)
+    if hit is None or hit[0] != ver:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+        hit = _BN_FOLDS[bn] = (ver, scale.contiguous(), shift.contiguous())
+    return hit[1], hit[2]
+
+
+def match_head(head):
+    """The read-out heads of the three reference wrappers (neuralsde.py:59-61; forecasting :133-136; torch-ists
+    nsde_model.py:52-55) as (pre_tanh, Linear1, BatchNorm1d | None, Linear2), or None for anything else."""
+    nn = torch.nn
+    if not isinstance(head, nn.Sequential):
+        return None
+    mods = [m for m in head if not isinstance(m, (nn.Dropout, nn.Identity))]
+    pre_tanh = bool(mods) and isinstance(mods[0], nn.Tanh)
+    if pre_tanh:
+        mods = mods[1:]
+    if len(mods) == 4 and isinstance(mods[1], nn.BatchNorm1d):
+        lin1, bn, relu, lin2 = mods
+        if not (bn.affine and bn.track_running_stats):
+            return None
+    elif len(mods) == 3:
+        (lin1, relu, lin2), bn = mods, None
+    else:
+        return None
+    if not (isinstance(lin1, nn.Linear) and isinstance(relu, nn.ReLU) and isinstance(lin2, nn.Linear)):
+        return None
+    if lin1.bias is None or lin2.bias is None or lin2.in_features != lin1.out_features:
+        return None
+    return pre_tanh, lin1, bn, lin2
+
+
+def readout_head(head, z):
+    """``head(z)`` for one of the reference read-out heads in EVAL mode, in one engine kernel (``z``: ``[..., H]``).
+    Returns None when the head is not one of the recognised stacks or is in training mode (BatchNorm batch statistics and
+    dropout masks stay in PyTorch)."""
+    m = match_head(head)
+    if m is None or head.training or not z.is_cuda:
+        return None
+    pre_tanh, lin1, bn, lin2 = m
+    lib = _lib.load()
+    z = _f32c(z)
+    H = z.shape[-1]
+    if lin1.in_features != H:
+        return None
+    R = z.numel() // H
+    scale, shift = _bn_affine(bn) if bn is not None else (None, None)
+    out = torch.empty((*z.shape[:-1], lin2.out_features), device=z.device, dtype=torch.float32)
+    stream = torch.cuda.current_stream(z.device).cuda_stream
+    _lib.check(lib.snsde_readout_head(_ptr(z), R, H, int(pre_tanh), _ptr(_f32c(lin1.weight)), _ptr(_f32c(lin1.bias)),
+                                      _ptr(scale), _ptr(shift), lin1.out_features, _ptr(_f32c(lin2.weight)),
+                                      _ptr(_f32c(lin2.bias)), lin2.out_features, _ptr(out), z.device.index or 0,
+                                      ctypes.c_void_p(stream)))
+    return out
+
+
+def _neighbours_fusable(model, z0):
+    return not torch.is_grad_enabled() or not (
+        any(p.requires_grad for p in model.parameters()) or (z0 is not None and z0.requires_grad))
+
+
+def _initial_state_of(model, coeffs, times, z0, fused):
+    if fused and z0 is None and getattr(model, "initial", False) and isinstance(model.initial_network, torch.nn.Linear) \
+            and coeffs.is_cuda:
+        return initial_state(model.initial_network, coeffs, times)
+    return model._prepare_initial_state(times, z0)
+
+
+def _head_of(model, z_t, fused):
+    if fused:
+        out = readout_head(model.linear, z_t)
+        if out is not None:
+            return out
+    return model.linear(z_t)
+
+
 # ---- patching the reference wrappers ----------------------------------------------------------------
 _ENGINE_KW = ("bm", "seed", "precision", "row_offset", "check_range")
 
@@ -492,9 +603,12 @@ def _solve_sde_path_torch_ists(self, times, y0, kwargs):
 
 
 def _forward_classification(self, times, coeffs, final_index, z0=None, stream=False, **kwargs):
-    """``NeuralSDE.forward`` (neuralsde.py:84-120) with the final_index gather fused into the solve."""
-    self.func.set_X(_cat_coeffs(coeffs), times)
-    z0 = self._prepare_initial_state(times, z0)
+    """``NeuralSDE.forward`` (neuralsde.py:84-120) with the final_index gather fused into the solve; without autograd
+    the initial state and (eval mode) the read-out head run as engine kernels too."""
+    coeffs = _cat_coeffs(coeffs)
+    self.func.set_X(coeffs, times)
+    fused = _neighbours_fusable(self, z0)
+    z0 = _initial_state_of(self, coeffs, times, z0, fused)
     eng = {k: kwargs.pop(k) for k in _ENGINE_KW if k in kwargs}
     method = kwargs.pop("method", None)
     kwargs.pop("options", None)
@@ -505,14 +619,16 @@ def _forward_classification(self, times, coeffs, final_index, z0=None, stream=Fa
         if kwargs:
             warnings.warn(f"Unexpected arguments {sorted(kwargs)}")
         z_t = solve_final(self.func, times, final_index, z0, method=method, **eng)
-    return self.linear(z_t)
+    return _head_of(self, z_t, fused)
 
 
 def _forward_forecasting(self, times, coeffs, final_index, z0=None, stream=False, **kwargs):
     """``NeuralSDE_forecasting.forward`` (benchmark_forecasting/models_sde/neuralsde.py:158-186): the reference
     streams every knot and heads the last ``output_time`` of them (:184-185); only those are written here."""
-    self.func.set_X(_cat_coeffs(coeffs), times)
-    z0 = self._prepare_initial_state(times, z0)
+    coeffs = _cat_coeffs(coeffs)
+    self.func.set_X(coeffs, times)
+    fused = _neighbours_fusable(self, z0)
+    z0 = _initial_state_of(self, coeffs, times, z0, fused)
     eng = {k: kwargs.pop(k) for k in _ENGINE_KW if k in kwargs}
     method = kwargs.pop("method", None)
     kwargs.pop("options", None)
@@ -524,7 +640,7 @@ def _forward_forecasting(self, times, coeffs, final_index, z0=None, stream=False
     else:                                   # the reference's slice z_t[:, K - ot:] with ot >= K (or 0) on the full stream
         z_t = sdeint(self.func, z0, times, dt=dt, method=method, **eng, **kwargs)
         z_t = z_t[K - ot:] if ot else z_t[K:]
-    return self.linear(z_t.transpose(0, 1))
+    return _head_of(self, z_t.transpose(0, 1), fused)
 
 
 # pickling a bound method stores (getattr, (instance, __name__)): name the replacements after the attributes they fill

@@ -191,6 +191,42 @@ def forward_golden(ref_c, ref_f, ref_t=None):
                         state_dict={k: v.clone() for k, v in func.state_dict().items()},
                         initial_network={k: v.clone() for k, v in model.initial_network.state_dict().items()},
                         times=times, coeffs=torch.cat(coeffs4, -1), dW=dW, z=z))
+        # the wrappers WITH their own neighbours in eval mode: z0 = initial_network(X(t0)) and the real
+        # read-out heads (classification: Linear, BatchNorm1d (non-trivial running statistics), ReLU, Dropout, Linear;
+        # forecasting: Linear, ReLU, Linear)
+        B, K, C, H, L, O = 6, 9, 3, 8, 1, 2
+        torch.manual_seed(777)
+        func = ref_c.Diffusion_model(C, H, H, L, input_option=4, noise_option=17)
+        model = ref_c.NeuralSDE(func, C, H, O, initial=True)
+        bn = model.linear[1]
+        bn.running_mean.copy_(torch.randn(H) * 0.3); bn.running_var.copy_(torch.rand(H) + 0.5)
+        bn.weight.data.copy_(torch.rand(H) + 0.5); bn.bias.data.copy_(torch.randn(H) * 0.2)
+        model.eval()
+        times = torch.arange(K, dtype=torch.float32)
+        x = torch.randn(B, K, C).cumsum(1) * 0.3
+        coeffs = ospline.hermite_cubic_coefficients_with_backward_differences(x, times)
+        final_index = torch.tensor([8, 3, 5, 8, 1, 6])
+        dW = torch.randn(K - 1, B, H)
+        pred = model(times, [coeffs], final_index, bm=osolver.BrownianTable(dW))
+        out.append(dict(kind="classification_full", input_option=4, noise_option=17, dims=(B, K, C, H, H, L), out_channels=O,
+                        state_dict={k: v.clone() for k, v in func.state_dict().items()},
+                        model_state={k: v.clone() for k, v in model.state_dict().items()},
+                        times=times, coeffs=coeffs, final_index=final_index, dW=dW, pred=pred))
+        B, K, C, H, L, O, output_time = 4, 8, 2, 8, 1, 3, 3
+        torch.manual_seed(778)
+        func = ref_f.Diffusion_model(C, H, H, L, input_option=6, noise_option=17)
+        model = ref_f.NeuralSDE_forecasting(func, C, output_time, H, O, initial=True)
+        model.eval()
+        times = torch.linspace(0, K - 1, K)
+        x = torch.randn(B, K, C).cumsum(1) * 0.3
+        coeffs4 = ospline.natural_cubic_spline_coeffs(times, x)
+        dW = torch.randn(K - 1, B, H)
+        pred = model(times, coeffs4, None, bm=osolver.BrownianTable(dW))
+        out.append(dict(kind="forecasting_full", input_option=6, noise_option=17, dims=(B, K, C, H, H, L), out_channels=O,
+                        output_time=output_time,
+                        state_dict={k: v.clone() for k, v in func.state_dict().items()},
+                        model_state={k: v.clone() for k, v in model.state_dict().items()},
+                        times=times, coeffs=torch.cat(coeffs4, -1), dW=dW, pred=pred))
         # torch-ists wrapper (nsde_model.py:45-84): forward(coeffs, times) -> (head(z), z), every knot, default method
         # 'srk' (needs the space-time Levy integrals beside the increments), linspace grid with a sliver step
         if ref_t is not None:

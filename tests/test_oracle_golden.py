@@ -98,6 +98,8 @@ def test_hermite_nan_fill():
 
 def test_forward_wrappers_match_reference(golden_dir):
     for c in torch.load(golden_dir / "forward_golden.pt"):
+        if c["kind"].endswith("_full"):         # wrapper + its own neighbours: consumed by the GPU tests through patch()
+            continue
         m = _build(c)
         bm = solver.BrownianTable(c["dW"])
         if c["kind"] == "classification":

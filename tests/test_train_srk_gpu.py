@@ -34,19 +34,8 @@ def grad_close(got, want, name, rtol=1e-4):
 
 
 def euler_with_grad(m, y0, ts, dt, dW):
-    """The oracle's fixed-step Euler loop with autograd enabled (oracle.solver.sdeint is @no_grad by design)."""
-    bm = solver.BrownianTable(dW)
-    prev_t = curr_t = ts[0]
-    prev_y = curr_y = y0
-    ys = [y0]
-    for out_t in ts[1:]:
-        while curr_t < out_t:
-            next_t = min(curr_t + dt, ts[-1])
-            prev_t, prev_y = curr_t, curr_y
-            curr_y = solver.euler_step(m, bm, curr_t, next_t, curr_y)
-            curr_t = next_t
-        ys.append(solver._lerp(prev_t, prev_y, curr_t, curr_y, out_t))
-    return torch.stack(ys, 0)
+    """The oracle's fixed-step Euler loop with autograd enabled (oracle.solver.sdeint itself is @no_grad)."""
+    return solver.sdeint_with_grad(m, y0, ts, dt, solver.BrownianTable(dW))
 
 
 BWD_CASES = [
@@ -425,3 +414,82 @@ def test_saturated_tensor_core_solve_is_reported_on_the_next_call_or_rerun(dev):
     with torch.no_grad():                               # flag consumed: the plan is usable again
         mg = m.to(dev); mg.set_X(coeffs.to(dev), times.to(dev))
         snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, bm=bm())
+
+
+# ---- the seam's neighbours as engine kernels ---------------------------------------------
+class _RefStyleClassification(torch.nn.Module):      # attributes / signatures of reference NeuralSDE (neuralsde.py:51-120)
+    def __init__(self, func, C, H, O):
+        super().__init__()
+        self.func, self.initial = func, True
+        self.initial_network = torch.nn.Linear(C, H)
+        self.linear = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.BatchNorm1d(H), torch.nn.ReLU(), torch.nn.Dropout(0.1),
+                                          torch.nn.Linear(H, O))
+
+    def _prepare_initial_state(self, times, z0):
+        return self.initial_network(self.func.X.evaluate(times[0])) if z0 is None else z0
+
+    def _solve_sde_path(self, times, ts, z0, kwargs):
+        raise AssertionError("replaced by patch()")
+
+    def forward(self, times, coeffs, final_index, z0=None, stream=False, **kwargs):
+        raise AssertionError("replaced by patch()")
+
+
+class _RefStyleForecasting(_RefStyleClassification):   # NeuralSDE_forecasting (benchmark_forecasting/...:123-186)
+    def __init__(self, func, C, H, O, output_time):
+        super().__init__(func, C, H, O)
+        self.output_time = output_time
+        self.linear = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.ReLU(), torch.nn.Linear(H, O))
+
+
+def test_full_forward_goldens_with_fused_neighbours(golden_dir, dev, monkeypatch):
+    """Eval-mode forward of the classification / forecasting wrappers INCLUDING z0 = initial_network(X(t0)) and the real
+    read-out heads (BatchNorm1d running statistics, Dropout), against predictions minted from the reference's own classes.
+    The PyTorch modules of the neighbours must not run: they are replaced by raising stubs after patch()."""
+    cases = {c["kind"]: c for c in torch.load(golden_dir / "forward_golden.pt") if c["kind"].endswith("_full")}
+    assert set(cases) == {"classification_full", "forecasting_full"}
+    for kind, c in cases.items():
+        B, K, C, H, HH, L = c["dims"]
+        func = _oracle_func(c, dev)
+        if kind == "classification_full":
+            model = _RefStyleClassification(func, C, H, c["out_channels"])
+        else:
+            model = _RefStyleForecasting(func, C, H, c["out_channels"], c["output_time"])
+        model.load_state_dict(c["model_state"])
+        model = snsde_b200.patch(model.to(dev)).eval()
+        called = []
+        model._prepare_initial_state = lambda *a, **k: called.append("z0") or (_ for _ in ()).throw(AssertionError("PyTorch z0 producer ran"))
+        for mod in model.linear:
+            mod.register_forward_hook(lambda *a: called.append("head"))
+        coeffs = [c["coeffs"].to(dev)] if kind == "classification_full" else tuple(t.to(dev) for t in c["coeffs"].chunk(4, -1))
+        fi = c["final_index"].to(dev) if kind == "classification_full" else None
+        with torch.no_grad():
+            pred = model(c["times"].to(dev), coeffs, fi, bm=snsde_b200.BrownianIncrements(c["dW"].to(dev)), precision="fp32")
+        assert not called, called
+        assert pred.shape == c["pred"].shape
+        close(pred, c["pred"], rtol=1e-5)
+        # training mode: BatchNorm batch statistics / dropout stay in PyTorch (and gradients flow)
+        model.train()
+        del model._prepare_initial_state
+        pred_t = model(c["times"].to(dev), coeffs, fi, seed=3)
+        assert "head" in called and pred_t.requires_grad
+
+
+def test_neighbour_kernels_alone(dev):
+    torch.manual_seed(0)
+    B, K, C, H, O = 37, 6, 5, 96, 4
+    times = torch.linspace(0.5, 3.0, K)
+    x = torch.randn(B, K, C).cumsum(1)
+    coeffs = spline.hermite_cubic_coefficients_with_backward_differences(x, times)
+    lin = torch.nn.Linear(C, H)
+    want = lin(spline.CubicSpline(coeffs, times).evaluate(times[0]))
+    got = snsde_b200.initial_state(lin.to(dev), coeffs.to(dev), times.to(dev))
+    close(got, want, rtol=1e-6)
+    head = torch.nn.Sequential(torch.nn.Tanh(), torch.nn.Linear(H, 64), torch.nn.ReLU(), torch.nn.Linear(64, O)).eval()
+    z = torch.randn(B, 7, H)
+    want = head(z)
+    got = snsde_b200.readout_head(head.to(dev), z.to(dev))
+    assert got.shape == (B, 7, O)
+    close(got, want, rtol=1e-5)
+    assert snsde_b200.readout_head(torch.nn.Linear(H, O).to(dev), z.to(dev)) is None          # not a recognised stack
+    assert snsde_b200.readout_head(head.train(), z.to(dev)) is None                           # training mode stays in PyTorch
