@@ -365,6 +365,7 @@ cudaError_t bwd_launch(const BwdParams& p, int R, size_t smem, cudaStream_t stre
   const int n_groups = (p.B + R - 1) / R;
   const int grid = (n_groups + p.groups - 1) / p.groups;
   const bool ws = p.smem_w_floats > 0;
+  if (R == 8 && nt <= 512) return ws ? bwd_launch_one<8, 512, true>(p, grid, nt, smem, stream) : bwd_launch_one<8, 512, false>(p, grid, nt, smem, stream);
   if (R == 4 && nt <= 512) return ws ? bwd_launch_one<4, 512, true>(p, grid, nt, smem, stream) : bwd_launch_one<4, 512, false>(p, grid, nt, smem, stream);
   if (R == 1 && nt <= 512) return ws ? bwd_launch_one<1, 512, true>(p, grid, nt, smem, stream) : bwd_launch_one<1, 512, false>(p, grid, nt, smem, stream);
   if (R == 4) return ws ? bwd_launch_one<4, 1024, true>(p, grid, nt, smem, stream) : bwd_launch_one<4, 1024, false>(p, grid, nt, smem, stream);

@@ -221,8 +221,15 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
     u = (METHOD == 1) ? levy_U(w, pick4(nrmu, (int)(gb & 3ull)), h, sqrt_h) : 0.f;
   };
 
+  snsde_step st_next = p.S > 0 ? p.steps[0] : snsde_step{};
   for (int s = 0; s < p.S; ++s) {
-    const snsde_step st = p.steps[s];
+    // step record of the NEXT step and this step's first emit are requested now: their global-memory latency is
+    // hidden behind the step instead of opening and closing it
+    const snsde_step st = st_next;
+    if (s + 1 < p.S) st_next = p.steps[s + 1];
+    snsde_emit em0;
+    em0.slot = 0; em0.w_prev = 0.f; em0.w_curr = 0.f;
+    if (st.emit_end > st.emit_begin) em0 = p.emits[st.emit_begin];
 
     if (METHOD == 0) {
       // =============================== Euler / Milstein ===============================================
@@ -419,7 +426,8 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
         for (int r = 0; r < R; ++r) sY[r * ld + tid] = y[r];
       }
     }
-    for (int e = st.emit_begin; e < st.emit_end; ++e) emit(p.emits[e]);
+    if (st.emit_end > st.emit_begin) emit(em0);
+    for (int e = st.emit_begin + 1; e < st.emit_end; ++e) emit(p.emits[e]);
   }
 }
 

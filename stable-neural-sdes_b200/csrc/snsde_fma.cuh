@@ -45,10 +45,31 @@ __device__ __forceinline__ void stage_weights(float* __restrict__ dst, const flo
 template <int ROWS>
 __device__ __forceinline__ void dot_accumulate(float (&acc)[ROWS], const float* __restrict__ src, int ld,
                                                const float* __restrict__ w, int K, int stride) {
-  const int K4 = K & ~3;
-  const int s2 = 2 * stride, s3 = 3 * stride, s4 = 4 * stride;
   const float* wk = w;
   int k = 0;
+  if (ROWS == 1) {
+    // A single-row group is pure latency: batch 16 weight reads and 4 activation reads, THEN the 16 dependent FMAs
+    // (same k order as the general path below, so a row's result does not depend on how the batch was grouped).
+    const int K16 = K & ~15;
+    for (; k < K16; k += 16) {
+      float wv[16];
+      float4 av[4];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wv[i] = wk[i * stride];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(src + k + 4 * i);
+      wk += 16 * stride;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[0] = fmaf(av[i].x, wv[4 * i + 0], acc[0]);
+        acc[0] = fmaf(av[i].y, wv[4 * i + 1], acc[0]);
+        acc[0] = fmaf(av[i].z, wv[4 * i + 2], acc[0]);
+        acc[0] = fmaf(av[i].w, wv[4 * i + 3], acc[0]);
+      }
+    }
+  }
+  const int K4 = K & ~3;
+  const int s2 = 2 * stride, s3 = 3 * stride, s4 = 4 * stride;
 #pragma unroll 2
   for (; k < K4; k += 4, wk += s4) {
     const float w0 = wk[0], w1 = wk[stride], w2 = wk[s2], w3 = wk[s3];
