@@ -669,7 +669,7 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
 
   if (p->kind >= 1) {
     TcForwardArgs a;
-    a.coeffs = coeffs_dev; a.coeff_row_stride = coeff_row_stride; a.y0 = y0_dev; a.B = B;
+    a.coeffs = coeffs_dev; a.coeff_row_stride = coeff_row_stride; a.n_knots = n_knots; a.y0 = y0_dev; a.B = B;
     a.steps = p->d_steps; a.steps_host = steps_host; a.S = S; a.emits = p->d_emits; a.n_init_emits = n_init_emits;
     a.n_out = n_out; a.row_slot = row_slot_dev; a.dW = dW_dev; a.seed = seed; a.row_offset = row_offset; a.out = out_dev;
     a.status = p->d_status;

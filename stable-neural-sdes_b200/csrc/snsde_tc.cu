@@ -90,7 +90,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int wimg_bytes, int H, int C, i
   s.b = (wimg_bytes + 127) & ~127;
   s.x = s.b + (H / 8) * s.lbo_b;
   s.x_slot_bytes = uses_control ? (Cpad / 8) * s.lbo_b : 0;
-  s.stg = s.x + nx * s.x_slot_bytes;
+  s.stg = (s.x + nx * s.x_slot_bytes + 127) & ~127;  // TMA tensor copies land here: 128-byte aligned
   s.stg_bytes = uses_control ? NR * 16 * C : 0;
   s.prep = (s.stg + nstg * s.stg_bytes + 15) & ~15;
   s.prep_bytes = (NR + 2) * 128 * 4 + 32;
@@ -176,7 +176,7 @@ __device__ __forceinline__ void issue_segment(bool leader, const SegOps& o, uint
 // DIFF = 1: the diffusion is tanh(sigmoid(theta) * nan_to_num(coef * y)) (noise options 3,6,13,17) - the
 // form of every proposed model with multiplicative noise; DIFF = 0: generic (runtime-selected) form.
 template <int NR, int DIFF, int CH>
-__global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int N = NR < 16 ? 16 : NR;              // MMA N (rows padded to >= 16)
   using Acc = AccRegion<N, CH>;                     // CH accumulator chains per product; 2 regions of CH*2N columns
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -602,6 +602,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) snsde_tc_kernel(const TcParams 
         if (s >= p.S) return;
         const int stg = s % p.nstg;
         const uint32_t bar = bar_cfull + 8 * stg;
+        if (p.use_tmap) {                               // ONE tensor copy: box [NR rows][4C floats] at (interval*4C, row0)
+          if (ptid == 0) tma_load_2d(smem_u32(smem + L.stg + stg * L.stg_bytes), &p.tmap, interval * 4 * C, row0, bar);
+          return;
+        }
         const int r = pwarp * rows_per_warp + lane;
         if (lane < rows_per_warp && r < NR) {
           const int b = min(row0 + r, p.B - 1);
@@ -971,8 +975,36 @@ static cudaError_t tc_launch_one(const TcParams& p, int grid, size_t smem, cudaS
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+// coefficients [B][(K-1)*4C] fp32 (row stride in floats), box [NR][4C]
+static bool make_coeff_tmap(CUtensorMap* tm, const float* coeffs, long long row_stride, int B, int n_intervals, int C, int NR) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || getenv("SNSDE_TC_NO_TMAP") != nullptr) return false;
+  if (4 * C > 256 || NR > 256 || ((row_stride * 4) & 15) || ((uintptr_t)coeffs & 15)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n_intervals * 4 * C, (cuuint64_t)B};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_stride * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)(4 * C), (cuuint32_t)NR};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)coeffs, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, int* n_launches) {
   TcParams p = tc.proto;
+  p.use_tmap = 0;
   p.coeffs = a.coeffs; p.coeff_row_stride = a.coeff_row_stride; p.y0 = a.y0; p.B = a.B;
   p.steps = a.steps; p.S = a.S; p.emits = a.emits; p.n_init_emits = a.n_init_emits; p.n_out = a.n_out;
   p.row_slot = a.row_slot; p.dW = a.dW; p.seed = a.seed; p.row_offset = a.row_offset; p.out = a.out;
@@ -1031,6 +1063,8 @@ cudaError_t tc_forward(TcPlan& tc, const TcForwardArgs& a, cudaStream_t stream, 
     NR /= 2;
   }
   const int grid = (a.B + NR - 1) / NR;
+  if (p.uses_control && a.S > 0)
+    p.use_tmap = make_coeff_tmap(&p.tmap, a.coeffs, a.coeff_row_stride, a.B, a.n_knots - 1, p.C, NR) ? 1 : 0;
   cudaError_t e;
   const bool fast_diff = p.tail.bounded && p.tail.special == SP_NONE && p.tail.mult == MU_Y;
   // Accumulator chains per product: with the weights in TMEM the MMA phase is short and one chain is best (fewer

@@ -1,5 +1,6 @@
 // Tensor-core (tcgen05) path: host-visible interface used by snsde_api.cu.
 #pragma once
+#include <cuda.h>             // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "snsde_common.cuh"
@@ -51,6 +52,10 @@ struct TcParams {
   int nx, nstg;              // control-operand ring depth, coefficient staging depth
   long long* dbg;            // optional: clock64 trace of CTA 0 (SNSDE_TC_TRACE env), [step][event]
   int* status;               // sticky flags (bit 0: operand beyond the fp16 range was saturated)
+  // 2-D tensor map of the coefficients [B][(K-1)*4C] with box [NR][4C]: one TMA tensor copy per step fetches the
+  // spline rows of all NR rows of the CTA (use_tmap = 0: per-row 1-D bulk copies, e.g. 4C > 256)
+  int use_tmap;
+  CUtensorMap tmap;
 };
 
 // Per-step table of the row-independent noise networks (options 12,13,16,17).
@@ -73,7 +78,7 @@ struct TcPlan {
 };
 
 struct TcForwardArgs {
-  const float* coeffs; long long coeff_row_stride;
+  const float* coeffs; long long coeff_row_stride; int n_knots;
   const float* y0; int B;
   const snsde_step* steps; const snsde_step* steps_host; int S;
   const snsde_emit* emits; int n_init_emits; int n_out;
