@@ -115,6 +115,22 @@ def test_c3_full_size_milstein(dev):
     # rows of a shard see the same increments as in the full batch (global-row keyed stream)
     assert quantile_err(z_tc[sl], want, 0.5) <= 1e-6 and quantile_err(z_tc[sl], want, 0.99) <= RTOL
     assert quantile_err(z_fma[sl], want, 0.5) <= 1e-6 and quantile_err(z_fma[sl], want, 0.99) <= RTOL
+    # hard bound on EVERY element: no further from the fp32 reference than a few times the reference's own fp32-vs-fp64
+    # distance on this trajectory (tests/golden/conditioning.json: up to 0.2 of the scale for this model at 200 steps)
+    import copy
+    o64 = copy.deepcopy(oracle_model(m.cpu(), io, no, C, H)).double()
+    want64 = wrapper.classification_latent(o64, times.double(), coeffs[sl].double(), fi[sl], z0[sl].double(),
+                                           solver.BrownianTable(dW[:, sl].double()), method="milstein")
+    bound = max(RTOL, 3.0 * rel_err(want, want64))
+    assert rel_err(z_tc[sl], want) <= bound and rel_err(z_fma[sl], want) <= bound, (rel_err(z_tc[sl], want), rel_err(z_fma[sl], want), bound)
+    # strict gate on the well-conditioned part of the horizon: the first 24 steps of the FULL batch, 1e-4
+    with torch.no_grad():
+        mg.set_X(cg[:, :24], tg[:25])
+        z24 = snsde_b200.sdeint(mg, zg, tg[:25], dt=1.0, method="milstein", seed=9, precision="tc")
+    o = oracle_model(m.cpu(), io, no, C, H)
+    o.set_X(coeffs[sl, :24], times[:25])
+    want24 = solver.sdeint(o, z0[sl], times[:25], 1.0, solver.BrownianTable(dW[:24, sl]), method="milstein")
+    assert rel_err(z24[:, sl], want24) <= RTOL
 
 
 def test_c4_shape_state_network_noise(dev):
@@ -139,9 +155,11 @@ def test_c4_shape_state_network_noise(dev):
     def run64(o64):
         o64.set_X(coeffs.double(), times.double())
         return solver.sdeint(o64, z0.double(), ts.double(), 1.0, solver.BrownianTable(dW.double()))
-    tol, want64 = conditioned_tol(o, want, run64, with_fp64=True)   # fp32 vs fp64 reference: ~6e-5 here (|z| reaches ~190)
-    err = min(rel_err(z, want), rel_err(z, want64))
-    assert err <= tol, (rel_err(z, want), rel_err(z, want64), tol)
+    # ONE reference for the max norm: the reference path evaluated in fp64 (the closest thing to its exact trajectory);
+    # tolerance 1e-4 or 3x the distance at which the reference's own fp32 evaluation sits from it (~6e-5: |z| reaches ~190)
+    tol, want64 = conditioned_tol(o, want, run64, with_fp64=True)
+    err = rel_err(z, want64)
+    assert err <= tol, (err, rel_err(z, want), tol)
     assert quantile_err(z, want, 0.999) <= RTOL
 
 

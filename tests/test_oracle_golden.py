@@ -273,3 +273,16 @@ def test_philox_normal_reference_moments():
     n = np.concatenate([philox.normals_reference(7, s, np.arange(64), 32).ravel() for s in range(40)])
     assert abs(n.mean()) < 0.02 and abs(n.std() - 1) < 0.02
     assert abs((n ** 3).mean()) < 0.08 and abs((n ** 4).mean() - 3) < 0.15
+
+
+def test_committed_conditioning_evidence_is_consistent():
+    """tests/golden/conditioning.json (minted by make_conditioning.py with the CPU oracle) is the evidence behind the relaxed
+    long-horizon tolerances: the fp32 reference path is itself 0.2 of the scale away from its fp64 evaluation on the
+    GSDE model (c3), while all four are within 4e-7 over the first 24 steps - where the strict 1e-4 gates apply."""
+    import json
+    import pathlib
+    ev = json.loads((pathlib.Path(__file__).parent / "golden" / "conditioning.json").read_text())
+    assert set(ev) == {"c2", "c3", "c4", "c5"}
+    assert ev["c3"]["max_rel"] > 1e-3 and ev["c3"]["median_rel"] < 1e-6          # ill-conditioned in rare elements only
+    assert all(v["max_rel_first_24_steps"] < 1e-5 for v in ev.values())
+    assert ev["c2"]["max_rel"] < 1e-4
