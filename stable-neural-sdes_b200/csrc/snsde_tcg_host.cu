@@ -314,12 +314,18 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
     NR /= 2;
   }
   const int grid = (a.B + NR - 1) / NR;
-  const bool fast_diff = p.tail.bounded && p.tail.special == SP_NONE && p.tail.mult == MU_Y;
+  // DIFF 1: tanh(s * nan_to_num(coef * y)) with a per-step / per-feature coefficient; 2: the coefficient is the noise
+  // network's output (options 14,15,18,19, Euler); 0: generic runtime-selected form
+  const bool net_diff = p.nets > 1 && p.tail.coef_src == CO_RBUF && p.tail.bounded && p.tail.special == SP_NONE && !p.tail.milstein &&
+                        (p.tail.mult == MU_Y || p.tail.mult == MU_ONE);
+  const bool fast_diff = !net_diff && p.tail.bounded && p.tail.special == SP_NONE && p.tail.mult == MU_Y;
+  const int diff = net_diff ? 2 : (fast_diff ? 1 : 0);
   cudaError_t e = cudaErrorInvalidConfiguration;
   const int key = NR * 100 + CH * 10 + p.MT;
 #define TCG_CASE(nr, ch, mt)                                                              \
   case nr * 100 + ch * 10 + mt:                                                          \
-    e = fast_diff ? tcg_launch<nr, ch, mt, 1>(p, grid, L.total, stream) : tcg_launch<nr, ch, mt, 0>(p, grid, L.total, stream); \
+    e = diff == 2 ? tcg_launch<nr, ch, mt, 2>(p, grid, L.total, stream)                  \
+      : (diff == 1 ? tcg_launch<nr, ch, mt, 1>(p, grid, L.total, stream) : tcg_launch<nr, ch, mt, 0>(p, grid, L.total, stream)); \
     break;
   switch (key) {
     TCG_CASE(8, 1, 1) TCG_CASE(16, 1, 1) TCG_CASE(32, 1, 1)

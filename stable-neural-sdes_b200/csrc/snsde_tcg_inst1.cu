@@ -4,4 +4,5 @@
 namespace snsde {
 template cudaError_t tcg_launch<32, 1, 1, 0>(const TcgParams&, int, size_t, cudaStream_t);
 template cudaError_t tcg_launch<32, 1, 1, 1>(const TcgParams&, int, size_t, cudaStream_t);
+template cudaError_t tcg_launch<32, 1, 1, 2>(const TcgParams&, int, size_t, cudaStream_t);
 }  // namespace snsde

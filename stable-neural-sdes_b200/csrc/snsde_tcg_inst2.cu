@@ -6,4 +6,6 @@ template cudaError_t tcg_launch<8, 1, 2, 0>(const TcgParams&, int, size_t, cudaS
 template cudaError_t tcg_launch<8, 1, 2, 1>(const TcgParams&, int, size_t, cudaStream_t);
 template cudaError_t tcg_launch<16, 1, 2, 0>(const TcgParams&, int, size_t, cudaStream_t);
 template cudaError_t tcg_launch<16, 1, 2, 1>(const TcgParams&, int, size_t, cudaStream_t);
+template cudaError_t tcg_launch<8, 1, 2, 2>(const TcgParams&, int, size_t, cudaStream_t);
+template cudaError_t tcg_launch<16, 1, 2, 2>(const TcgParams&, int, size_t, cudaStream_t);
 }  // namespace snsde

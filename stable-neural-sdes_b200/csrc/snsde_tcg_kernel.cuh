@@ -231,6 +231,14 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         const bool fin = (raw == raw) && (fabsf(raw) != INFINITY);
         g = tanh_fast(t.s_theta * nan_to_num_f(raw));
         dgy = t.milstein ? ((1.f - g * g) * t.s_theta) * (fin ? 1.f : 0.f) * cf : 0.f;
+      } else if (DIFF == 2) {
+        // state-network noise (options 14,15,18,19; BASELINE c4 is (3,18)): cf = q, the network's output for this row.
+        // Euler only (Milstein needs the vjp through the network: fp32 kernel), so no derivative.  Kept apart from the
+        // generic form below, whose inlined switch (sqrt / sigmoid / division slow paths) made this kernel 128 KB of
+        // SASS against a 32 KB instruction cache.
+        const float raw = (t.mult == MU_Y) ? cf * yr : cf;
+        g = tanh_fast(t.s_theta * nan_to_num_f(raw));
+        dgy = 0.f;
       } else {
         diffusion_eval<true>(t, cf, yr, t0, g, dgy);
       }
@@ -348,41 +356,41 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     // Descriptor arithmetic is incremental (one 64-bit add per operand and chunk) and the resident / streamed
     // cases are separate loops: the issue rate of this warp bounds the step time.
     const uint64_t ring_desc0 = umma_smem_desc(ring_base, kGALbo, kGASbo);
+    static_assert(CH == 1, "the resident issue loops assume one accumulator chain");
     auto issue_job = [&](int j, uint32_t bbase) {
       const int nk = p.jobs[j].nk;
       const uint32_t d = tmem + (p.jobs[j].phase == 0 ? 0u : region_cols) + (uint32_t)p.jobs[j].acc * Acc::kCols;
       uint64_t db = umma_smem_desc(bbase + p.jobs[j].b_chunk0 * 2 * L.lbo_b, L.lbo_b, 128);
       uint32_t acc = p.jobs[j].fresh ? 0u : 1u;
+      // Resident tiles: the elected lane alone runs the issue loop (the others wait at the warp sync), unrolled by
+      // 4 chunks: with the election test and the loop bookkeeping inside every iteration an MMA took ~50 cycles to issue
+      // (clock trace, c4: 1584 cycles for the 32 MMAs of a phase) against ~20 in the resident kernel.
       if (p.jobs[j].tmem_col >= 0) {                     // tiles resident in TMEM: TS-form MMAs (11-17 vs >= 39 cycles)
-        uint32_t ah = tmem + (uint32_t)p.jobs[j].tmem_col, al = ah + 8u * (uint32_t)nk;
-#pragma unroll 2
-        for (int kb = 0; kb < nk; kb += CH) {
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            if (leader) {
-              umma_f16_ts(d + Acc::a(c), ah, db, idesc2, acc);
-              umma_f16_ts(d + Acc::b(c), al, db, idesc1, 1u);
-            }
+        if (leader) {
+          uint32_t ah = tmem + (uint32_t)p.jobs[j].tmem_col, al = ah + 8u * (uint32_t)nk;
+#pragma unroll 4
+          for (int kb = 0; kb < nk; ++kb) {
+            umma_f16_ts(d + Acc::a(0), ah, db, idesc2, acc);
+            umma_f16_ts(d + Acc::b(0), al, db, idesc1, 1u);
             ah += 8; al += 8;
             db += b_step;
+            acc = 1u;
           }
-          acc = 1u;
         }
+        __syncwarp();
       } else if (!p.jobs[j].stream) {
-        uint64_t da = umma_smem_desc(w_base + p.jobs[j].a_off, kGALbo, kGASbo);
-#pragma unroll 2
-        for (int kb = 0; kb < nk; kb += CH) {
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            if (leader) {
-              umma_f16(d + Acc::a(c), da, db, idesc2, acc);
-              umma_f16(d + Acc::b(c), da + (4096 >> 4), db, idesc1, 1u);     // corr columns: the hi product just initialised them
-            }
+        if (leader) {
+          uint64_t da = umma_smem_desc(w_base + p.jobs[j].a_off, kGALbo, kGASbo);
+#pragma unroll 4
+          for (int kb = 0; kb < nk; ++kb) {
+            umma_f16(d + Acc::a(0), da, db, idesc2, acc);
+            umma_f16(d + Acc::b(0), da + (4096 >> 4), db, idesc1, 1u);     // corr columns: the hi product just initialised them
             da += (uint64_t)(kTcgSlotBytes >> 4);
             db += b_step;
+            acc = 1u;
           }
-          acc = 1u;
         }
+        __syncwarp();
       } else {
         for (int kb = 0; kb < nk; kb += CH) {
 #pragma unroll
