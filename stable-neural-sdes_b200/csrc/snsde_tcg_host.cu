@@ -297,7 +297,8 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
       // Ring depth: 8 slots (64 KB in flight).  With one CTA per SM all streaming the same tiles the limit is the
       // chip-wide L2 throughput (c5: 128 CTAs x 444 KB per step ~ 6 TB/s), not the ring; deeper rings only take
       // shared memory away from resident segments (measured: no gain on c5, a loss on c4).
-      const int nslot = ((long long)total_tiles > room) ? 8 : 0;
+      int nslot = ((long long)total_tiles > room) ? 8 : 0;
+      if (nslot && getenv("SNSDE_TCG_NSLOT") != nullptr) nslot = std::max(2, atoi(getenv("SNSDE_TCG_NSLOT")));   // experiment knob
       int res_bytes = 0, n_stream = 0;
       bool x_ok = true;
       plan_residency(nslot, true, res_bytes, n_stream, x_ok);

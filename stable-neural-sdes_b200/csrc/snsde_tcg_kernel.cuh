@@ -1,5 +1,8 @@
 // General tcgen05 kernel (see snsde_tcg.cuh).  Included by the instantiation units only.
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -64,6 +67,11 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
   const TcgSmem L = tcg_smem_layout(p.wres_bytes, p.nslot, HP, nets, C, Cpad, N, NR, p.nx, p.nstg, NP, p.uses_control);
   const int row0 = blockIdx.x * NR;
   const uint32_t region_cols = (uint32_t)(nets * MT) * Acc::kCols;       // 2 regions: phase 0 | later phases
+  // Thread-block cluster (1 = none): every CTA of a cluster streams the SAME weight tiles in the same order, so each
+  // tile is fetched from L2 once and multicast into all their rings (c5: the chip-wide L2 stream, not the ring, bounded
+  // the step).  CTA r issues the copies of the slots with index % CL == r; a slot is free once all CL CTAs have consumed it.
+  const uint32_t CL = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   const uint32_t bar_acc = smem_u32(&bars[1]);
@@ -96,13 +104,14 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     mbar_init(bar_acc, 1);
     for (int i = 0; i < p.nx; ++i) { mbar_init(bar_xfull + 8 * i, kGProdWarps); mbar_init(bar_xempty + 8 * i, 1); }
     for (int i = 0; i < p.nstg; ++i) mbar_init(bar_cfull + 8 * i, 1);
-    for (int i = 0; i < p.nslot; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rempty + 8 * i, 1); }
+    for (int i = 0; i < p.nslot; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rempty + 8 * i, CL); }
     mbar_fence_init();
   }
   if (warp == kGMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();            // every CTA's barriers exist before a peer arrives on them / copies into the rings
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // TMEM-resident jobs: lane m = weight row m of the tile, each 32-bit column packs two consecutive K elements
@@ -401,7 +410,8 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
             if (leader) {
               umma_f16(d + Acc::a(c), da, db, idesc2, acc);
               umma_f16(d + Acc::b(c), da + (4096 >> 4), db, idesc1, 1u);     // corr columns: the hi product just initialised them
-              umma_commit(bar_rempty + 8 * rslot);
+              if (CL > 1) umma_commit_multicast(bar_rempty + 8 * rslot, cmask);   // "consumed" to every CTA of the cluster
+              else umma_commit(bar_rempty + 8 * rslot);
             }
             __syncwarp();
             if (++rslot == (uint32_t)p.nslot) { rslot = 0; rphase ^= 1; }
@@ -601,7 +611,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     // The streamed segments are consumed in the same order every step, so one lane keeps the ring full with
     // 8 KB bulk copies, running ahead of the MMA warp across layers and steps.
     if (lane == 0 && p.n_stream_chunks > 0) {
-      uint32_t slot = 0, phase = 0;
+      uint32_t slot = 0, phase = 0, turn = 0;               // turn: whose copy this is (round robin over the cluster)
       for (int s = 0; s < p.S; ++s) {
         for (int j = 0; j < p.n_jobs; ++j) {
           const TcgJob& jb = p.jobs[j];
@@ -609,8 +619,11 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
           for (int kb = 0; kb < jb.nk; ++kb) {
             mbar_wait(bar_rempty + 8 * slot, phase ^ 1);      // tight poll: a sleeping streamer caps the ring at ~30 B/cycle
             mbar_arrive_expect_tx(bar_rfull + 8 * slot, kTcgSlotBytes);
-            bulk_g2s(smem_u32(smem + L.ring + slot * kTcgSlotBytes), p.wblob + jb.g_off + (size_t)kb * kTcgSlotBytes,
-                     kTcgSlotBytes, bar_rfull + 8 * slot);
+            const uint8_t* src = p.wblob + jb.g_off + (size_t)kb * kTcgSlotBytes;
+            const uint32_t dst = smem_u32(smem + L.ring + slot * kTcgSlotBytes);
+            if (CL == 1) bulk_g2s(dst, src, kTcgSlotBytes, bar_rfull + 8 * slot);
+            else if (turn == crank) bulk_g2s_multicast(dst, src, kTcgSlotBytes, bar_rfull + 8 * slot, cmask);
+            if (++turn == CL) turn = 0;
             if (++slot == (uint32_t)p.nslot) { slot = 0; phase ^= 1; }
           }
         }
@@ -621,6 +634,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
   tc_fence_before();
   __syncthreads();
   if (warp == kGMmaWarp) tmem_dealloc(tmem, 512);
+  if (CL > 1) cluster_sync_all();            // no CTA leaves while a peer may still multicast into its ring / barriers
 }
 
 template <int NR, int CH, int MT, int DIFF>
@@ -628,8 +642,41 @@ cudaError_t tcg_launch(const TcgParams& p, int grid, size_t smem, cudaStream_t s
   auto kern = snsde_tcg_kernel<NR, CH, MT, DIFF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kTcgThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  // Streamed weights: launch thread-block clusters so that one L2 read of a tile feeds several CTAs (multicast).
+  // Largest cluster (4, 2) the device can keep resident for the whole grid in one wave; SNSDE_TCG_CLUSTER overrides.
+  int cl = 1;
+  if (p.n_stream_chunks > 0) {
+    const char* env = getenv("SNSDE_TCG_CLUSTER");
+    for (int want : {4, 2}) {
+      if (env != nullptr && atoi(env) != want) continue;
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3((unsigned)((grid + want - 1) / want * want)); q.blockDim = dim3(kTcgThreads); q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute a[1];
+      a[0].id = cudaLaunchAttributeClusterDimension;
+      a[0].val.clusterDim.x = want; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+      q.attrs = a; q.numAttrs = 1;
+      int n_clusters = 0;
+      const cudaError_t eo = cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q);
+      if (getenv("SNSDE_TCG_DEBUG") != nullptr)
+        fprintf(stderr, "[snsde] cluster %d: occupancy query %s, %d active clusters, grid %u\n", want, cudaGetErrorString(eo), n_clusters, q.gridDim.x);
+      if (eo == cudaSuccess && n_clusters * want >= (int)q.gridDim.x) { cl = want; break; }
+      (void)cudaGetLastError();
+    }
+    if (env != nullptr && atoi(env) == 1) cl = 1;
+  }
+  if (cl == 1) {
+    kern<<<grid, kTcgThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((grid + cl - 1) / cl * cl)); cfg.blockDim = dim3(kTcgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 }  // namespace snsde
