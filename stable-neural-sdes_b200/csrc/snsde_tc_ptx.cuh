@@ -122,6 +122,17 @@ __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatil
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// shared::cluster address of `smem_addr` (an address in THIS CTA's window) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// local shared memory -> a peer CTA's shared memory (DSMEM bulk copy); completes `bytes` on the PEER's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t peer_dst, uint32_t local_src, uint32_t bytes, uint32_t peer_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(peer_dst), "r"(local_src), "r"(bytes), "r"(peer_bar) : "memory");
+}
 // global -> shared bulk copy delivered to the same shared-memory offset (and mbarrier) of every CTA in `cta_mask`:
 // one L2 read feeds the whole cluster.
 __device__ __forceinline__ void bulk_g2s_multicast(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {

@@ -31,6 +31,7 @@ struct TcgJob {
   int stream;       // A tiles come through the ring
   int a_off;        // resident: byte offset in the shared-memory weight area (packed per launch)
   int g_off;        // byte offset of the job's tiles in the global weight blob ([chunk][hi 4 KB | lo 4 KB])
+  int g_off1;       // M-split launches: the tiles of the cluster's second CTA (output features 128..255)
   int tmem_col;     // >= 0: the job's tiles are resident in TMEM (TS-form MMAs): hi images at [col, col + 8 nk),
                     // lo images at [col + 8 nk, col + 16 nk); -1: shared memory / ring
 };
@@ -80,7 +81,7 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
 void tcg_release(TcgPlan& tc);
 
 // launchers instantiated in snsde_tcg_inst*.cu
-template <int NR, int CH, int MT, int DIFF>
+template <int NR, int CH, int MT, int DIFF, bool MS = false>
 cudaError_t tcg_launch(const TcgParams& p, int grid, size_t smem, cudaStream_t stream);
 
 }  // namespace snsde

@@ -217,6 +217,51 @@ int tcg_set_weights(TcgPlan& tc, const snsde_model_desc& d, const Program& pg, c
   return SNSDE_OK;
 }
 
+// M-split launch: `p` is the fully prepared single-CTA parameter block (MT = 2).  Returns cudaErrorNotSupported when
+// the halved weight set does not fit resident.
+static cudaError_t tcg_forward_msplit(TcgPlan& tc, const TcgParams& full, int B, cudaStream_t stream, int* n_launches) {
+  TcgParams p = full;
+  p.MT = 1; p.HP = 128;
+  // jobs come in (tile 0, tile 1) pairs: keep one job per pair, remember both tile images
+  int nj = 0;
+  for (int j = 0; j + 1 < full.n_jobs; j += 2) {
+    TcgJob jb = full.jobs[j];
+    jb.g_off1 = full.jobs[j + 1].g_off;
+    jb.acc = 0; jb.stream = 0; jb.a_off = 0; jb.tmem_col = -1;
+    p.jobs[nj++] = jb;
+  }
+  if (2 * nj != full.n_jobs) return cudaErrorNotSupported;
+  p.n_jobs = nj; p.n_xjobs = full.n_xjobs / 2;
+  int NR = 8;
+  while (NR < 16 && 2 * ((B + NR - 1) / NR) > tc.num_sms) NR *= 2;
+  const int N = 16;
+  // tensor memory behind the two accumulator regions (one accumulator set each), then shared memory: everything resident
+  int col = 2 * 2 * N;
+  for (int j = 0; j < p.n_jobs; ++j) {
+    const int need = 16 * p.jobs[j].nk;
+    if (getenv("SNSDE_TC_NO_TMEM") == nullptr && col + need <= 512) { p.jobs[j].tmem_col = col; col += need; }
+  }
+  int packed = 0;
+  for (int j = 0; j < p.n_jobs; ++j) if (p.jobs[j].tmem_col < 0) { p.jobs[j].a_off = packed; packed += p.jobs[j].nk * kTcgSlotBytes; }
+  TcgSmem L;
+  bool ok = false;
+  for (int cfg = 0; cfg < 3 && !ok; ++cfg) {
+    p.nx = cfg == 0 ? 4 : 2;
+    p.nstg = cfg == 2 ? 2 : 4;
+    L = tcg_smem_layout(packed, 0, p.HP, p.nets, p.C, p.Cpad, N, NR, p.nx, p.nstg, p.NP, p.uses_control, 1);
+    ok = L.total <= tc.smem_optin;
+  }
+  if (!ok) return cudaErrorNotSupported;
+  p.nslot = 0; p.n_stream_chunks = 0; p.wres_bytes = packed;
+  const int grid = 2 * ((B + NR - 1) / NR);
+  const bool fast_diff = p.tail.bounded && p.tail.special == SP_NONE && p.tail.mult == MU_Y;
+  cudaError_t e = cudaErrorNotSupported;
+  if (NR == 8) e = fast_diff ? tcg_launch<8, 1, 1, 1, true>(p, grid, L.total, stream) : tcg_launch<8, 1, 1, 0, true>(p, grid, L.total, stream);
+  else e = fast_diff ? tcg_launch<16, 1, 1, 1, true>(p, grid, L.total, stream) : tcg_launch<16, 1, 1, 0, true>(p, grid, L.total, stream);
+  if (e == cudaSuccess) *n_launches += 1;
+  return e;
+}
+
 cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream, int* n_launches) {
   TcgParams p = tc.proto;
   p.coeffs = a.coeffs; p.coeff_row_stride = a.coeff_row_stride; p.y0 = a.y0; p.B = a.B;
@@ -245,6 +290,13 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
     p.dbg = s_dbg;
   }
 
+  // M-split (hidden 129..256, one network): a cluster of CTA pairs, each CTA owning one 128-feature tile of every
+  // layer, when half the weight set fits tensor memory + shared memory (then nothing is streamed).  Tried first;
+  // SNSDE_TCG_NO_MSPLIT=1 forces the single-CTA form below (tests compare the two).
+  if (p.MT == 2 && p.nets == 1 && getenv("SNSDE_TCG_NO_MSPLIT") == nullptr) {
+    cudaError_t e = tcg_forward_msplit(tc, p, a.B, stream, n_launches);
+    if (e != cudaErrorNotSupported) return e;
+  }
   const int nacc = p.nets * p.MT;
   // rows per CTA: fewest that covers the batch in one wave; MT = 2 keeps the state of two features per thread
   int NR = 8;

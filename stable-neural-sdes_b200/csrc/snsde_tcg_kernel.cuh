@@ -35,16 +35,19 @@ struct TcgSmem {
   int lbo_b, b_bytes, x_slot_bytes, stg_bytes, prep_bytes, n_bars;
 };
 
+// msplit: the launch is a cluster of CTA pairs, each CTA owning 128 of the 256 output features (HP = 128 local features)
+// while the B operands hold all 256 input features (two buffers, ping-pong per phase) and two more mbarriers count the
+// peer's half arriving.
 __host__ __device__ inline TcgSmem tcg_smem_layout(int wres_bytes, int nslot, int HP, int nets, int C, int Cpad, int N, int NR,
-                                                   int nx, int nstg, int NP, int uses_control) {
+                                                   int nx, int nstg, int NP, int uses_control, int msplit = 0) {
   TcgSmem s;
   s.lbo_b = (2 * N / 8) * 128 + 16;
   s.w = 0;
   s.ring = (wres_bytes + 127) & ~127;
   s.b0 = s.ring + nslot * kTcgSlotBytes;
-  s.b_bytes = (HP / 8) * s.lbo_b;
+  s.b_bytes = ((msplit ? 2 * HP : HP) / 8) * s.lbo_b;
   s.b1 = s.b0 + s.b_bytes;
-  s.x = s.b1 + (nets > 1 ? s.b_bytes : 0);
+  s.x = s.b1 + ((nets > 1 || msplit) ? s.b_bytes : 0);
   s.x_slot_bytes = uses_control ? (Cpad / 8) * s.lbo_b : 0;
   s.stg = s.x + nx * s.x_slot_bytes;
   s.stg_bytes = uses_control ? NR * 16 * C : 0;
@@ -52,26 +55,35 @@ __host__ __device__ inline TcgSmem tcg_smem_layout(int wres_bytes, int nslot, in
   s.prep_bytes = (NR + 2) * HP * 4 + 32;
   s.bias = s.prep + 2 * s.prep_bytes;
   s.bars = s.bias + NP * nets * HP * 4;
-  s.n_bars = 2 + 2 * nx + nstg + 4 + 2 * nslot;
+  s.n_bars = 2 + 2 * nx + nstg + 4 + 2 * nslot + 2;     // the last two: peer-half arrival (msplit)
   s.total = s.bars + 8 * s.n_bars + 16;
   return s;
 }
 
-template <int NR, int CH, int MT, int DIFF>
+// MS ("M-split", hidden 129..256 with every weight tile resident): the launch is a cluster of CTA PAIRS.  Both CTAs of
+// a pair integrate the same NR rows; CTA c owns output features [128c, 128c+128) of every layer - half the weights,
+// which then fit in tensor memory + shared memory with nothing streamed - and after each layer pushes its half of the
+// next B operand into the peer's shared memory with one DSMEM bulk copy (cp.async.bulk.shared::cluster.shared::cta)
+// that completes on the peer's mbarrier.  The MMA warp issues the K chunks of its OWN half first and waits for the
+// peer's half only then, so the exchange overlaps the first half of the layer's MMAs.  B operands ping-pong between two
+// buffers per phase, which makes the exchange race-free without credits (a CTA can be at most one phase ahead).
+template <int NR, int CH, int MT, int DIFF, bool MS>
 __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgParams p) {
+  static_assert(!MS || MT == 1, "M-split CTAs own one 128-feature tile");
   constexpr int N = NR < 16 ? 16 : NR;
   using Acc = AccRegion<N, CH>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, HP = p.HP, C = p.C, Cpad = p.Cpad, NP = p.NP, nets = p.nets;
-  const TcgSmem L = tcg_smem_layout(p.wres_bytes, p.nslot, HP, nets, C, Cpad, N, NR, p.nx, p.nstg, NP, p.uses_control);
-  const int row0 = blockIdx.x * NR;
+  const TcgSmem L = tcg_smem_layout(p.wres_bytes, p.nslot, HP, nets, C, Cpad, N, NR, p.nx, p.nstg, NP, p.uses_control, MS ? 1 : 0);
   const uint32_t region_cols = (uint32_t)(nets * MT) * Acc::kCols;       // 2 regions: phase 0 | later phases
   // Thread-block cluster (1 = none): every CTA of a cluster streams the SAME weight tiles in the same order, so each
   // tile is fetched from L2 once and multicast into all their rings (c5: the chip-wide L2 stream, not the ring, bounded
   // the step).  CTA r issues the copies of the slots with index % CL == r; a slot is free once all CL CTAs have consumed it.
   const uint32_t CL = cluster_nctarank(), crank = cluster_ctarank();
   const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  const int fbase = MS ? 128 * (int)crank : 0;                           // global index of this CTA's local feature 0
+  const int row0 = (MS ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * NR; // M-split: both CTAs of a pair share the rows
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   const uint32_t bar_acc = smem_u32(&bars[1]);
@@ -79,13 +91,14 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
   const uint32_t bar_cfull = bar_xempty + 8 * p.nx;
   const uint32_t bar_pfull = bar_cfull + 8 * p.nstg, bar_pempty = bar_pfull + 16;
   const uint32_t bar_rfull = bar_pempty + 16, bar_rempty = bar_rfull + 8 * p.nslot;
+  const uint32_t bar_peer = bar_rempty + 8 * p.nslot;                    // [2]: the peer's half of operand buffer 0 / 1 landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[L.n_bars]);
 
   // ---- one-time setup ----
   for (int j = 0; j < p.n_jobs; ++j) {                 // resident weight segments -> smem
     const TcgJob& jb = p.jobs[j];
     if (jb.stream || jb.tmem_col >= 0) continue;
-    const uint4* src = reinterpret_cast<const uint4*>(p.wblob + jb.g_off);
+    const uint4* src = reinterpret_cast<const uint4*>(p.wblob + ((MS && crank) ? jb.g_off1 : jb.g_off));
     uint4* dst = reinterpret_cast<uint4*>(smem + L.w + jb.a_off);
     for (int i = tid; i < jb.nk * (kTcgSlotBytes / 16); i += kTcgThreads) dst[i] = src[i];
   }
@@ -97,7 +110,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     for (int i = tid; i < NP * nets * HP; i += kTcgThreads) {
       const int f = i % HP, pn = i / HP, net = pn % nets, ph = pn / nets;
       const int off = p.bias[ph][net];
-      sb[i] = (off >= 0 && f < H) ? p.vec[off + f] : 0.f;
+      sb[i] = (off >= 0 && fbase + f < H) ? p.vec[off + fbase + f] : 0.f;
     }
   }
   if (tid == 0) {
@@ -105,6 +118,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     for (int i = 0; i < p.nx; ++i) { mbar_init(bar_xfull + 8 * i, kGProdWarps); mbar_init(bar_xempty + 8 * i, 1); }
     for (int i = 0; i < p.nstg; ++i) mbar_init(bar_cfull + 8 * i, 1);
     for (int i = 0; i < p.nslot; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rempty + 8 * i, CL); }
+    mbar_init(bar_peer, 1); mbar_init(bar_peer + 8, 1);
     mbar_fence_init();
   }
   if (warp == kGMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -122,7 +136,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     for (int j = 0; j < p.n_jobs; ++j) {
       const int col = p.jobs[j].tmem_col, nk = p.jobs[j].nk;
       if (col < 0) continue;
-      const uint8_t* src = p.wblob + p.jobs[j].g_off + (m >> 3) * kGASbo + (m & 7) * 16;
+      const uint8_t* src = p.wblob + ((MS && crank) ? p.jobs[j].g_off1 : p.jobs[j].g_off) + (m >> 3) * kGASbo + (m & 7) * 16;
       for (int i = (warp >> 2); i < 2 * nk; i += kGEpiPerQuad) {          // i < nk: hi image of chunk i; else lo image
         const int kb = i < nk ? i : i - nk;
         const uint8_t* q = src + (size_t)kb * kTcgSlotBytes + (i < nk ? 0 : 4096);
@@ -196,7 +210,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       myslot[i] = p.row_slot ? p.row_slot[b] : -1;
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const int f = h + 128 * mt;
+        const int f = fbase + h + 128 * mt;                 // global feature
         y[mt][i] = f < H ? p.y0[(size_t)b * H + f] : 0.f;
         yprev[mt][i] = y[mt][i];
         qn[mt][i] = 0.f;
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     auto emit = [&](snsde_emit em) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const int f = h + 128 * mt;
+        const int f = fbase + h + 128 * mt;
         if (f >= H) continue;
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
@@ -281,13 +295,15 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int i = 0; i < NPRE; ++i)
-            if (h + 128 * mt < H) state_terms(y[mt][i], vec1[mt], si.t0, gv[mt][i], dg[mt][i], thy[mt][i]);
+            if (fbase + h + 128 * mt < H) state_terms(y[mt][i], vec1[mt], si.t0, gv[mt][i], dg[mt][i], thy[mt][i]);
       }
       for (int ph = 0; ph < NP; ++ph) {
         mbar_wait(bar_acc, pacc);
         pacc ^= 1;
         tc_fence_after();
         TC_TRACE(tid == 0 && ph < 2, s, ph == 0 ? EV_EPI_ACC0 : EV_EPI_ACC1);
+        // M-split: the operand of global phase q lives in buffer q & 1; this phase (q = s*NP + ph) writes the next one's
+        const int ob = MS ? ((((s * NP + ph + 1) & 1) != 0) ? L.b1 : L.b0) : L.b0;
         // ---- noise network (state-dependent noise options), layers 0..NN-1 ride on phases 0..NN-1 ----
         if (net2 && ph < p.NN) {
 #pragma unroll
@@ -309,21 +325,21 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         // ---- drift network ----
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          const int f = h + 128 * mt;
+          const int fl = h + 128 * mt, f = fbase + fl;        // local (tables in shared memory) / global feature
           float vm[RT], vc[RT];
           load_acc(ph, mt, vm, vc);
           TC_TRACE(tid == 0 && ph < 2 && mt == 0, s, ph == 0 ? EV_EPI_LD0 : EV_EPI_LD1);
           if (f >= H) continue;
           if (ph < NP - 1) {
-            const float add = (ph == 0) ? add0[mt] : bias_of(ph, 0, f);
+            const float add = (ph == 0) ? add0[mt] : bias_of(ph, 0, fl);
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
               float v = fmaf(vc[i], kLoInv, vm[i]) + add;
               v = v < 0.f ? 0.f : v;
-              write_operand(L.b0, f, rbase + i, v);
+              write_operand(ob, f, rbase + i, v);
             }
           } else {
-            const float bl = bias_of(ph, 0, f);
+            const float bl = bias_of(ph, 0, fl);
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
               float d = fmaf(vc[i], kLoInv, vm[i]) + bl;
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
               else state_terms(y[mt][i], net2 ? qn[mt][i] : vec1[mt], si.t0, g, dgy, th);
               if (t.geometric) d *= th;
               if (t.clip_drift) d = tanh_fast(d);
-              const float dw = sdw[(rbase + i) * HP + f];
+              const float dw = sdw[(rbase + i) * HP + fl];
               float yn = __fadd_rn(__fadd_rn(y[mt][i], __fmul_rn(d, si.h)), __fmul_rn(g, dw));
               if (t.milstein) {
                 const float v2 = __fmul_rn(dw, dw) - si.h;
@@ -340,7 +356,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
               }
               yprev[mt][i] = y[mt][i];
               y[mt][i] = yn;
-              write_operand(L.b0, f, rbase + i, yn);
+              write_operand(ob, f, rbase + i, yn);
             }
           }
         }
@@ -366,19 +382,20 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     // cases are separate loops: the issue rate of this warp bounds the step time.
     const uint64_t ring_desc0 = umma_smem_desc(ring_base, kGALbo, kGASbo);
     static_assert(CH == 1, "the resident issue loops assume one accumulator chain");
-    auto issue_job = [&](int j, uint32_t bbase) {
+    // chunks [kb0, kb1) of job j; `acc0`: accumulate flag of the first MMA issued (later ones always accumulate)
+    auto issue_job = [&](int j, uint32_t bbase, int kb0, int kb1, uint32_t acc0) {
       const int nk = p.jobs[j].nk;
       const uint32_t d = tmem + (p.jobs[j].phase == 0 ? 0u : region_cols) + (uint32_t)p.jobs[j].acc * Acc::kCols;
-      uint64_t db = umma_smem_desc(bbase + p.jobs[j].b_chunk0 * 2 * L.lbo_b, L.lbo_b, 128);
-      uint32_t acc = p.jobs[j].fresh ? 0u : 1u;
+      uint64_t db = umma_smem_desc(bbase + (p.jobs[j].b_chunk0 + kb0) * 2 * L.lbo_b, L.lbo_b, 128);
+      uint32_t acc = acc0;
       // Resident tiles: the elected lane alone runs the issue loop (the others wait at the warp sync), unrolled by
       // 4 chunks: with the election test and the loop bookkeeping inside every iteration an MMA took ~50 cycles to issue
       // (clock trace, c4: 1584 cycles for the 32 MMAs of a phase) against ~20 in the resident kernel.
       if (p.jobs[j].tmem_col >= 0) {                     // tiles resident in TMEM: TS-form MMAs (11-17 vs >= 39 cycles)
         if (leader) {
-          uint32_t ah = tmem + (uint32_t)p.jobs[j].tmem_col, al = ah + 8u * (uint32_t)nk;
+          uint32_t ah = tmem + (uint32_t)p.jobs[j].tmem_col + 8u * (uint32_t)kb0, al = ah + 8u * (uint32_t)nk;
 #pragma unroll 4
-          for (int kb = 0; kb < nk; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             umma_f16_ts(d + Acc::a(0), ah, db, idesc2, acc);
             umma_f16_ts(d + Acc::b(0), al, db, idesc1, 1u);
             ah += 8; al += 8;
@@ -389,9 +406,9 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         __syncwarp();
       } else if (!p.jobs[j].stream) {
         if (leader) {
-          uint64_t da = umma_smem_desc(w_base + p.jobs[j].a_off, kGALbo, kGASbo);
+          uint64_t da = umma_smem_desc(w_base + p.jobs[j].a_off + kb0 * kTcgSlotBytes, kGALbo, kGASbo);
 #pragma unroll 4
-          for (int kb = 0; kb < nk; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             umma_f16(d + Acc::a(0), da, db, idesc2, acc);
             umma_f16(d + Acc::b(0), da + (4096 >> 4), db, idesc1, 1u);     // corr columns: the hi product just initialised them
             da += (uint64_t)(kTcgSlotBytes >> 4);
@@ -400,8 +417,8 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
           }
         }
         __syncwarp();
-      } else {
-        for (int kb = 0; kb < nk; kb += CH) {
+      } else {                                           // streamed tiles (never under M-split): whole job, ring order
+        for (int kb = kb0; kb < kb1; kb += CH) {
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             mbar_wait(bar_rfull + 8 * rslot, rphase);
@@ -445,8 +462,30 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
         }
         tc_fence_after();
         TC_TRACE(lane == 0 && ph < 2, s, ph == 0 ? EV_MMA_WAKE0 : EV_MMA_WAKE1);
+        if (MS && !isx) {
+          // operand of global phase q = s*NP + ph: buffer q & 1.  Send this CTA's half to the peer, run the MMAs over the
+          // own half, wait for the peer's half, run the rest.
+          const uint32_t q = (uint32_t)(s * NP + ph), buf = q & 1u;
+          const uint32_t bbase = buf ? b_base1 : b_base0;
+          const uint32_t half_bytes = 16u * (uint32_t)L.lbo_b, own_off = crank * half_bytes;
+          if (lane == 0) {
+            mbar_arrive_expect_tx(bar_peer + 8 * buf, half_bytes);                 // the bytes the PEER will deliver here
+            dsmem_bulk_copy(mapa_u32(bbase + own_off, crank ^ 1u), bbase + own_off, half_bytes, mapa_u32(bar_peer + 8 * buf, crank ^ 1u));
+          }
+          __syncwarp();
+          const int k_own = 8 * (int)crank, k_peer = 8 * (int)(crank ^ 1u);
+          const int j0 = j;
 #pragma unroll 1
-        for (; j < j_end; ++j) issue_job(j, isx ? xb : (p.jobs[j].b_src ? b_base1 : b_base0));
+          for (; j < j_end; ++j) issue_job(j, bbase, k_own, k_own + 8, p.jobs[j].fresh ? 0u : 1u);
+          mbar_wait(bar_peer + 8 * buf, (q >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll 1
+          for (j = j0; j < j_end; ++j) issue_job(j, bbase, k_peer, k_peer + 8, 1u);
+        } else {
+#pragma unroll 1
+          for (; j < j_end; ++j)
+            issue_job(j, isx ? xb : (p.jobs[j].b_src ? b_base1 : b_base0), 0, p.jobs[j].nk, p.jobs[j].fresh ? 0u : 1u);
+        }
         if (leader) umma_commit(commit_bar);
         __syncwarp();
         TC_TRACE(lane == 0 && (ph < 2 || isx), s, isx ? EV_MMA_X_DONE : (ph == 0 ? EV_MMA_COMMIT0 : EV_MMA_COMMIT1));
@@ -543,7 +582,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
     float c0[MT], csin[MT], ccos[MT], n0[MT], nsin[MT], ncos[MT], coef[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const int f = h + 128 * mt;
+      const int f = fbase + h + 128 * mt;
       const bool a = f < H;
       c0[mt] = (a && p.bias[0][0] >= 0) ? p.vec[p.bias[0][0] + f] : 0.f;
       csin[mt] = (a && p.c_sin[0] >= 0) ? p.vec[p.c_sin[0] + f] : 0.f;
@@ -566,7 +605,7 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       float v1[MT];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const int f = h + 128 * mt;
+        const int f = fbase + h + 128 * mt;
         v1[mt] = coef[mt];
         if (f >= H) continue;
         if (nets > 1) v1[mt] = fmaf(st.cos_t0, ncos[mt], fmaf(st.sin_t0, nsin[mt], n0[mt]));
@@ -579,11 +618,11 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
       if (s >= 2) named_sync(kGBarPEmpty + (s & 1), kGCntPrep);
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        const int f = h + 128 * mt;
+        const int fl = h + 128 * mt, f = fbase + fl;
         if (f >= H) continue;
         if (p.dW != nullptr) {
 #pragma unroll 4
-          for (int r = 0; r < NR; ++r) sdw[r * HP + f] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + f];
+          for (int r = 0; r < NR; ++r) sdw[r * HP + fl] = p.dW[((size_t)s * p.B + min(row0 + r, p.B - 1)) * H + f];
         } else {
 #pragma unroll 1
           for (int q = 0; q < nq; ++q) {
@@ -592,16 +631,16 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
             const int rq = q * 4 - lane0;               // CTA-local row of the quad's first normal
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if ((unsigned)(rq + k) < (unsigned)NR) sdw[(rq + k) * HP + f] = __fmul_rn(nrm[k], st.sqrt_h);
+              if ((unsigned)(rq + k) < (unsigned)NR) sdw[(rq + k) * HP + fl] = __fmul_rn(nrm[k], st.sqrt_h);
           }
         }
       }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const int f = h + 128 * mt;
-        if (f >= H) continue;
-        sdw[NR * HP + f] = fmaf(st.cos_t0, ccos[mt], fmaf(st.sin_t0, csin[mt], c0[mt]));
-        sdw[(NR + 1) * HP + f] = v1[mt];
+        const int fl = h + 128 * mt;
+        if (fbase + fl >= H) continue;
+        sdw[NR * HP + fl] = fmaf(st.cos_t0, ccos[mt], fmaf(st.sin_t0, csin[mt], c0[mt]));
+        sdw[(NR + 1) * HP + fl] = v1[mt];
       }
       if (h == 0) *reinterpret_cast<StepInfo*>(slot + (NR + 2) * HP * 4) = si;
       named_arrive(kGBarPFull + (s & 1), kGCntPrep);
@@ -637,15 +676,16 @@ __global__ void __launch_bounds__(kTcgThreads, 1) snsde_tcg_kernel(const TcgPara
   if (CL > 1) cluster_sync_all();            // no CTA leaves while a peer may still multicast into its ring / barriers
 }
 
-template <int NR, int CH, int MT, int DIFF>
+template <int NR, int CH, int MT, int DIFF, bool MS>
 cudaError_t tcg_launch(const TcgParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = snsde_tcg_kernel<NR, CH, MT, DIFF>;
+  auto kern = snsde_tcg_kernel<NR, CH, MT, DIFF, MS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // Streamed weights: launch thread-block clusters so that one L2 read of a tile feeds several CTAs (multicast).
   // Largest cluster (4, 2) the device can keep resident for the whole grid in one wave; SNSDE_TCG_CLUSTER overrides.
   int cl = 1;
-  if (p.n_stream_chunks > 0) {
+  if (MS) cl = 2;                              // `grid` already counts both CTAs of every pair
+  else if (p.n_stream_chunks > 0) {
     const char* env = getenv("SNSDE_TCG_CLUSTER");
     for (int want : {4, 2}) {
       if (env != nullptr && atoi(env) != want) continue;
