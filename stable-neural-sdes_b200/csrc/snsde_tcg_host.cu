@@ -217,6 +217,20 @@ int tcg_set_weights(TcgPlan& tc, const snsde_model_desc& d, const Program& pg, c
   return SNSDE_OK;
 }
 
+// debug only (SNSDE_TC_TRACE): synchronous dump of the clock64 trace of CTA 0
+static void tcg_dump_trace(const TcgParams& p, cudaStream_t stream) {
+  if (p.dbg == nullptr) return;
+  std::vector<long long> hbuf((size_t)16 * p.S);
+  cudaStreamSynchronize(stream);
+  cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  FILE* f = fopen(getenv("SNSDE_TC_TRACE"), "w");
+  if (f) {
+    for (int s2 = 0; s2 < p.S; ++s2)
+      for (int k = 0; k < 16; ++k) fprintf(f, "%lld%c", hbuf[(size_t)s2 * 16 + k], k == 15 ? '\n' : ' ');
+    fclose(f);
+  }
+}
+
 // M-split launch: `p` is the fully prepared single-CTA parameter block (MT = 2).  Returns cudaErrorNotSupported when
 // the halved weight set does not fit resident.
 static cudaError_t tcg_forward_msplit(TcgPlan& tc, const TcgParams& full, int B, cudaStream_t stream, int* n_launches) {
@@ -258,7 +272,7 @@ static cudaError_t tcg_forward_msplit(TcgPlan& tc, const TcgParams& full, int B,
   cudaError_t e = cudaErrorNotSupported;
   if (NR == 8) e = fast_diff ? tcg_launch<8, 1, 1, 1, true>(p, grid, L.total, stream) : tcg_launch<8, 1, 1, 0, true>(p, grid, L.total, stream);
   else e = fast_diff ? tcg_launch<16, 1, 1, 1, true>(p, grid, L.total, stream) : tcg_launch<16, 1, 1, 0, true>(p, grid, L.total, stream);
-  if (e == cudaSuccess) *n_launches += 1;
+  if (e == cudaSuccess) { *n_launches += 1; tcg_dump_trace(p, stream); }
   return e;
 }
 
@@ -387,17 +401,7 @@ cudaError_t tcg_forward(TcgPlan& tc, const TcForwardArgs& a, cudaStream_t stream
   }
 #undef TCG_CASE
   if (e == cudaSuccess) *n_launches += 1;
-  if (p.dbg != nullptr && e == cudaSuccess) {
-    std::vector<long long> hbuf((size_t)16 * a.S);
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    FILE* f = fopen(getenv("SNSDE_TC_TRACE"), "w");
-    if (f) {
-      for (int s2 = 0; s2 < a.S; ++s2)
-        for (int k = 0; k < 16; ++k) fprintf(f, "%lld%c", hbuf[(size_t)s2 * 16 + k], k == 15 ? '\n' : ' ');
-      fclose(f);
-    }
-  }
+  if (e == cudaSuccess) tcg_dump_trace(p, stream);
   return e;
 }
 

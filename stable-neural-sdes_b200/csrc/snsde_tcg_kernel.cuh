@@ -15,7 +15,7 @@
 
 namespace snsde {
 
-constexpr int kGEpiPerQuad = 2;
+constexpr int kGEpiPerQuad = 4;
 constexpr int kGEpiWarps = 4 * kGEpiPerQuad;          // warps 0..7
 constexpr int kGMmaWarp = kGEpiWarps;                 // warp 8
 constexpr int kGProdWarp0 = kGMmaWarp + 1;            // warps 9..10 : X(t) producer

@@ -553,3 +553,26 @@ def test_noise_table_cache_follows_weight_updates_and_plan_is_safe_across_stream
         want_full = snsde_b200.sdeint(mg, y0d, td, dt=1.0, seed=5, precision="tc")
         for i, z in outs:
             assert torch.equal(z, want_full if i % 2 == 0 else want_full[::2])
+
+
+def test_m_split_cta_pairs_agree_with_the_single_cta_kernel(dev, monkeypatch):
+    """hidden 256: the cluster launch (CTA pairs, each owning 128 output features, operand halves exchanged through
+    DSMEM) against the single-CTA general kernel (streamed weights) and the oracle; ragged batch (odd number of pairs'
+    rows), control model, in-kernel Philox."""
+    for (io, no, B, C, L) in ((4, 17, 37, 14, 1), (3, 6, 20, 5, 1), (6, 17, 9, 7, 1)):
+        m, times, coeffs, y0 = make_problem(io, no, B, 256, C, L, 14, seed=500 + io)
+        mg = m.to(dev)
+        mg.set_X(coeffs.to(dev), times.to(dev))
+        with torch.no_grad():
+            a = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=21, precision="tc")
+            plan = snsde_b200.plans_of(mg)[("euler", "tc", str(dev))]
+            assert plan.kernel == "tcgen05_general"
+            dW = snsde_b200.philox_increments(21, plan.step_plan(times, 1.0, times), B, 256, dev).cpu()
+            monkeypatch.setenv("SNSDE_TCG_NO_MSPLIT", "1")
+            b = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=21, precision="tc")
+            monkeypatch.delenv("SNSDE_TCG_NO_MSPLIT")
+        m.to("cpu"); m.set_X(coeffs, times)
+        want = solver.sdeint(m, y0, times, 1.0, solver.BrownianTable(dW))
+        close(a, want)
+        close(b, want)
+        close(a, b, rtol=2e-5)
