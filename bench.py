@@ -499,11 +499,12 @@ def time_resident(wl, steps, warmup, barrier, max_over_ranks, clock_index=None):
         t_wall = time.perf_counter() - t_wall
         launches = wl.plan.launches - launches0
         if sampler and t_wall < 1.5:                # keep the GPU under load long enough for >= 10 clock samples
-            t_end = time.perf_counter() + 1.5
-            j = 0
-            while time.perf_counter() < t_end:
-                wl.step(j); j += 1
-                if j % 8 == 0:
+            # a FIXED number of extra solves agreed by all ranks: every solve carries a collective at N > 1, so a
+            # time-based loop would leave the ranks with different collective counts (and hang the next one)
+            n_extra = int(max_over_ranks(min(20000.0, 1.5 / max(t_wall / steps, 1e-5))))
+            for j in range(n_extra):
+                wl.step(j)
+                if j % 8 == 7:
                     torch.cuda.synchronize()
             wl.drain()
             torch.cuda.synchronize()
@@ -557,6 +558,10 @@ def main():
     torch.cuda.set_device(dev)
     numa_node = bind_to_gpu_numa(local_rank)
     if world > 1:
+        # The path's one collective moves 0.5 MB per rank and runs UNDER the next solve (side stream): keep NCCL to one
+        # channel so its CTAs do not take issue slots from the persistent solve kernel (measured at N=8: the solve slowed
+        # from 0.293 to 0.319 ms with NCCL's default channel count).  An explicit NCCL_MAX_NCHANNELS wins.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
