@@ -558,10 +558,11 @@ def main():
     torch.cuda.set_device(dev)
     numa_node = bind_to_gpu_numa(local_rank)
     if world > 1:
-        # The path's one collective moves 0.5 MB per rank and runs UNDER the next solve (side stream): keep NCCL to one
-        # channel so its CTAs do not take issue slots from the persistent solve kernel (measured at N=8: the solve slowed
-        # from 0.293 to 0.319 ms with NCCL's default channel count).  An explicit NCCL_MAX_NCHANNELS wins.
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+        # The path's one collective moves 0.5 MB per rank and runs UNDER the next solve (side stream).  Cap NCCL's channel
+        # count so its CTAs take few issue slots from the persistent solve kernel, but not below what the gather needs to
+        # finish within a solve - measured at N=8 (ms per solve): default channels 0.325, 4 channels 0.301, 1 channel 0.621
+        # (the gather itself becomes the bottleneck).  An explicit NCCL_MAX_NCHANNELS wins.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
