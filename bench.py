@@ -236,29 +236,46 @@ def run_reference_arm(args, w):
 
 
 # ---------------------------------------------------------------------------------------------------
+def _cpu_list(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus += list(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa(local_rank):
-    """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off, so the
-    host<->device copies of the e2e leg do not cross the socket interconnect (e2e erratic on the 8-GPU box)."""
+    """Best effort: run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU, so the host<->device
+    copies of the e2e leg do not cross the socket interconnect (e2e erratic on the 8-GPU box).  Sources, in
+    order: sysfs numa_node of the GPU's PCI function; the "CPU Affinity" column of `nvidia-smi topo -m`."""
     try:
+        cpus, where = [], None
         pr = torch.cuda.get_device_properties(local_rank)
         if all(hasattr(pr, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
             bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
-        else:
-            bus = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                 capture_output=True, text=True, timeout=10).stdout.strip().lower()
-            if len(bus.split(":")[0]) == 8:             # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
-                bus = bus[4:]
-        node = int(pathlib.Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
-        if node < 0:
-            return None
-        cpus = []
-        for part in pathlib.Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus += list(range(int(lo), int(hi or lo) + 1))
+            f = pathlib.Path(f"/sys/bus/pci/devices/{bus}/numa_node")
+            if f.exists():
+                node = int(f.read_text())
+                if node >= 0:
+                    cpus = _cpu_list(pathlib.Path(f"/sys/devices/system/node/node{node}/cpulist").read_text())
+                    where = f"numa node {node} (sysfs)"
+        if not cpus:
+            out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+            lines = [l for l in out.splitlines() if l.strip()]
+            hdr = next(l for l in lines if "CPU Affinity" in l)
+            cols = [c.strip() for c in hdr.split("\t")]
+            ci = cols.index("CPU Affinity")
+            row = next(l for l in lines if l.startswith(f"GPU{local_rank}\t") or l.startswith(f"GPU{local_rank} "))
+            cells = [c.strip() for c in row.split("\t")]
+            cpus = _cpu_list(cells[ci]) if ci < len(cells) else []
+            where = f"cpus {cells[ci]} (nvidia-smi topo)" if cpus else None
         allowed = sorted(set(cpus) & os.sched_getaffinity(0))
-        if allowed:
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
             os.sched_setaffinity(0, allowed)
-        return node
+            return where
+        return None
     except Exception as exc:                             # noqa: BLE001
         if os.environ.get("BENCH_DEBUG"):
             print(f"[bench] NUMA binding skipped: {exc!r}", file=sys.stderr)
@@ -556,6 +573,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    affinity0 = os.sched_getaffinity(0)
     numa_node = bind_to_gpu_numa(local_rank)
     if world > 1:
         # The path's one collective moves 0.5 MB per rank and runs UNDER the next solve (side stream).  Cap NCCL's channel
@@ -704,6 +722,7 @@ def main():
         roof = roofline_block(args.workload, w, plan, kern_ms, n_out_rows)
         cpu = None
         if not args.no_cpu_baseline:
+            os.sched_setaffinity(0, affinity0)          # the CPU baseline gets every host core again
             v, ts_cpu = time_cpu_reference(w, B)
             cpu = {"value": v, "unit": "SDE-steps/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"median of {len(ts_cpu)} full solves of the workload (B={B}, S={S}); {sum(ts_cpu):.1f}s of CPU work"}
