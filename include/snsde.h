@@ -214,6 +214,13 @@ int snsde_hermite_coeffs(const float* x_dev, const float* knots_dev, int32_t B, 
 int snsde_natural_coeffs(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
                          float* coeffs_dev, float* scratch_dev, int device, void* stream);
 
+/* The same builder for paths WITH missing values (NaN): benchmark_classification/controldiffeq/interpolate.py:56-153.
+ * Per scalar series: an all-NaN series gives zero coefficients, a NaN at either end is imputed with the nearest
+ * observation, the natural spline is built on the observed knots only and every original interval receives the piece
+ * it lies in, re-centred at its own knot.  x_dev [B,K,C] (NaN = missing) -> coeffs_dev [B,K-1,4C]; no scratch. */
+int snsde_natural_coeffs_missing(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
+                                 float* coeffs_dev, int device, void* stream);
+
 /* Missing-value (NaN) fill that torchcde applies before the Hermite builder (linear_interpolation_coeffs):
  * linear in t between observed neighbours, first observed value at the head, forward fill at the tail.
  * x_dev [B,K,C] -> out_dev [B,K,C] (must not alias x_dev). */

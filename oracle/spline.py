@@ -77,7 +77,7 @@ def natural_cubic_spline_coeffs(t, x):
     misc.py:52-64 so fp32 results match the reference to rounding.
     """
     if torch.isnan(x).any():
-        raise ValueError("oracle natural spline: missing values not supported (data prep is out of scope)")
+        return _natural_with_missing_values(t, x)
     K = x.size(-2)
     path = x.transpose(-1, -2)                       # [..., C, K]
     if K == 2:
@@ -119,6 +119,42 @@ def natural_cubic_spline_coeffs(t, x):
         three_d = (-six_dx * r + 3 * (kd[..., :-1] + kd[..., 1:])) * r2
         out = (a, b, two_c, three_d)
     return tuple(o.transpose(-1, -2) for o in out)
+
+
+def _natural_with_missing_values(t, x):
+    """Missing-value branch of the in-tree builder (interpolate.py:56-153), one scalar series at a time as the reference
+    does: an all-NaN series gives zero coefficients; a NaN at either end is imputed with the nearest observation; the
+    natural spline is built on the OBSERVED knots only and every original interval [t_i, t_{i+1}) then receives the
+    piece it lies in, re-centred at t_i:  with offset = t_obs - t_i <= 0
+        a_i = a + ((two_c/2 - three_d offset/3) offset - b) offset,   b_i = b + (three_d offset - two_c) offset,
+        two_c_i = two_c - 2 three_d offset,                           three_d_i = three_d."""
+    lead = x.shape[:-2]
+    K, C = x.shape[-2:]
+    flat = x.reshape(-1, K, C)
+    outs = [torch.zeros(flat.shape[0], K - 1, C, dtype=x.dtype) for _ in range(4)]
+    for n in range(flat.shape[0]):
+        for c in range(C):
+            path = flat[n, :, c].clone()
+            obs = ~torch.isnan(path)
+            if not obs.any():
+                continue
+            vals = path[obs]
+            if torch.isnan(path[0]):
+                path[0] = vals[0]
+            if torch.isnan(path[-1]):
+                path[-1] = vals[-1]
+            obs = ~torch.isnan(path)
+            t_o, p_o = t[obs], path[obs]
+            a, b, c2, d3 = natural_cubic_spline_coeffs(t_o, p_o.unsqueeze(-1))
+            a, b, c2, d3 = a[:, 0], b[:, 0], c2[:, 0], d3[:, 0]
+            piece = torch.bucketize(t[:-1], t_o, right=True) - 1          # observed interval containing t_i
+            off = t_o[piece] - t[:-1]
+            a_inner = (0.5 * c2[piece] - d3[piece] * off / 3) * off
+            outs[0][n, :, c] = a[piece] + (a_inner - b[piece]) * off
+            outs[1][n, :, c] = b[piece] + (d3[piece] * off - c2[piece]) * off
+            outs[2][n, :, c] = c2[piece] - 2 * d3[piece] * off
+            outs[3][n, :, c] = d3[piece]
+    return tuple(o.reshape(*lead, K - 1, C) for o in outs)
 
 
 class CubicSpline:

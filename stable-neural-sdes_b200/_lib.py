@@ -35,7 +35,7 @@ class Point(ctypes.Structure):
                 ("frac", ctypes.c_float), ("interval", ctypes.c_int32)]
 
 
-EXPORTS = ("snsde_initial_state", "snsde_readout_head", "snsde_plan_status_nowait", "snsde_backward", "snsde_backward_workspace_bytes", "snsde_abi_version", "snsde_last_error", "snsde_weight_count", "snsde_plan_create",
+EXPORTS = ("snsde_natural_coeffs_missing", "snsde_initial_state", "snsde_readout_head", "snsde_plan_status_nowait", "snsde_backward", "snsde_backward_workspace_bytes", "snsde_abi_version", "snsde_last_error", "snsde_weight_count", "snsde_plan_create",
            "snsde_plan_destroy", "snsde_plan_set_weights", "snsde_plan_kernel_kind", "snsde_forward",
            "snsde_philox_fill", "snsde_plan_launch_count", "snsde_plan_status", "snsde_hermite_coeffs",
            "snsde_natural_coeffs", "snsde_fill_missing")
@@ -72,6 +72,7 @@ def load():
     lib.snsde_hermite_coeffs.argtypes = [vp, vp, i32, i32, i32, vp, ctypes.c_int, vp]
     lib.snsde_natural_coeffs.argtypes = [vp, vp, i32, i32, i32, vp, vp, ctypes.c_int, vp]
     lib.snsde_fill_missing.argtypes = [vp, vp, i32, i32, i32, vp, ctypes.c_int, vp]
+    lib.snsde_natural_coeffs_missing.argtypes = [vp, vp, i32, i32, i32, vp, ctypes.c_int, vp]
     lib.snsde_plan_status_nowait.argtypes = [vp]
     lib.snsde_initial_state.argtypes = [vp, i64, i32, i32, i32, i32, ctypes.c_float, vp, vp, i32, vp, ctypes.c_int, vp]
     lib.snsde_readout_head.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, ctypes.c_int, vp]

@@ -147,6 +147,102 @@ __global__ void __launch_bounds__(128) natural_coeffs_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Natural cubic spline WITH missing values: benchmark_classification/controldiffeq/interpolate.py:56-153
+// (`_natural_cubic_spline_coeffs_with_missing_values`).  The reference treats every scalar series on its own: an
+// all-NaN series gives zero coefficients; a NaN at either end is imputed with the nearest observation; the spline is
+// built on the OBSERVED knots only (their own irregular grid) and every original interval [t_i, t_{i+1}) receives the
+// piece it lies in, re-centred at t_i.  One thread per series: forward Thomas sweep over the observed knots (modified
+// diagonal and right-hand side parked in the b / two_c slots of the knot's own interval), backward sweep that turns each
+// observed interval into the coefficients of the original intervals it covers.
+__global__ void __launch_bounds__(128) natural_coeffs_missing_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                                     float* __restrict__ out, int B, int K, int C) {
+  const long long series = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (series >= (long long)B * C) return;
+  const int b = (int)(series / C), c = (int)(series - (long long)b * C);
+  const float* xs = x + (size_t)b * K * C + c;
+  float* os = out + (size_t)b * (K - 1) * 4 * C + c;
+  auto xat = [&](int i) { return xs[(size_t)i * C]; };
+  int first = -1, last = -1;
+  for (int i = 0; i < K; ++i) { const float v = xat(i); if (v == v) { if (first < 0) first = i; last = i; } }
+  if (first < 0) {                                         // nothing observed: constant zero path
+    for (int i = 0; i < K - 1; ++i) { float* o = os + (size_t)i * 4 * C; o[0] = 0.f; o[C] = 0.f; o[2 * C] = 0.f; o[3 * C] = 0.f; }
+    return;
+  }
+  const float x_first = xat(first), x_last = xat(last);
+  // value at knot i after imputing the two ends; "observed" = not NaN, or an end point
+  auto obs = [&](int i) { const float v = xat(i); return i == 0 || i == K - 1 || v == v; };
+  auto val = [&](int i) { const float v = xat(i); return (v == v) ? v : (i == 0 ? x_first : x_last); };
+  auto next_obs = [&](int i) { int j = i + 1; while (!obs(j)) ++j; return j; };      // i < K-1
+  auto prev_obs = [&](int i) { int j = i - 1; while (!obs(j)) --j; return j; };      // i > 0
+  // expands the piece (a, bb, c2, d3) anchored at observed knot j0 onto the original intervals [j0, j1)
+  auto expand = [&](int j0, int j1, float a, float bb, float c2, float d3) {
+    const float t0 = t[j0];
+    for (int i = j0; i < j1; ++i) {
+      const float off = t0 - t[i];
+      const float a_inner = (0.5f * c2 - d3 * off / 3.f) * off;
+      float* o = os + (size_t)i * 4 * C;
+      o[0] = a + (a_inner - bb) * off;
+      o[C] = bb + (d3 * off - c2) * off;
+      o[2 * C] = c2 - 2.f * d3 * off;
+      o[3 * C] = d3;
+    }
+  };
+  const int second = next_obs(0);
+  if (second == K - 1) {                                   // two observed knots: the straight line (interpolate.py:15-19)
+    const float x0 = val(0);
+    expand(0, K - 1, x0, (val(K - 1) - x0) / (t[K - 1] - t[0]), 0.f, 0.f);
+    return;
+  }
+  // ---- forward sweep over the observed knots j (previous observed p, next observed n) ----
+  //   diag_j = 2 (r_j + r_p) [ends: one term], rhs_j = 3 dx_j r_j^2 + 3 dx_p r_p^2, w = r_p / nd_p,
+  //   nd_j = diag_j - w r_p, nb_j = rhs_j - w nb_p            (oracle/spline.py, misc.py:52-64)
+  float nd_prev, nb_prev, r_prev, s_prev;
+  {
+    const float r0 = 1.f / (t[second] - t[0]);
+    const float s0 = 3.f * (val(second) - val(0)) * (r0 * r0);
+    nd_prev = 2.f * r0; nb_prev = s0; r_prev = r0; s_prev = s0;
+    os[C] = nb_prev; os[2 * C] = nd_prev;                  // parked at the knot's own interval (knot 0)
+  }
+  int j = second;
+  while (j < K - 1) {
+    const int n = next_obs(j);
+    const float rj = 1.f / (t[n] - t[j]);
+    const float sj = 3.f * (val(n) - val(j)) * (rj * rj);
+    const float w = r_prev / nd_prev;
+    const float nd = 2.f * (rj + r_prev) - w * r_prev;
+    const float nb = (sj + s_prev) - w * nb_prev;
+    os[(size_t)j * 4 * C + C] = nb; os[(size_t)j * 4 * C + 2 * C] = nd;
+    nd_prev = nd; nb_prev = nb; r_prev = rj; s_prev = sj;
+    j = n;
+  }
+  // last observed knot (index K-1): diag = 2 r_p, rhs = s_p
+  float k_next;
+  {
+    const float w = r_prev / nd_prev;
+    const float nd = 2.f * r_prev - w * r_prev;
+    const float nb = s_prev - w * nb_prev;
+    k_next = nb / nd;
+  }
+  // ---- backward sweep: k_j, then the piece on [j, n) ----
+  int n = K - 1;
+  j = prev_obs(K - 1);
+  for (;;) {
+    const float nb = os[(size_t)j * 4 * C + C], nd = os[(size_t)j * 4 * C + 2 * C];
+    const float rj = 1.f / (t[n] - t[j]);
+    const float kj = (nb - rj * k_next) / nd;
+    const float xj = val(j);
+    const float six_dx = 2.f * (3.f * (val(n) - xj));
+    const float two_c = (six_dx * rj - 4.f * kj - 2.f * k_next) * rj;
+    const float three_d = (-six_dx * rj + 3.f * (kj + k_next)) * (rj * rj);
+    expand(j, n, xj, kj, two_c, three_d);
+    k_next = kj;
+    if (j == 0) break;
+    n = j;
+    j = prev_obs(j);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Missing values (NaN) before the Hermite builder: torchcde fills them through linear_interpolation_coeffs -
 // linear in t between the observed neighbours, first observed value before the first, last observed value after
 // the last (forward fill); an all-NaN series stays NaN.  One thread per (row, channel) series, one forward scan.
@@ -219,6 +315,22 @@ extern "C" int snsde_natural_coeffs(const float* x_dev, const float* knots_dev, 
   snsde::natural_coeffs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(x_dev, r, cp, w, coeffs_dev, B, K, C);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "natural_coeffs launch: %s", cudaGetErrorString(e));
+  return SNSDE_OK;
+  SNSDE_API_END(SNSDE_ERR_INTERNAL)
+}
+
+extern "C" int snsde_natural_coeffs_missing(const float* x_dev, const float* knots_dev, int32_t B, int32_t K, int32_t C,
+                                            float* coeffs_dev, int device, void* stream_v) {
+  SNSDE_API_BEGIN
+  if (!x_dev || !knots_dev || !coeffs_dev) return fail(SNSDE_ERR_BAD_ARG, "natural_coeffs_missing: x/knots/coeffs is NULL");
+  if (B < 1 || K < 2 || C < 1) return fail(SNSDE_ERR_BAD_ARG, "natural_coeffs_missing: need B >= 1, K >= 2, C >= 1 (got B=%d K=%d C=%d)", B, K, C);
+  const long long n = (long long)B * C;
+  if (n > 0x7fffffffLL * 128LL) return fail(SNSDE_ERR_BAD_ARG, "natural_coeffs_missing: tensor too large");
+  snsde::DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return fail(SNSDE_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err));
+  snsde::natural_coeffs_missing_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream_v>>>(x_dev, knots_dev, coeffs_dev, B, K, C);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "natural_coeffs_missing launch: %s", cudaGetErrorString(e));
   return SNSDE_OK;
   SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }

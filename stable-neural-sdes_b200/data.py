@@ -81,14 +81,22 @@ def fill_missing_cuda(x, t):
     return out
 
 
-def natural_coeffs_cuda(x, t, out=None):
+def natural_coeffs_cuda(x, t, out=None, missing=False):
     """CUDA version of :func:`natural_cubic_coeffs` (bit-identical to that torch-op chain) for a NaN-free CUDA tensor
-    ``x [B, K, C]``: knot-only Thomas factors once, then one thread per (row, channel) series (``snsde_natural_coeffs``)."""
+    ``x [B, K, C]``: knot-only Thomas factors once, then one thread per (row, channel) series (``snsde_natural_coeffs``).
+    ``missing=True``: ``x`` may hold NaNs (missing observations); the reference's per-series missing-value branch
+    (controldiffeq/interpolate.py:56-153) runs on device (``snsde_natural_coeffs_missing``)."""
     from . import _lib
     x, t = _cuda_args(x, t, "natural_coeffs_cuda")
     B, K, C = x.shape
     if out is None:
         out = torch.empty((B, K - 1, 4 * C), device=x.device, dtype=torch.float32)
+    if missing:
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.load().snsde_natural_coeffs_missing(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(t.data_ptr()), B, K, C,
+                                                            ctypes.c_void_p(out.data_ptr()), x.device.index or 0,
+                                                            ctypes.c_void_p(stream)))
+        return out
     scratch = torch.empty(3 * K, device=x.device, dtype=torch.float32)
     stream = torch.cuda.current_stream(x.device).cuda_stream
     _lib.check(_lib.load().snsde_natural_coeffs(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(t.data_ptr()), B, K, C,

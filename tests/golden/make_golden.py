@@ -152,6 +152,14 @@ def spline_golden(cde):
                         torch.tensor([times[0] - 0.3, times[-1] + 0.3])])
         ev = torch.stack([sp.evaluate(t) for t in tq])
         out.append(dict(times=times, x=x, a=a, b=b, two_c=c2, three_d=d3, tq=tq, evaluate=ev))
+    # missing values (interpolate.py:56-153): NaNs inside, at either end, a whole series missing
+    for K, C, B in ((7, 3, 3), (12, 2, 2)):
+        times = torch.cat([torch.zeros(1), torch.rand(K - 1, generator=g) + 0.2]).cumsum(0)
+        x = torch.randn(B, K, C, generator=g)
+        x[torch.rand(B, K, C, generator=g) < 0.35] = float("nan")
+        x[0, 0, 0] = float("nan"); x[0, -1, 1] = float("nan"); x[1, :, 0] = float("nan"); x[1, 2, 1] = 0.5
+        a, b, c2, d3 = cde.natural_cubic_spline_coeffs(times, x)
+        out.append(dict(times=times, x=x, a=a, b=b, two_c=c2, three_d=d3, missing=True))
     torch.save(out, HERE / "spline_golden.pt")
     print("spline_golden.pt:", len(out), "cases")
 

@@ -576,3 +576,27 @@ def test_m_split_cta_pairs_agree_with_the_single_cta_kernel(dev, monkeypatch):
         close(a, want)
         close(b, want)
         close(a, b, rtol=2e-5)
+
+
+def test_natural_spline_with_missing_values_on_device_matches_the_reference_golden(golden_dir, dev):
+    """snsde_natural_coeffs_missing vs coefficients minted by the reference's in-tree builder (interpolate.py:56-153):
+    NaNs inside, at either end, a whole series missing; plus a larger random case against the pinned oracle."""
+    from snsde_b200 import data
+    cases = [c for c in torch.load(golden_dir / "spline_golden.pt") if c.get("missing")]
+    assert len(cases) == 2
+    for c in cases:
+        want = torch.cat([c["a"], c["b"], c["two_c"], c["three_d"]], dim=-1)
+        got = data.natural_coeffs_cuda(c["x"].to(dev), c["times"].to(dev), missing=True)
+        close(got, want, rtol=2e-5)
+    g = torch.Generator().manual_seed(9)
+    B, K, C = 33, 40, 5
+    times = torch.cat([torch.zeros(1), torch.rand(K - 1, generator=g) + 0.1]).cumsum(0)
+    x = torch.randn(B, K, C, generator=g).cumsum(1)
+    x[torch.rand(B, K, C, generator=g) < 0.4] = float("nan")
+    x[3, :, 2] = float("nan")
+    want = torch.cat(spline.natural_cubic_spline_coeffs(times, x), dim=-1)
+    got = data.natural_coeffs_cuda(x.to(dev), times.to(dev), missing=True)
+    close(got, want, rtol=5e-5)
+    full = torch.randn(4, 9, 3, generator=g)                     # no NaN: the missing-value kernel equals the plain builder
+    close(data.natural_coeffs_cuda(full.to(dev), times[:9].to(dev), missing=True),
+          torch.cat(spline.natural_cubic_spline_coeffs(times[:9], full), dim=-1), rtol=2e-5)

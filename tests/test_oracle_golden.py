@@ -52,6 +52,8 @@ def test_natural_spline_matches_in_tree_controldiffeq(golden_dir):
         a, b, c2, d3 = spline.natural_cubic_spline_coeffs(c["times"], c["x"])
         for own, ref in ((a, c["a"]), (b, c["b"]), (c2, c["two_c"]), (d3, c["three_d"])):
             assert torch.allclose(own, ref, atol=1e-5, rtol=1e-5)
+        if c.get("missing"):                   # missing-value branch: coefficients only
+            continue
         sp = spline.CubicSpline(torch.cat([c["a"], c["b"], c["two_c"], c["three_d"]], -1), c["times"])
         ev = torch.stack([sp.evaluate(t) for t in c["tq"]])
         assert torch.allclose(ev, c["evaluate"], **TOL)
