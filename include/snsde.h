@@ -43,7 +43,12 @@ typedef enum {
 } snsde_status;
 
 enum { SNSDE_FAMILY_BENCHMARK = 0,   /* Diffusion_model, neuralsde.py:123-307                        */
-       SNSDE_FAMILY_TUTORIAL_LSDE = 1 /* NeuralLSDEFunc, tutorial "Neural LSDE" notebook cell 7      */ };
+       SNSDE_FAMILY_TUTORIAL_LSDE = 1, /* NeuralLSDEFunc, tutorial "Neural LSDE" notebook cell 7     */
+       SNSDE_FAMILY_LATENT_SDE = 2   /* LatentSDE augmented system f_aug/g_aug (posterior drift + KL path
+                                        accumulator), torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:29-93,
+                                        solved by sdeint_adjoint(..., names={'drift':'f_aug','diffusion':'g_aug'})
+                                        at :134-141.  hidden = hidden_channels = latent width + 1 (the last state
+                                        channel accumulates 0.5*|u|^2, u = (f - theta(mu - y)) / sigma)            */ };
 enum { SNSDE_METHOD_EULER = 0,       /* torchsde Euler.step (Ito)                                     */
        SNSDE_METHOD_MILSTEIN = 1,    /* torchsde Milstein.step (Ito, diagonal, derivative-based)      */
        SNSDE_METHOD_SRK = 2          /* torchsde SRK.diagonal_or_scalar_step (SRID2 tableau, strong
@@ -56,8 +61,8 @@ enum { SNSDE_PRECISION_FP32 = 0,     /* fp32 FMA kernel, every model/shape      
  * (neuralsde.py:124) plus the `method=` kwarg of sdeint (neuralsde.py:35-36). */
 typedef struct {
   int32_t family;           /* SNSDE_FAMILY_*                                        */
-  int32_t input_option;     /* 0..6   (neuralsde.py:148-156,200-225); 0 for tutorial */
-  int32_t noise_option;     /* 0..19  (neuralsde.py:233-288);        0 for tutorial  */
+  int32_t input_option;     /* 0..6   (neuralsde.py:148-156,200-225); 0 for tutorial / latent */
+  int32_t noise_option;     /* 0..19  (neuralsde.py:233-288);        0 for tutorial / latent  */
   int32_t input_channels;   /* C                                                     */
   int32_t hidden;           /* H  = hidden_channels                                  */
   int32_t hidden_hidden;    /* HH = hidden_hidden_channels                           */
@@ -111,6 +116,8 @@ const char* snsde_last_error(void);
  *   benchmark: initial_network, linear_in, [emb], linears.0..L-2, linear_out, theta(1),
  *              [sigma(1) | sigma_diag(H)], [noise_t | noise_t.0, noise_t.2 | noise_y | noise_y.0, noise_y.2]
  *   tutorial : linear_X, emb, f_net._model.{0,2,..}, linear_out, noise_in, g_net._model.{0,2,..}
+ *   latent   : linear_in [HH, H+1], linears.0..L-2, linear_out [H-1, HH], then the three buffers theta(1), mu(1),
+ *              sigma(1) of the prior (latent_sde.py:35-37; not parameters: their gradient slots stay zero)
  * Returns a negative status for an invalid descriptor. */
 int64_t snsde_weight_count(const snsde_model_desc* desc);
 

@@ -13,6 +13,8 @@ reference hot path ``torchsde.sdeint(Diffusion_model, ...)``:
 * ``oracle.solver``       - torchsde 0.2.5 fixed-step ``integrate`` + ``Euler.step`` +
                             diagonal Ito ``Milstein.step`` + explicit-increment
                             Brownian source.
+* ``oracle.latent``       - the LatentSDE augmented system ``f_aug``/``g_aug`` and its forward
+                            (reference torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:24-147).
 * ``oracle.philox``       - numpy replica of the Philox4x32-10 counter RNG bits.
 * ``oracle.wrapper``      - ``NeuralSDE.forward`` output-time selection / gather
                             (reference neuralsde.py:84-120) on top of the oracle solver.
@@ -30,6 +32,8 @@ PARITY PINNING STATUS
   absent torchsde/torchcde/controldiffeq imports) and freezes its f/g outputs for
   all 140 option pairs under a seeded init into ``tests/golden/fg_golden.pt``;
   ``tests/test_oracle_golden.py`` checks this oracle against them.
+* ``LatentSDE.f_aug/g_aug`` and ``LatentSDE.forward`` (given the oracle solver): PINNED the same way
+  (``latent_golden.pt``, minted from the reference's own class).
 * natural cubic spline coefficients + evaluate: PINNED against the reference's
   in-tree ``controldiffeq.interpolate`` (same script, ``spline_golden.pt``).
 * torchsde 0.2.5 (``integrate``/``Euler``/``Milstein``/``linear_interp``) and

@@ -70,7 +70,11 @@ def milstein_step(sde, bm, t0, t1, y0):
     with torch.enable_grad():
         yr = y0.detach().requires_grad_(True)
         g = sde.g(t0, yr)
-        (gdg,) = torch.autograd.grad(g, yr, grad_outputs=g.detach() * v, allow_unused=True)
+        # torchsde misc.vjp: an output outside the graph (a g built from buffers only, e.g. LatentSDE.g_aug) is made a
+        # leaf first, so the vjp is "unused" -> zeros, not an error
+        gdg = None
+        if g.requires_grad:
+            (gdg,) = torch.autograd.grad(g, yr, grad_outputs=g.detach() * v, allow_unused=True)
     if gdg is None:
         gdg = torch.zeros_like(y0)
     return y0 + f * dt + g_prod + 0.5 * gdg
@@ -136,16 +140,27 @@ def step_times(ts, dt):
     return out
 
 
-def sdeint_with_grad(sde, y0, ts, dt, bm, method="euler", options=None, **unused):
+class _Renamed:
+    """torchsde's ``names={'drift': ..., 'diffusion': ...}`` (``sdeint`` wraps the SDE so that ``f``/``g`` resolve to the
+    named methods; used by the reference at torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:139)."""
+
+    def __init__(self, sde, names):
+        self.f = getattr(sde, names.get("drift", "f"))
+        self.g = getattr(sde, names.get("diffusion", "g"))
+        self.noise_type = getattr(sde, "noise_type", "diagonal")
+        self.sde_type = getattr(sde, "sde_type", "ito")
+
+
+def sdeint_with_grad(sde, y0, ts, dt, bm, method="euler", options=None, names=None, **unused):
     """``sdeint`` with autograd left on: what the reference does when it trains through ``torchsde.sdeint``
     (benchmark_classification/common_sde.py:156-162) - the oracle for the engine's backward pass."""
-    return _integrate(sde, y0, ts, dt, bm, method)
+    return _integrate(_Renamed(sde, names) if names else sde, y0, ts, dt, bm, method)
 
 
 @torch.no_grad()
-def sdeint(sde, y0, ts, dt, bm, method="euler", options=None, **unused):
+def sdeint(sde, y0, ts, dt, bm, method="euler", options=None, names=None, **unused):
     """Returns ``[len(ts), B, H]`` like ``torchsde.sdeint``.  ``bm`` is mandatory here."""
-    return _integrate(sde, y0, ts, dt, bm, method)
+    return _integrate(_Renamed(sde, names) if names else sde, y0, ts, dt, bm, method)
 
 
 def _integrate(sde, y0, ts, dt, bm, method):

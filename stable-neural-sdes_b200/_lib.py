@@ -8,7 +8,7 @@ LIB_PATH = HERE / ("libsnsde_trace.so" if os.environ.get("SNSDE_TRACE_BUILD") el
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_WEIGHTS, ERR_INTERNAL = 0, -1, -2, -3, -4, -5
 ABI_VERSION = 2
-FAMILY_BENCHMARK, FAMILY_TUTORIAL_LSDE = 0, 1
+FAMILY_BENCHMARK, FAMILY_TUTORIAL_LSDE, FAMILY_LATENT_SDE = 0, 1, 2
 METHOD = {"euler": 0, "milstein": 1, "srk": 2}
 PRECISION = {"fp32": 0, "tc": 1, "auto": 2}
 

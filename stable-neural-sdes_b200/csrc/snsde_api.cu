@@ -78,8 +78,10 @@ static bool uses_control(int io) { return io == 0 || is_emb_opt(io); }
 
 static int validate(const snsde_model_desc* d) {
   if (!d) return fail(SNSDE_ERR_BAD_ARG, "desc is NULL");
-  if (d->family != SNSDE_FAMILY_BENCHMARK && d->family != SNSDE_FAMILY_TUTORIAL_LSDE)
+  if (d->family != SNSDE_FAMILY_BENCHMARK && d->family != SNSDE_FAMILY_TUTORIAL_LSDE && d->family != SNSDE_FAMILY_LATENT_SDE)
     return fail(SNSDE_ERR_BAD_ARG, "unknown family %d", d->family);
+  if (d->family == SNSDE_FAMILY_LATENT_SDE && d->hidden < 2)
+    return fail(SNSDE_ERR_BAD_ARG, "LatentSDE needs hidden >= 2 (latent width hidden-1 plus the KL accumulator channel)");
   if (d->input_channels < 1 || d->hidden < 1 || d->hidden_hidden < 1 || d->num_hidden_layers < 1)
     return fail(SNSDE_ERR_BAD_ARG, "C/H/HH/L must be >= 1");
   if (std::max(d->hidden, d->hidden_hidden) > 1024)
@@ -94,7 +96,7 @@ static int validate(const snsde_model_desc* d) {
     if ((d->input_option == 0 || is_emb_opt(d->input_option)) && d->hidden != d->hidden_hidden)
       return fail(SNSDE_ERR_BAD_ARG, "input_option %d requires hidden_hidden == hidden (emb is Linear(2H,H), neuralsde.py:154,210)", d->input_option);
   }
-  const int n_ops = d->family == SNSDE_FAMILY_BENCHMARK ? 6 + d->num_hidden_layers : 6 + 2 * d->num_hidden_layers;
+  const int n_ops = d->family == SNSDE_FAMILY_TUTORIAL_LSDE ? 6 + 2 * d->num_hidden_layers : 6 + d->num_hidden_layers;
   if (n_ops > kMaxOps) return fail(SNSDE_ERR_UNSUPPORTED, "num_hidden_layers too large");
   return SNSDE_OK;
 }
@@ -116,6 +118,11 @@ static int64_t weight_count(const snsde_model_desc* d) {
     if (no == 14 || no == 15) n += H * (H + 2) + H;
     if (no == 16 || no == 17) n += H * 2 + H + H * H + H;
     if (no == 18 || no == 19) n += H * (H + 2) + H + H * H + H;
+  } else if (d->family == SNSDE_FAMILY_LATENT_SDE) {
+    n += HH * (H + 1) + HH;                    // linear_in: Linear(hidden+2-1, HH)     latent_sde.py:48
+    n += (L - 1) * (HH * HH + HH);             // linears                               :49-50
+    n += (H - 1) * HH + (H - 1);               // linear_out: Linear(HH, hidden-1)      :51
+    n += 3;                                    // theta, mu, sigma buffers              :35-37
   } else {
     const int64_t mlp = (HH * H + HH) + (L - 1) * (HH * HH + HH) + (H * HH + H);
     n += H * C + H;            // linear_X
@@ -346,6 +353,46 @@ static void compile_tutorial(const snsde_model_desc& d, const float* blob, Progr
   t.bounded = 0; t.clip_drift = 0; t.geometric = 0; t.s_theta = 1.f;
   t.milstein = d.method == SNSDE_METHOD_MILSTEIN;
   t.g_theta = -1; t.g_sigma = -1; t.coef_op = -1;
+}
+
+// LatentSDE.f_aug / g_aug (torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:57-90): the posterior drift is an MLP
+// on (sin t, cos t, y[:, :-1]) with relu between layers and NO clip; the KL channel and the masked constant diffusion are
+// tail work (TailOp::latent).
+static void compile_latent(const snsde_model_desc& d, const float* blob, Program& pg, ImageBuilder& ib) {
+  const int H = d.hidden, HH = d.hidden_hidden, L = d.num_hidden_layers, Hl = H - 1;
+  BlobCursor bc(blob);
+  memset(&pg, 0, sizeof(pg));
+  pg.C = d.input_channels; pg.H = H; pg.HH = HH;
+  pg.ld = (std::max(H, HH) + 3) & ~3;
+  pg.uses_control = 0;
+  ProgramBuilder pb(pg, bc);
+  const float* Win = bc.take((size_t)HH * (Hl + 2)); const float* bin = bc.take(HH);
+  DenseOp o = make_op(BUF_A, BUF_Y, Hl, HH, ib.add_T(Win, HH, Hl + 2, 2, Hl), ib.add_vec(bin, HH), ACT_RELU);
+  o.tmode = TM_SINCOS; o.tw_off = ib.add_T(Win, HH, Hl + 2, 0, 2);
+  pb.push(o, 0, Win, Hl + 2, 2, 0, bin);
+  int cur = BUF_A;
+  for (int l = 0; l < L - 1; ++l) {
+    const float* W = bc.take((size_t)HH * HH); const float* b = bc.take(HH);
+    const int dst = (cur == BUF_A) ? BUF_B : BUF_A;
+    pb.push(make_op(dst, cur, HH, HH, ib.add_T(W, HH, HH, 0, HH), ib.add_vec(b, HH), ACT_RELU), 0, W, HH, 0, 0, b);
+    cur = dst;
+  }
+  const float* Wo = bc.take((size_t)Hl * HH); const float* bo = bc.take(Hl);
+  DenseOp fo = make_op(BUF_NONE, cur, HH, Hl, ib.add_T(Wo, Hl, HH, 0, HH), ib.add_vec(bo, Hl), ACT_NONE);
+  fo.final_drift = 1;
+  pb.push(fo, 0, Wo, HH, 0, 0, bo);
+  pg.n_ops = pb.n;
+  const float theta = *bc.take(1), mu = *bc.take(1), sigma = *bc.take(1);
+  TailOp& t = pg.tail;
+  memset(&t, 0, sizeof(t));
+  t.coef_src = CO_SCALAR; t.coef_scalar = sigma; t.mult = MU_ONE; t.special = SP_NONE;
+  t.bounded = 0; t.clip_drift = 0; t.geometric = 0; t.s_theta = 1.f;
+  t.milstein = d.method == SNSDE_METHOD_MILSTEIN;
+  t.g_theta = -1; t.g_sigma = -1; t.coef_op = -1;
+  t.latent = 1; t.lat_theta = theta; t.lat_mu = mu;
+  // _stable_division(a, b, eps=1e-7): b = where(|b| > eps, b, eps * sign(b))        latent_sde.py:24-26
+  const float eps = 1e-7f;
+  t.lat_div = fabsf(sigma) > eps ? sigma : eps * (sigma > 0.f ? 1.f : (sigma < 0.f ? -1.f : 0.f));
 }
 
 // ---- Philox materialisation kernel -------------------------------------------------------------
@@ -591,6 +638,7 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
   }
   ImageBuilder ib;
   if (p->desc.family == SNSDE_FAMILY_BENCHMARK) compile_benchmark(p->desc, blob, p->prog, ib);
+  else if (p->desc.family == SNSDE_FAMILY_LATENT_SDE) compile_latent(p->desc, blob, p->prog, ib);
   else compile_tutorial(p->desc, blob, p->prog, ib);
   ib.pad4();
   if ((int)ib.img.size() > p->wimg_floats) {

@@ -178,7 +178,30 @@ __global__ void __launch_bounds__(NTMAX) snsde_bwd_kernel(const BwdParams p) {
     // ---- 3. the SDE update, differentiated ----
     float a_y[R];
     float gv_sum = 0.f;
-    if (jact) {
+    if (t.latent) {
+      // LatentSDE.f_aug (latent_sde.py:77-82): y_kl' = y_kl + h * 0.5 sum_j u_j^2, u_j = (f_j - theta (mu - y_j)) / div.
+      // lambda of the KL channel reaches every latent feature: broadcast it through sD (idle since the previous
+      // step's reverse ops, which are behind the hand-offs of the re-evaluation above).
+      if (tid == H - 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) sD[r * ld] = lam[r];
+      }
+      gsync();
+      if (jact) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                               // g_aug is constant: the noise term has no cotangent
+          float a_f = 0.f, ay = lam[r];
+          if (tid < H - 1) {
+            const float lk = sD[r * ld] * st.h;
+            const float u = __fdiv_rn(acc[r] - t.lat_theta * (t.lat_mu - y[r]), t.lat_div);
+            a_f = lam[r] * st.h + lk * __fdiv_rn(u, t.lat_div);
+            ay += lk * u * __fdiv_rn(t.lat_theta, t.lat_div);
+          }
+          a_y[r] = ay;
+          sCot[final_i * slot + r * ld + tid] = a_f;
+        }
+      }
+    } else if (jact) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const float d = acc[r];

@@ -61,6 +61,10 @@ struct TailOp {
   int vjp_h1;         // buffer holding relu(noise_y.0(...)) (kind 2)
   // backward pass: blob offsets of theta / sigma / sigma_diag (-1: absent) and the op producing a CO_RBUF coefficient
   int g_theta, g_sigma, coef_op;
+  // LatentSDE augmented system (latent_sde.py:77-90): features 0..H-2 carry the posterior drift f and the constant
+  // diffusion sigma; feature H-1 has drift 0.5 * sum_j u_j^2 with u = (f - theta (mu - y)) / stable(sigma) and no noise.
+  int latent;
+  float lat_theta, lat_mu, lat_div;   // prior drift theta (mu - y); lat_div = the _stable_division denominator (:24-26)
 };
 
 struct Program {

@@ -194,6 +194,41 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
     if (t.clip_drift) d = tanhf(d);
     return d;
   };
+  // LatentSDE.f_aug (latent_sde.py:77-82): the drift of the last state channel is 0.5 * sum_j u_j^2 over the latent
+  // features, u = (f - theta (mu - y)) / stable(sigma), evaluated at the state the dense program just read (sY).
+  // Whole-group call (shuffles + at most two hand-offs); the partial sums of the warps meet in the BUF_U rows.
+  auto latent_drift = [&](float (&f)[R]) {
+    if (!t.latent) return;
+    float part[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float u = 0.f;
+      if (tid < H - 1) u = __fdiv_rn(f[r] - t.lat_theta * (t.lat_mu - sY[r * ld + tid]), t.lat_div);
+      part[r] = u * u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
+    }
+    if (nw > 1) {
+      float* const red = sm.buf(BUF_U);                        // (its previous readers are behind the dense program's hand-offs)
+      if ((tid & 31) == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) red[r * ld + (tid >> 5)] = part[r];
+      }
+      gsync();
+      if (tid == H - 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float v = 0.f;
+          for (int q = 0; q < nw; ++q) v += red[r * ld + q];
+          part[r] = v;
+        }
+      }
+    }
+    if (tid == H - 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) f[r] = 0.5f * part[r];
+    }
+  };
   // coefficient entering the elementwise diffusion for row r (table / image / scalar / per-row network output)
   auto coef_of = [&](int r, float vcoef) {
     return t.coef_src == CO_RBUF ? sm.buf(t.coef_ref)[r * ld + tid] : vcoef;
@@ -202,6 +237,7 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
     float v = t.coef_scalar;
     if (t.coef_src == CO_IMG) v = W[t.coef_ref + tid];
     else if (t.coef_src == CO_VBUF) v = p.vtab[((size_t)s * NPG + q) * H + tid];
+    if (t.latent && tid == H - 1) v = 0.f;                    // g_aug: no noise on the KL accumulator (latent_sde.py:84-90)
     return v;
   };
   // Brownian increment (and, for SRK, the space-time Levy integral U) of row r at step s
@@ -243,6 +279,7 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
         prefetch_spline(s + 1);
       }
       run_ops(2, tp);
+      latent_drift(acc);
 
       const bool net_vjp = t.milstein && t.vjp_kind != 0;       // block-uniform
       float* const sA = sm.buf(BUF_X);                            // scratch of the vjp (dead since the first ops)
@@ -322,6 +359,7 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
       if (pg.uses_control) { cp_async_wait_all(); gsync(); eval_control(s, 0, pts[0].frac); }
       // stage 0: f0 = f(t0, y0), g0 = g(t0, y0)            (sY holds y0)
       run_ops(2, tp0);
+      latent_drift(acc);
       if (jact) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -344,6 +382,7 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
       }
       if (pg.uses_control) { gsync(); eval_control(s, 1, pts[3].frac); }
       run_ops(0, tp1);                                       // f1 = f(t0 + h, H0_1)
+      latent_drift(acc);
       if (jact) {
 #pragma unroll
         for (int r = 0; r < R; ++r) f1[r] = drift_value(acc[r], sY[r * ld + tid]);
@@ -373,6 +412,7 @@ __global__ void __launch_bounds__(NTMAX) snsde_fma_kernel(const FmaParams p) {
       }
       if (pg.uses_control) { gsync(); eval_control(s, 2, pts[2].frac); prefetch_spline(s + 1); }
       run_ops(0, tph);                                       // f2 = f(t0 + h/2, H0_2)
+      latent_drift(acc);
       if (jact) {
 #pragma unroll
         for (int r = 0; r < R; ++r) f2[r] = drift_value(acc[r], sY[r * ld + tid]);

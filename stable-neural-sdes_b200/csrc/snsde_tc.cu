@@ -803,7 +803,7 @@ static int tc_env_chains() { const char* e = getenv("SNSDE_TC_CH"); return (e &&
 bool tc_supported(const snsde_model_desc& d, int cc_major, int smem_optin) {
   const int no = d.noise_option, io = d.input_option;
   if (cc_major != 10) { g_reason = "needs an sm_100 device"; return false; }
-  if (d.family != SNSDE_FAMILY_BENCHMARK) { g_reason = "tutorial family runs on the FMA kernel"; return false; }
+  if (d.family != SNSDE_FAMILY_BENCHMARK) { g_reason = "the tutorial and LatentSDE families run on the FMA kernel"; return false; }
   if (io == 0) { g_reason = "input_option 0 (control only) runs on the FMA kernel"; return false; }
   if (no == 14 || no == 15 || no == 18 || no == 19) { g_reason = "state-network noise options run on the FMA kernel"; return false; }
   if (d.hidden != d.hidden_hidden) { g_reason = "needs hidden_hidden == hidden"; return false; }

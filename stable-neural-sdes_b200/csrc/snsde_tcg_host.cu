@@ -29,7 +29,7 @@ bool tcg_supported(const snsde_model_desc& d, int cc_major, int smem_optin) {
   (void)smem_optin;
   const int io = d.input_option, no = d.noise_option, H = d.hidden;
   if (cc_major != 10) { g_greason = "needs an sm_100 device"; return false; }
-  if (d.family != SNSDE_FAMILY_BENCHMARK) { g_greason = "tutorial family runs on the FMA kernel"; return false; }
+  if (d.family != SNSDE_FAMILY_BENCHMARK) { g_greason = "the tutorial and LatentSDE families run on the FMA kernel"; return false; }
   if (io == 0) { g_greason = "input_option 0 (control only) runs on the FMA kernel"; return false; }
   if (d.hidden != d.hidden_hidden) { g_greason = "needs hidden_hidden == hidden"; return false; }
   if (H % 32 || H < 32 || H > 256) { g_greason = "needs hidden in {32,64,...,256}"; return false; }

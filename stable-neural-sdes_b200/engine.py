@@ -10,7 +10,9 @@ the reference's three wrappers at the ``_solve_sde_path`` seam:
 * ``NeuralSDE_forecasting`` (benchmark_forecasting/models_sde/neuralsde.py:123-186): ``forward``
   streams only the last ``output_time`` knots the head reads (:184-185);
 * torch-ists ``NeuralSDE`` (torch-ists/torch_ists/diff_module/NSDE/nsde_model.py:45-84): only
-  ``_solve_sde_path`` (signature ``(times, y0, kwargs)``, default method ``'srk'``) is replaced.
+  ``_solve_sde_path`` (signature ``(times, y0, kwargs)``, default method ``'srk'``) is replaced;
+* torch-ists ``LatentSDE`` (torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:29-147): ``forward``
+  (which calls ``torchsde.sdeint_adjoint`` on the augmented system inline) is replaced.
 
 Training: under autograd the solve saves every solver state and the backward pass runs the
 reverse-sweep kernel behind ``snsde_backward`` (the reference back-propagates through
@@ -106,7 +108,10 @@ class Plan:
 
     @property
     def uses_control(self):
-        return self.desc["family"] == _lib.FAMILY_TUTORIAL_LSDE or self.desc["input_option"] in (0, 2, 4, 6)
+        fam = self.desc["family"]
+        if fam == _lib.FAMILY_LATENT_SDE:
+            return False
+        return fam == _lib.FAMILY_TUTORIAL_LSDE or self.desc["input_option"] in (0, 2, 4, 6)
 
     @property
     def kernel(self):
@@ -353,7 +358,7 @@ def _states_with_grad(sde, plan, sp, y0, dW, seed, row_offset):
     if plan.method != "euler":
         raise RuntimeError(f"snsde: the backward pass is implemented for method='euler' (the reference's training "
                            f"default, neuralsde.py:75), not {plan.method!r}; call under torch.no_grad() for inference")
-    keys = packing.blob_keys(plan.desc)
+    keys = packing.grad_keys(plan.desc)
     named = dict(sde.named_parameters())
     missing = [k for k in keys if k not in named]
     if missing:
@@ -417,12 +422,16 @@ def _solve(sde, plan, sp, y0, row_slot, bm, seed, row_offset, out, check_range):
     return res
 
 
+_LATENT_NAMES = {"drift": "f_aug", "diffusion": "g_aug"}
+
+
 def sdeint(sde, y0, ts, dt=1e-3, method=None, options=None, bm=None, seed=None, precision="auto",
            row_offset=0, names=None, out=None, check_range=False, **unused_kwargs):
     """Drop-in for ``torchsde.sdeint(sde, y0, ts, dt=..., method=...)`` on this path.
 
     ``sde`` is a reference ``Diffusion_model`` (or the tutorial ``NeuralLSDEFunc``) on which
-    ``set_X(coeffs, times)`` has been called; the engine reads ``sde.coeffs``, ``sde.times`` and the
+    ``set_X(coeffs, times)`` has been called, or a ``LatentSDE`` (latent_sde.py:29) with
+    ``names={'drift': 'f_aug', 'diffusion': 'g_aug'}`` and the augmented ``y0 [B, hidden]``; the engine reads ``sde.coeffs``, ``sde.times`` and the
     parameters and never calls Python ``f``/``g``.  ``method``: ``'euler'`` (default), ``'milstein'``,
     ``'srk'``.  ``options`` is accepted and ignored, as torchsde's fixed-step solvers ignore ``options['dt']``
     (neuralsde.py:39-46).  ``bm=None`` draws increments in-kernel (Philox, ``seed``);
@@ -433,11 +442,15 @@ def sdeint(sde, y0, ts, dt=1e-3, method=None, options=None, bm=None, seed=None, 
     """
     if unused_kwargs:
         warnings.warn(f"Unexpected arguments {sorted(unused_kwargs)}")          # torchsde does the same
-    if names is not None:
-        raise ValueError("snsde: `names` remapping is not supported")
     method = "euler" if method is None else method
     _check_sde(sde)
     plan = _plan_for(sde, method, precision, y0.device)
+    if plan.desc["family"] == _lib.FAMILY_LATENT_SDE:
+        # the engine integrates the augmented system the reference selects with `names` (latent_sde.py:134-141)
+        if names is None or dict(names) != _LATENT_NAMES:
+            raise ValueError(f"snsde: a LatentSDE is solved as its augmented system; pass names={_LATENT_NAMES}")
+    elif names is not None:
+        raise ValueError("snsde: `names` remapping is only supported for LatentSDE's f_aug / g_aug")
     sp = plan.step_plan(ts, dt, getattr(sde, "times", None))
     return _solve(sde, plan, sp, y0, None, bm, seed, row_offset, out, check_range)
 
@@ -643,14 +656,56 @@ def _forward_forecasting(self, times, coeffs, final_index, z0=None, stream=False
     return _head_of(self, z_t.transpose(0, 1), fused)
 
 
+def _control_at(coeffs, times, t):
+    """``CubicSpline(coeffs, times).evaluate(t)`` in torch ops (autograd-visible; used outside the fused eval path)."""
+    C = coeffs.shape[-1] // 4
+    idx = int((torch.bucketize(t.detach(), times.detach()) - 1).clamp(0, len(times) - 2))
+    a, b, two_c, three_d = coeffs[:, idx].split(C, dim=-1)
+    frac = t - times[idx]
+    inner = 0.5 * two_c + three_d * frac / 3
+    inner = b + inner * frac
+    return a + inner * frac
+
+
+def _forward_latent(self, coeffs, times, **kwargs):
+    """``LatentSDE.forward`` (torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:92-147): the augmented system
+    (posterior drift + KL path accumulator) is one engine solve; returns ``(embedding(latent), latent, logqp)``.
+    Default method ``'srk'`` (:107-109); ``adjoint_method`` / ``options`` are accepted and ignored (fixed-step solve;
+    gradients come from the engine's own reverse sweep, method ``'euler'``)."""
+    coeffs = _cat_coeffs(coeffs)
+    eng = {k: kwargs.pop(k) for k in _ENGINE_KW if k in kwargs}
+    method = kwargs.pop("method", None) or "srk"
+    kwargs.pop("adjoint_method", None)
+    kwargs.pop("options", None)
+    net = self.initial_network
+    lin = net[0] if isinstance(net, torch.nn.Sequential) and len(net) == 1 else net
+    if _neighbours_fusable(self, None) and isinstance(lin, torch.nn.Linear) and coeffs.is_cuda:
+        lat0 = initial_state(lin, coeffs, times)                              # initial_network(X(times[0]))  :100-101,131
+    else:
+        lat0 = net(_control_at(coeffs, times, times[0]))
+    aug_y0 = torch.cat([lat0, torch.zeros(lat0.shape[0], 1).to(lat0)], dim=1)  # :132
+    qy0 = torch.distributions.Normal(loc=self.qy0_mean, scale=self.qy0_std)
+    py0 = torch.distributions.Normal(loc=self.py0_mean, scale=self.py0_std)
+    logqp0 = torch.distributions.kl_divergence(qy0, py0).sum(dim=1)           # KL(t=0)  :103-105
+    aug_ys = sdeint(self, aug_y0, times, dt=stepplan.solver_dt(_host_array(times)), method=method,
+                    names=_LATENT_NAMES, **eng, **kwargs)
+    aug_ys = aug_ys.permute(1, 0, 2)
+    latent = aug_ys[:, :, :-1]
+    logqp = (logqp0 + aug_ys[:, -1, -1]).mean(dim=0)                          # KL(t=0) + KL(path)  :144-145
+    return self.embedding(latent), latent, logqp
+
+
 # pickling a bound method stores (getattr, (instance, __name__)): name the replacements after the attributes they fill
 # so that torch.save(model) works (the loaded copy comes back with the class's own methods: patch() it again)
 _solve_sde_path_benchmark.__name__ = _solve_sde_path_torch_ists.__name__ = "_solve_sde_path"
-_forward_classification.__name__ = _forward_forecasting.__name__ = "forward"
+_forward_classification.__name__ = _forward_forecasting.__name__ = _forward_latent.__name__ = "forward"
 
 
 def wrapper_kind(model):
-    """Which of the reference's three wrappers ``model`` is, from its own ``forward`` signature."""
+    """Which of the reference's wrappers ``model`` is, from its own ``forward`` signature (``'latent_sde'``: the
+    LatentSDE module, which is its own wrapper)."""
+    if all(hasattr(model, a) for a in ("f_aug", "g_aug", "qy0_mean", "embedding")):
+        return "latent_sde"
     try:
         names = list(inspect.signature(type(model).forward).parameters)
     except (TypeError, ValueError):
@@ -669,13 +724,17 @@ def patch(model, fuse=True):
       ``(times, ts, z0, kwargs)``, default ``'euler'``; torch-ists signature ``(times, y0, kwargs)``, default ``'srk'``);
     * ``fuse`` and a classification ``NeuralSDE``: ``forward`` fuses the ``final_index`` gather;
     * ``fuse`` and ``NeuralSDE_forecasting``: ``forward`` writes only the last ``output_time`` knots;
-    * torch-ists ``NeuralSDE`` or an unrecognised wrapper: ``forward`` is left alone.
+    * torch-ists ``NeuralSDE`` or an unrecognised wrapper: ``forward`` is left alone;
+    * ``LatentSDE`` (it has no ``_solve_sde_path``: ``forward`` calls ``sdeint_adjoint`` inline): ``forward`` is replaced.
     The replacements are module-level functions bound to the instance, so ``copy.deepcopy`` and ``torch.save`` of a
     patched model work and a copy drives its own ``func``.
     """
-    if not hasattr(model, "func") or not hasattr(model, "_solve_sde_path"):
-        raise ValueError("snsde: patch() expects a NeuralSDE-style wrapper with `.func` and `._solve_sde_path`")
     kind = wrapper_kind(model)
+    if kind == "latent_sde":                # latent_sde.py:92-147 calls sdeint_adjoint inline: forward IS the seam
+        model.forward = types.MethodType(_forward_latent, model)
+        return model
+    if not hasattr(model, "func") or not hasattr(model, "_solve_sde_path"):
+        raise ValueError("snsde: patch() expects a NeuralSDE-style wrapper with `.func` and `._solve_sde_path`, or a LatentSDE")
     n_args = len(inspect.signature(type(model)._solve_sde_path).parameters)
     if n_args == 5:
         model._solve_sde_path = types.MethodType(_solve_sde_path_benchmark, model)

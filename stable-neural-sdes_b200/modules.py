@@ -7,6 +7,8 @@ stand-ins with identical parameter names, shapes, declaration order and default 
 (neuralsde.py:146-179; tutorial notebook cell 7) for benchmarks, serving and tests where the
 reference package is not importable.
 """
+import math
+
 import torch
 from torch import nn
 
@@ -75,3 +77,41 @@ class TutorialLSDEParams(_ControlMixin, nn.Module):
         self.linear_out = nn.Linear(hidden_dim, hidden_dim)
         self.noise_in = nn.Linear(1, hidden_dim)
         self.g_net = _MLPParams(hidden_dim, hidden_dim, hidden_hidden_dim, num_layers)
+
+
+class LatentSDEParams(nn.Module):
+    """Stand-in for the reference ``LatentSDE`` (torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:29-55): the
+    same parameters / buffers under the same names; ``hidden_channels`` counts the KL accumulator channel."""
+    sde_type = "ito"
+    noise_type = "diagonal"
+
+    def __init__(self, input_channels, hidden_channels, hidden_hidden_channels, num_hidden_layers,
+                 theta=1.0, mu=0.0, sigma=0.5):
+        super().__init__()
+        H, HH = hidden_channels, hidden_hidden_channels
+        logvar = math.log(sigma ** 2 / (2. * theta))
+        self.register_buffer("theta", torch.tensor([[theta]]))
+        self.register_buffer("mu", torch.tensor([[mu]]))
+        self.register_buffer("sigma", torch.tensor([[sigma]]))
+        self.register_buffer("py0_mean", torch.tensor([[mu]]))
+        self.register_buffer("py0_logvar", torch.tensor([[logvar]]))
+        self.initial_network = nn.Sequential(nn.Linear(input_channels, H - 1))
+        self.linear_in = nn.Linear(H + 2 - 1, HH)
+        self.linears = nn.ModuleList(nn.Linear(HH, HH) for _ in range(num_hidden_layers - 1))
+        self.linear_out = nn.Linear(HH, H - 1)
+        self.embedding = nn.Linear(H - 1, H)
+        self.qy0_mean = nn.Parameter(torch.tensor([[mu]]))
+        self.qy0_logvar = nn.Parameter(torch.tensor([[logvar]]))
+
+    @property
+    def py0_std(self):
+        return torch.exp(.5 * self.py0_logvar)
+
+    @property
+    def qy0_std(self):
+        return torch.exp(.5 * self.qy0_logvar)
+
+    def f_aug(self, t, y):
+        raise NotImplementedError("parameter container: the augmented drift is evaluated inside the CUDA engine")
+
+    g_aug = f_aug

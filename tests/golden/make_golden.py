@@ -22,7 +22,11 @@ What is real reference code here and what is shim:
   ``forward_golden.pt`` also holds the torch-ists wrapper (nsde_model.py, loaded by file path as the
   reference's own test does), whose default method is 'srk'.
 
-Outputs: fg_golden.pt, spline_golden.pt, forward_golden.pt (a few hundred KB in total).
+  ``latent_golden.pt`` holds the reference's own ``LatentSDE`` (latent_sde.py, loaded by file path; ``torchsde.SDEIto``
+  shimmed as an nn.Module base, ``sdeint_adjoint(..., names=...)`` provided by the oracle solver): f_aug / g_aug values
+  and full forward outputs ``(out, latent, logqp)``.
+
+Outputs: fg_golden.pt, spline_golden.pt, forward_golden.pt, latent_golden.pt (a few hundred KB in total).
 """
 import importlib
 import pathlib
@@ -47,8 +51,15 @@ def install_shims():
         ospline.hermite_cubic_coefficients_with_backward_differences)
     tsde = types.ModuleType("torchsde")
 
-    def sdeint(sde, y0, ts, dt, bm=None, method="euler", options=None, **kw):
-        return osolver.sdeint(sde, y0, ts, dt, bm, method=method, options=options)
+    def sdeint(sde, y0, ts, dt, bm=None, method="euler", options=None, names=None, **kw):
+        return osolver.sdeint(sde, y0, ts, dt, bm, method=method, options=options, names=names)
+
+    class SDEIto(torch.nn.Module):          # torchsde.SDEIto: an nn.Module carrying sde_type / noise_type
+        def __init__(self, noise_type):
+            super().__init__()
+            self.sde_type, self.noise_type = "ito", noise_type
+
+    tsde.SDEIto = SDEIto
 
     tsde.sdeint_adjoint = sdeint
 
@@ -89,6 +100,52 @@ def load_torch_ists_module():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_latent_module():
+    """The reference's LatentSDE, loaded by file path (the torch_ists package itself is not importable)."""
+    path = REF / "torch-ists" / "torch_ists" / "diff_module" / "NSDE" / "latent_sde.py"
+    spec = importlib.util.spec_from_file_location("ref_torch_ists_latent_sde", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def latent_golden(ref_l):
+    """LatentSDE (latent_sde.py:29-147): f_aug / g_aug at fixed (t, y) and the full forward on the oracle solver."""
+    out = []
+    with torch.no_grad():
+        for i, (C, H, HH, L, theta, mu, sigma) in enumerate(((3, 5, 6, 1, 1.0, 0.0, 0.5), (2, 9, 8, 3, 0.7, 0.2, 0.3),
+                                                              (4, 33, 40, 2, 1.3, -0.1, 0.8), (2, 4, 4, 1, 1.0, 0.1, 5e-8))):
+            torch.manual_seed(600 + i)
+            m = ref_l.LatentSDE(C, H, HH, L, theta=theta, mu=mu, sigma=sigma)
+            B = 4
+            y = torch.randn(B, H) * 0.8
+            tq = [torch.tensor(0.0), torch.tensor(0.37), torch.tensor(2.5)]
+            out.append(dict(kind="fg", dims=(C, H, HH, L), prior=(theta, mu, sigma),
+                            state_dict={k: v.clone() for k, v in m.state_dict().items()}, y=y, t=torch.stack(tq),
+                            f_aug=torch.stack([m.f_aug(t, y) for t in tq]),
+                            g_aug=torch.stack([m.g_aug(t, y) for t in tq])))
+        for i, (method, grid) in enumerate(((None, "linspace"), ("euler", "linspace"), ("euler", "arange"), ("srk", "arange"),
+                                            ("milstein", "linspace"))):
+            B, K, C, H, HH, L = 5, 9, 3, 8, 12, 2
+            torch.manual_seed(700 + i)
+            m = ref_l.LatentSDE(C, H, HH, L, theta=0.9, mu=0.1, sigma=0.4)
+            m.qy0_mean.data.fill_(0.3); m.qy0_logvar.data.fill_(-1.2)
+            times = torch.linspace(0, 1, K) if grid == "linspace" else torch.arange(K, dtype=torch.float32) * 0.25
+            x = torch.randn(B, K, C).cumsum(1) * 0.3
+            coeffs = ospline.hermite_cubic_coefficients_with_backward_differences(x, times)
+            steps = osolver.step_times(times, osolver.solver_dt(times))
+            h = torch.tensor([b - a for a, b in steps]).view(-1, 1, 1)
+            dW = torch.randn(len(steps), B, H) * h.sqrt()
+            dU = h * (dW / 2 + torch.randn(len(steps), B, H) * (h / 12).sqrt())
+            kw = {} if method is None else {"method": method}
+            pred, latent, logqp = m(coeffs, times, bm=osolver.BrownianTable(dW, dU=dU), **kw)
+            out.append(dict(kind="forward", method=method, dims=(B, K, C, H, HH, L), prior=(0.9, 0.1, 0.4), n_steps=len(steps),
+                            state_dict={k: v.clone() for k, v in m.state_dict().items()},
+                            times=times, coeffs=coeffs, dW=dW, dU=dU, pred=pred, latent=latent, logqp=logqp))
+    torch.save(out, HERE / "latent_golden.pt")
+    print("latent_golden.pt:", len(out), "cases")
 
 
 def make_inputs(seed, B, K, C, H):
@@ -262,9 +319,13 @@ def forward_golden(ref_c, ref_f, ref_t=None):
 
 if __name__ == "__main__":
     install_shims()
+    if "--only-latent" in sys.argv:         # the other fixtures are left untouched
+        latent_golden(load_latent_module())
+        sys.exit(0)
     ref_c, cde = load_reference_module(REF / "benchmark_classification")
     fg_golden(ref_c)
     spline_golden(cde)
     ref_f, _ = load_reference_module(REF / "benchmark_forecasting", real_cde=False)
     ref_c, _ = load_reference_module(REF / "benchmark_classification")
     forward_golden(ref_c, ref_f, load_torch_ists_module())
+    latent_golden(load_latent_module())
