@@ -686,29 +686,37 @@ def main():
     value = Bg * S * args.steps / (dev_ms * 1e-3)
     e2e_value = Bg * S * args.steps / e2e_s
 
-    # ---- the other BASELINE configs (c3 single GPU; c4 = B 4096 over 4 GPUs; c5 = B 8192 over 8 GPUs): device-resident
+    # ---- the other BASELINE configs (c1 tutorial, 64 rows; c3 single GPU; c4 = B 4096 over 4 GPUs; c5 = B 8192 over 8 GPUs): device-resident
     # value + roofline + parity, 1024 (c3: 2048) rows per GPU at whatever N this run has ----
     configs = {}
     if args.workload == "c2" and not args.no_configs and not args.rows and not args.solver_steps:
         del pinned, raw_pinned
-        for name in ("c3", "c4", "c5"):
+        for name in ("c1", "c3", "c4", "c5"):
             cw = dict(WORKLOADS[name])
             cwl = Workload(name, cw, args.precision, dev, rank, world)
             # long-horizon trajectories of these models are ill-conditioned in fp32 (tests/test_fullsize_gpu.py):
             # the gate attached to the measurement checks the full-batch launch over the first 24 solver steps
             cpar = parity_gate(cw, cwl.model, cwl.sets_host[0], cwl.sets_dev[0], cwl.plan, cwl.dt, dev, rank * cw["B"],
-                               args.precision, horizon=24) if rank == 0 else None
+                               args.precision, horizon=None if name == "c1" else 24) if rank == 0 else None
             c_dev_ms, c_kern_ms, c_launches, _ = time_resident(cwl, args.steps, args.warmup, barrier, max_over_ranks)
             if rank == 0:
                 nrows = 1 if cw["out"] == "final_index" else cwl.n_out
-                target_n = {"c3": 1, "c4": 4, "c5": 8}[name]
+                target_n = {"c1": 1, "c3": 1, "c4": 4, "c5": 8}[name]
                 configs[name] = {
                     "workload": cw["desc"], "value": cw["B"] * world * cw["S"] * args.steps / (c_dev_ms * 1e-3),
                     "unit": "SDE-steps/s", "global_rows": cw["B"] * world, "rows_per_gpu": cw["B"], "solver_steps": cw["S"],
                     "ms_per_step": c_dev_ms / args.steps, "kernel_ms": c_kern_ms, "kernel": cwl.plan.kernel,
+                    "fp32_variant": cwl.plan.variant,
                     "gpu_launches": c_launches, "host_step_plan_ms": cwl.host_plan_ms,
                     "baseline_config_n_gpus": target_n, "is_baseline_shape": world == target_n,
                     "roofline": roofline_block(name, cw, cwl.plan, c_kern_ms, nrows), "parity": cpar}
+                if name == "c1" and not args.no_cpu_baseline:      # BASELINE configs[0]: the reference's own CPU-runnable case
+                    aff = os.sched_getaffinity(0)
+                    os.sched_setaffinity(0, affinity0)
+                    v1, ts1 = time_cpu_reference(cw, cw["B"], budget_s=3.0)
+                    os.sched_setaffinity(0, aff)
+                    configs[name]["cpu_baseline"] = {"value": v1, "unit": "SDE-steps/s", "cores": os.cpu_count(), "kind": "port",
+                                                     "sample": f"median of {len(ts1)} full solves (B={cw['B']}, S={cw['S']}); {sum(ts1):.1f}s of CPU work"}
             del cwl
             torch.cuda.empty_cache()
 
@@ -731,7 +739,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "global_rows": Bg, "rows_per_gpu": B,
-                       "solver_steps": S, "precision": args.precision, "kernel": plan.kernel,
+                       "solver_steps": S, "precision": args.precision, "kernel": plan.kernel, "fp32_variant": plan.variant,
                        "parallelism": f"batch-shard x{world}" + (" + NCCL all-gather of final latents (side stream, double-buffered: "
                                                                  "the gather of solve i runs under solve i+1)" if world > 1 else ""),
                        "l2": f"rotating {N_INPUT_SETS} input sets ({N_INPUT_SETS * h2d / 1e6:.0f} MB) > 126 MB L2",

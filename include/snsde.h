@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SNSDE_ABI_VERSION 2
+#define SNSDE_ABI_VERSION 3
 
 typedef enum {
   SNSDE_OK = 0,
@@ -131,6 +131,11 @@ int snsde_plan_set_weights(snsde_plan* plan, const float* blob, int64_t n_floats
 /* Which kernel the plan will run: 0 = fp32 FMA, 1 = tcgen05 with resident weights, 2 = general tcgen05
  * (streamed weights / two M tiles / noise networks).  Negative on error. */
 int snsde_plan_kernel_kind(const snsde_plan* plan);
+
+/* For plans whose kernel kind is 0, after snsde_plan_set_weights: 0 = the shared-memory interpreter kernel (any shape /
+ * method), 1 = the warp-resident kernel (hidden, hidden_hidden and control width <= 32, euler / milstein: one warp owns
+ * its rows end to end, weights and activations in registers, inputs exchanged by warp shuffles).  Negative on error. */
+int snsde_plan_fma_variant(const snsde_plan* plan);
 
 /* The solve.  Replaces torchsde.sdeint as called at neuralsde.py:78-82.
  *   coeffs_dev       [B, K-1, 4C] fp32, packed cat(a,b,two_c,three_d); row b starts at

@@ -7,7 +7,7 @@ import os
 LIB_PATH = HERE / ("libsnsde_trace.so" if os.environ.get("SNSDE_TRACE_BUILD") else "libsnsde.so")
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_WEIGHTS, ERR_INTERNAL = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 2
+ABI_VERSION = 3
 FAMILY_BENCHMARK, FAMILY_TUTORIAL_LSDE, FAMILY_LATENT_SDE = 0, 1, 2
 METHOD = {"euler": 0, "milstein": 1, "srk": 2}
 PRECISION = {"fp32": 0, "tc": 1, "auto": 2}
@@ -35,7 +35,7 @@ class Point(ctypes.Structure):
                 ("frac", ctypes.c_float), ("interval", ctypes.c_int32)]
 
 
-EXPORTS = ("snsde_natural_coeffs_missing", "snsde_initial_state", "snsde_readout_head", "snsde_plan_status_nowait", "snsde_backward", "snsde_backward_workspace_bytes", "snsde_abi_version", "snsde_last_error", "snsde_weight_count", "snsde_plan_create",
+EXPORTS = ("snsde_plan_fma_variant", "snsde_natural_coeffs_missing", "snsde_initial_state", "snsde_readout_head", "snsde_plan_status_nowait", "snsde_backward", "snsde_backward_workspace_bytes", "snsde_abi_version", "snsde_last_error", "snsde_weight_count", "snsde_plan_create",
            "snsde_plan_destroy", "snsde_plan_set_weights", "snsde_plan_kernel_kind", "snsde_forward",
            "snsde_philox_fill", "snsde_plan_launch_count", "snsde_plan_status", "snsde_hermite_coeffs",
            "snsde_natural_coeffs", "snsde_fill_missing")
@@ -67,6 +67,7 @@ def load():
     lib.snsde_plan_set_weights.argtypes = [vp, vp, i64, ctypes.c_int, vp]
     lib.snsde_plan_kernel_kind.argtypes = [vp]
     lib.snsde_plan_launch_count.argtypes = [vp]
+    lib.snsde_plan_fma_variant.argtypes = [vp]
     lib.snsde_plan_launch_count.restype = i64
     lib.snsde_plan_status.argtypes = [vp, vp]
     lib.snsde_hermite_coeffs.argtypes = [vp, vp, i32, i32, i32, vp, ctypes.c_int, vp]

@@ -20,6 +20,7 @@
 #include "snsde_rng.cuh"
 #include "snsde_tc.cuh"
 #include "snsde_tcg.cuh"
+#include "snsde_warp.cuh"
 
 namespace snsde {
 size_t fma_group_smem_floats(const Program& pg, int R, int method);
@@ -55,6 +56,7 @@ struct snsde_plan {
   Program prog;
   float* d_wimg = nullptr;
   int wimg_floats = 0;
+  bool warp_ok = false; WarpProg wprog;   // kind == 0: the program fits the warp-resident kernel (hidden <= 32, snsde_warp.cu)
   TcPlan tc;                          // tensor-core path state (kind == 1)
   TcgPlan tcg;                        // general tensor-core path state (kind == 2)
   float* d_blob = nullptr; int blob_floats = 0;     // raw nn.Linear blob (the backward pass reads W in its [out][in] layout)
@@ -599,6 +601,12 @@ int snsde_plan_kernel_kind(const snsde_plan* p) {
 
 int64_t snsde_plan_launch_count(const snsde_plan* p) { return p ? p->launches : 0; }
 
+int snsde_plan_fma_variant(const snsde_plan* p) {
+  if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
+  if (!p->has_weights) return fail(SNSDE_ERR_NO_WEIGHTS, "the variant is chosen when the weights are set");
+  return (p->kind == 0 && p->warp_ok) ? 1 : 0;
+}
+
 int snsde_plan_status(snsde_plan* p, void* stream_v) {
   SNSDE_API_BEGIN
   if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
@@ -641,6 +649,7 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
   else if (p->desc.family == SNSDE_FAMILY_LATENT_SDE) compile_latent(p->desc, blob, p->prog, ib);
   else compile_tutorial(p->desc, blob, p->prog, ib);
   ib.pad4();
+  p->warp_ok = getenv("SNSDE_NO_WARP") == nullptr && warp_plan(p->prog, p->desc.method, p->wprog);   // env: testing aid
   if ((int)ib.img.size() > p->wimg_floats) {
     cudaFree(p->d_wimg);
     p->d_wimg = nullptr; p->wimg_floats = 0;
@@ -738,11 +747,7 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
   fp.row_slot = row_slot_dev; fp.dW = dW_dev; fp.dU = dU_dev; fp.seed = seed; fp.row_offset = row_offset; fp.out = out_dev;
   fp.vtab = nullptr;
 
-  GroupConfig gc;
-  const int method_ = p->desc.method;
-  if (!pick_group_config(p, B, [&](int R) { return fma_group_smem_floats(pg, R, method_); }, !srk, gc))
-    return fail(SNSDE_ERR_UNSUPPORTED, "activation buffers do not fit in shared memory");
-  fp.groups = gc.groups; fp.nw = gc.nw; fp.smem_w_floats = gc.smem_w_floats;
+  fp.groups = 1; fp.nw = 1; fp.smem_w_floats = 0;
   if (pg.tail.coef_src == CO_VBUF && S > 0) {
     const int npg = srk ? kSrkGPoints : 1;
     rc = ensure_vtab(p, (size_t)S * npg * pg.H);
@@ -752,6 +757,17 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
     p->launches += 1;
     fp.vtab = p->d_vtab;
   }
+  if (p->warp_ok) {                        // hidden <= 32: one warp per row group, everything in registers
+    cudaError_t e = warp_launch(fp, p->wprog, p->num_sms, stream);
+    if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "warp kernel launch: %s", cudaGetErrorString(e));
+    p->launches += 1;
+    return SNSDE_OK;
+  }
+  GroupConfig gc;
+  const int method_ = p->desc.method;
+  if (!pick_group_config(p, B, [&](int R) { return fma_group_smem_floats(pg, R, method_); }, !srk, gc))
+    return fail(SNSDE_ERR_UNSUPPORTED, "activation buffers do not fit in shared memory");
+  fp.groups = gc.groups; fp.nw = gc.nw; fp.smem_w_floats = gc.smem_w_floats;
   cudaError_t e = fma_launch(fp, gc.R, p->desc.method, gc.smem, stream);
   if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "fma kernel launch (R=%d nw=%d groups=%d smem=%zu): %s", gc.R, gc.nw, gc.groups, gc.smem, cudaGetErrorString(e));
   p->launches += 1;

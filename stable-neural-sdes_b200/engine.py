@@ -118,6 +118,15 @@ class Plan:
         return {0: "fma_fp32", 1: "tcgen05", 2: "tcgen05_general"}[_lib.check(self.lib.snsde_plan_kernel_kind(self._h))]
 
     @property
+    def variant(self):
+        """Form of the fp32 kernel this plan runs (after the weights are set): ``'warp'`` = the warp-resident kernel for
+        hidden sizes <= 32 (registers + shuffles), ``'interpreter'`` = the shared-memory row-group kernel; ``None`` for the
+        tensor-core kinds."""
+        if self.kernel != "fma_fp32":
+            return None
+        return "warp" if _lib.check(self.lib.snsde_plan_fma_variant(self._h)) == 1 else "interpreter"
+
+    @property
     def launches(self):
         return int(self.lib.snsde_plan_launch_count(self._h))
 

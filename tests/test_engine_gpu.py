@@ -600,3 +600,82 @@ def test_natural_spline_with_missing_values_on_device_matches_the_reference_gold
     full = torch.randn(4, 9, 3, generator=g)                     # no NaN: the missing-value kernel equals the plain builder
     close(data.natural_coeffs_cuda(full.to(dev), times[:9].to(dev), missing=True),
           torch.cat(spline.natural_cubic_spline_coeffs(times[:9], full), dim=-1), rtol=2e-5)
+
+
+# ---- the warp-resident kernel (hidden <= 32: registers + shuffles, csrc/snsde_warp.cu) against the interpreter kernel ----
+def _solve_with_variant(m, coeffs, times, y0, ts, dt, method, dev, warp, monkeypatch, **kw):
+    """A fresh plan with the warp-resident form enabled / disabled (SNSDE_NO_WARP is read when the weights are set)."""
+    if warp:
+        monkeypatch.delenv("SNSDE_NO_WARP", raising=False)
+    else:
+        monkeypatch.setenv("SNSDE_NO_WARP", "1")
+    snsde_b200.engine._PLANS.pop(m, None)
+    with torch.no_grad():
+        out = snsde_b200.sdeint(m, y0, ts, dt=dt, method=method, precision="fp32", **kw)
+    plan = next(iter(snsde_b200.plans_of(m).values()))
+    variant = plan.variant
+    snsde_b200.engine._PLANS.pop(m, None)
+    monkeypatch.delenv("SNSDE_NO_WARP", raising=False)
+    return out, variant
+
+
+WARP_CASES = [  # family, io, no, H, HH, C, L, B, method
+    ("tutorial", 0, 0, 32, 32, 2, 1, 64, "euler"),            # BASELINE c1's function
+    ("tutorial", 0, 0, 20, 28, 3, 2, 7, "euler"),              # 7 mat-vecs: over the register budget -> interpreter
+    ("benchmark", 4, 17, 32, 32, 5, 1, 19, "euler"), ("benchmark", 6, 17, 32, 32, 7, 1, 1500, "milstein"),
+    ("benchmark", 2, 16, 16, 16, 4, 2, 33, "euler"), ("benchmark", 3, 18, 32, 32, 3, 1, 40, "euler"),
+    ("benchmark", 1, 19, 24, 30, 3, 2, 9, "euler"), ("benchmark", 0, 5, 8, 8, 32, 1, 5, "milstein"),
+    ("benchmark", 5, 9, 32, 17, 3, 3, 1, "milstein"), ("benchmark", 4, 13, 31, 31, 6, 1, 2400, "euler"),
+    ("benchmark", 1, 14, 32, 32, 3, 1, 12, "euler"), ("benchmark", 3, 3, 5, 9, 2, 4, 3, "euler"),
+    ("benchmark", 1, 18, 32, 32, 3, 1, 1300, "euler"),          # <= 4 mat-vecs and a full machine: two rows per warp
+]
+
+
+@pytest.mark.parametrize("family,io,no,H,HH,C,L,B,method", WARP_CASES)
+def test_warp_kernel_agrees_with_the_interpreter_and_the_oracle(family, io, no, H, HH, C, L, B, method, dev, monkeypatch):
+    K = 12
+    m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, K, seed=7 * H + io + no, HH=HH, family=family, spacing=0.5)
+    if no == 7:
+        y0 = y0.abs() + 0.5
+    dt = 0.5
+    ts = torch.cat([times[:1], times[3:4], (times[5:6] + times[6:7]) / 2, times[-1:]])
+    dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(3)) * dt ** 0.5
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    args = (mg, coeffs, times.to(dev), y0.to(dev), ts.to(dev), dt, method, dev)
+    bm = snsde_b200.BrownianIncrements(dW.to(dev))
+    a, va = _solve_with_variant(*args, True, monkeypatch, bm=bm)
+    b, vb = _solve_with_variant(*args, False, monkeypatch, bm=bm)
+    expect_warp = family != "tutorial" or L + 5 <= 6          # tutorial: linear_X, emb (2 mat-vecs), L + 1 of f_net, linear_out
+    assert vb == "interpreter" and va == ("warp" if expect_warp else "interpreter"), (va, vb)
+    close(a, b, rtol=1e-6)                      # same arithmetic, same summation order
+    print("bit-identical to the interpreter kernel:", bool(torch.equal(a, b)))
+    # Philox mode: the two forms draw the same stream
+    pa, _ = _solve_with_variant(*args, True, monkeypatch, seed=21)
+    pb, _ = _solve_with_variant(*args, False, monkeypatch, seed=21)
+    close(pa, pb, rtol=1e-6)
+    if B <= 64:
+        m.to("cpu"); m.set_X(coeffs, times)
+        want = solver.sdeint(m, y0, ts, dt, solver.BrownianTable(dW), method=method)
+        close(a, want)
+
+
+def test_warp_kernel_fused_final_index_and_row_offset(dev, monkeypatch):
+    """Per-row capture and batch sharding on the warp-resident form: shards reproduce the full batch bit for bit."""
+    B, H, C, L, K = 70, 32, 4, 1, 10
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=5)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    fi = torch.randint(1, K, (B,), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        full = snsde_b200.solve_final(mg, times.to(dev), fi.to(dev), y0.to(dev), seed=9, precision="fp32")
+        assert next(iter(snsde_b200.plans_of(mg).values())).variant == "warp"
+        stream = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=9, precision="fp32")
+        parts = []
+        for lo, hi in ((0, 24), (24, 70)):
+            mg.set_X(coeffs[lo:hi].to(dev), times.to(dev))
+            parts.append(snsde_b200.solve_final(mg, times.to(dev), fi[lo:hi].to(dev), y0[lo:hi].to(dev), seed=9,
+                                                precision="fp32", row_offset=lo))
+    want = stream[fi.to(dev), torch.arange(B, device=dev)]
+    assert torch.equal(full, want)
+    assert torch.equal(torch.cat(parts), full)
