@@ -56,7 +56,8 @@ struct snsde_plan {
   Program prog;
   float* d_wimg = nullptr;
   int wimg_floats = 0;
-  bool warp_ok = false; WarpProg wprog;   // kind == 0: the program fits the warp-resident kernel (hidden <= 32, snsde_warp.cu)
+  bool warp_ok = false; WarpProg wprog;   // kind == 0: the program fits the warp-owned kernel (hidden <= 32, snsde_warp.cu)
+  float* d_wimg_warp = nullptr; int wimg_warp_floats = 0, wimg_warp_cap = 0;
   TcPlan tc;                          // tensor-core path state (kind == 1)
   TcgPlan tcg;                        // general tensor-core path state (kind == 2)
   float* d_blob = nullptr; int blob_floats = 0;     // raw nn.Linear blob (the backward pass reads W in its [out][in] layout)
@@ -579,6 +580,7 @@ int snsde_plan_destroy(snsde_plan* p) {
   if (!p) return SNSDE_OK;
   DeviceGuard guard(p->device);
   cudaFree(p->d_wimg);
+  cudaFree(p->d_wimg_warp);
   cudaFree(p->d_blob);
   cudaFree(p->d_steps);
   cudaFree(p->d_emits);
@@ -649,7 +651,22 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
   else if (p->desc.family == SNSDE_FAMILY_LATENT_SDE) compile_latent(p->desc, blob, p->prog, ib);
   else compile_tutorial(p->desc, blob, p->prog, ib);
   ib.pad4();
-  p->warp_ok = getenv("SNSDE_NO_WARP") == nullptr && warp_plan(p->prog, p->desc.method, p->wprog);   // env: testing aid
+  {
+    std::vector<float> wimg_warp;
+    p->warp_ok = getenv("SNSDE_NO_WARP") == nullptr &&                                               // env: testing aid
+                 warp_build(p->prog, p->desc.method, blob, ib.img.data(), p->wprog, wimg_warp) &&
+                 warp_smem_bytes((int)wimg_warp.size(), p->wprog.n_mv, 1, 1, 0, 0, false) <= (size_t)p->smem_optin;
+    if (p->warp_ok) {
+      if ((int)wimg_warp.size() > p->wimg_warp_cap) {
+        cudaFree(p->d_wimg_warp);
+        p->d_wimg_warp = nullptr; p->wimg_warp_cap = 0;
+        CUDA_TRY(cudaMalloc(&p->d_wimg_warp, wimg_warp.size() * sizeof(float)));
+        p->wimg_warp_cap = (int)wimg_warp.size();
+      }
+      p->wimg_warp_floats = (int)wimg_warp.size();
+      CUDA_TRY(cudaMemcpyAsync(p->d_wimg_warp, wimg_warp.data(), wimg_warp.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+  }
   if ((int)ib.img.size() > p->wimg_floats) {
     cudaFree(p->d_wimg);
     p->d_wimg = nullptr; p->wimg_floats = 0;
@@ -757,8 +774,9 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
     p->launches += 1;
     fp.vtab = p->d_vtab;
   }
-  if (p->warp_ok) {                        // hidden <= 32: one warp per row group, everything in registers
-    cudaError_t e = warp_launch(fp, p->wprog, p->num_sms, stream);
+  if (p->warp_ok) {                        // hidden <= 32: one warp owns its rows end to end
+    fp.wimg = p->d_wimg_warp; fp.wimg_floats = p->wimg_warp_floats;
+    cudaError_t e = warp_launch(fp, p->wprog, E, p->num_sms, p->smem_optin, stream);
     if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "warp kernel launch: %s", cudaGetErrorString(e));
     p->launches += 1;
     return SNSDE_OK;

@@ -54,6 +54,17 @@ __device__ __forceinline__ void philox_normals4(unsigned long long seed, uint32_
   box_muller(r.z, r.w, n[2], n[3]);
 }
 
+// The one normal of global row `gb` (= element gb & 3 of philox_normals4(seed, j, gb >> 2, s), bit for bit) when a
+// thread serves a single row: one Box-Muller pair instead of two.
+__device__ __forceinline__ float philox_normal1(unsigned long long seed, uint32_t j, unsigned long long gb, uint32_t s) {
+  const uint4 r = philox4x32_10(make_uint4(j, (uint32_t)(gb >> 2), s, kStreamTag),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const bool hi = (gb & 2ull) != 0ull;
+  float n0, n1;
+  box_muller(hi ? r.z : r.x, hi ? r.w : r.y, n0, n1);
+  return (gb & 1ull) ? n1 : n0;
+}
+
 // Second, independent stream for the SRK method: standard normals behind the space-time Levy area.
 __device__ __forceinline__ void philox_normals4_u(unsigned long long seed, uint32_t j, uint32_t p, uint32_t s,
                                                   float n[4]) {

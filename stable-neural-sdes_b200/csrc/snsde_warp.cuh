@@ -1,34 +1,47 @@
-// Warp-resident kernel for hidden sizes <= 32 (snsde_warp.cu): host-visible program form.
+// Warp-owned kernel for hidden sizes <= 32 (snsde_warp.cu): host-visible program form.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <vector>
 
 #include "snsde_common.cuh"
 
 namespace snsde {
 
-constexpr int kWarpMaxMv = 6;             // register budget: 32 weights per mat-vec per lane
+constexpr int kWarpMaxMv = 16;             // mat-vecs per step
 constexpr int kWarpDstDrift = kNumRowBufs; // pseudo-destination of the final drift op
+constexpr int kWarpMvInts = 12;            // a descriptor is read from shared memory with three 16-byte loads
+enum : int { kMvFirst = 1, kMvLast = 2, kMvSinCos = 4 };
 
-// One register-resident mat-vec of at most 32 x 32:  acc (+)= sum_{k<K} act_src[k] * Wt[k][lane].
+// One mat-vec of at most 32 x 32:  acc (+)= sum_k act_src[k] * W[lane][k], K padded to 8 * n8 with zero weights.
 struct WarpMv {
-  int src;          // activation buffer id read (BUF_Y .. BUF_Q)
-  int K, N;         // active inputs / outputs
-  int w_off;        // offset of the transposed [K][N] image in the FMA weight image
-  int first;        // starts an output: acc = bias + time term
-  int last;         // completes it: activation, write to dst
-  int dst;          // buffer id, or kWarpDstDrift
-  int act, tmode;
-  int b_off, tw_off;
+  int src;          // activation row read (BUF_Y .. BUF_Q)
+  int n8;           // chunks of 8 inputs
+  int N;            // outputs
+  int stride;       // floats between weight rows: 8 * n8 + 4 (conflict-free 16-byte loads, lane = row)
+  int w_off;        // offset of the [N][stride] rows in the warp image
+  int flags;        // kMvFirst: starts an output (acc = bias + time term); kMvLast: completes it (activation, write to
+                    // dst); kMvSinCos: the output has time-feature weights
+  int dst;          // activation row written, or kWarpDstDrift
+  int act;
+  int b_off, tw_off; // 32-float bias row; sin row followed by the cos row (time features)
+  int pad0, pad1;
 };
+static_assert(sizeof(WarpMv) == kWarpMvInts * 4, "descriptor layout");
 
 struct WarpProg {
   int n_mv;
+  int n_emits;      // entries of the emit table (filled in per launch)
+  int coef_off;     // 32-float row of the per-feature diffusion coefficient (CO_IMG)
+  int pad;
   WarpMv mv[kWarpMaxMv];
 };
 
-// Flattens the per-row ops of `pg` into mat-vecs; false when the model / method is outside the kernel's envelope
-// (hidden or control width above 32, more than kWarpMaxMv mat-vecs, SRK, Milstein through a noise network, LatentSDE).
-bool warp_plan(const Program& pg, int method, WarpProg& wp);
-cudaError_t warp_launch(const FmaParams& p, const WarpProg& wp, int num_sms, cudaStream_t stream);
+// Flattens the per-row ops of `pg` into mat-vecs and builds their weight image from the nn.Linear blob; false when the
+// model / method is outside the kernel's envelope (hidden or control width above 32, more than kWarpMaxMv mat-vecs, SRK,
+// Milstein through a noise network, LatentSDE).  `fma_img`: the interpreter's host image (per-feature coefficient).
+bool warp_build(const Program& pg, int method, const float* blob, const float* fma_img, WarpProg& wp, std::vector<float>& img);
+size_t warp_smem_bytes(int img_floats, int n_mv, int pairs, int R, int S, int n_emits, bool tables);
+cudaError_t warp_launch(const FmaParams& p, const WarpProg& wp, int n_emits, int num_sms, int smem_optin, cudaStream_t stream);
 
 }  // namespace snsde

@@ -119,8 +119,8 @@ class Plan:
 
     @property
     def variant(self):
-        """Form of the fp32 kernel this plan runs (after the weights are set): ``'warp'`` = the warp-resident kernel for
-        hidden sizes <= 32 (registers + shuffles), ``'interpreter'`` = the shared-memory row-group kernel; ``None`` for the
+        """Form of the fp32 kernel this plan runs (after the weights are set): ``'warp'`` = the warp-shuffle kernel for
+        hidden sizes <= 32 (one warp per row group, no barriers), ``'interpreter'`` = the shared-memory row-group kernel; ``None`` for the
         tensor-core kinds."""
         if self.kernel != "fma_fp32":
             return None

@@ -602,9 +602,9 @@ def test_natural_spline_with_missing_values_on_device_matches_the_reference_gold
           torch.cat(spline.natural_cubic_spline_coeffs(times[:9], full), dim=-1), rtol=2e-5)
 
 
-# ---- the warp-resident kernel (hidden <= 32: registers + shuffles, csrc/snsde_warp.cu) against the interpreter kernel ----
+# ---- the warp-shuffle kernel (hidden <= 32, csrc/snsde_warp.cu) against the interpreter kernel ----
 def _solve_with_variant(m, coeffs, times, y0, ts, dt, method, dev, warp, monkeypatch, **kw):
-    """A fresh plan with the warp-resident form enabled / disabled (SNSDE_NO_WARP is read when the weights are set)."""
+    """A fresh plan with the warp-shuffle form enabled / disabled (SNSDE_NO_WARP is read when the weights are set)."""
     if warp:
         monkeypatch.delenv("SNSDE_NO_WARP", raising=False)
     else:
@@ -621,13 +621,13 @@ def _solve_with_variant(m, coeffs, times, y0, ts, dt, method, dev, warp, monkeyp
 
 WARP_CASES = [  # family, io, no, H, HH, C, L, B, method
     ("tutorial", 0, 0, 32, 32, 2, 1, 64, "euler"),            # BASELINE c1's function
-    ("tutorial", 0, 0, 20, 28, 3, 2, 7, "euler"),              # 7 mat-vecs: over the register budget -> interpreter
+    ("tutorial", 0, 0, 20, 28, 3, 2, 7, "euler"),              # ragged widths, 7 mat-vecs
     ("benchmark", 4, 17, 32, 32, 5, 1, 19, "euler"), ("benchmark", 6, 17, 32, 32, 7, 1, 1500, "milstein"),
     ("benchmark", 2, 16, 16, 16, 4, 2, 33, "euler"), ("benchmark", 3, 18, 32, 32, 3, 1, 40, "euler"),
     ("benchmark", 1, 19, 24, 30, 3, 2, 9, "euler"), ("benchmark", 0, 5, 8, 8, 32, 1, 5, "milstein"),
-    ("benchmark", 5, 9, 32, 17, 3, 3, 1, "milstein"), ("benchmark", 4, 13, 31, 31, 6, 1, 2400, "euler"),
+    ("benchmark", 5, 9, 32, 17, 3, 3, 1, "milstein"), ("benchmark", 4, 13, 31, 31, 6, 1, 2400, "euler"),     # a full machine: two rows per warp
     ("benchmark", 1, 14, 32, 32, 3, 1, 12, "euler"), ("benchmark", 3, 3, 5, 9, 2, 4, 3, "euler"),
-    ("benchmark", 1, 18, 32, 32, 3, 1, 1300, "euler"),          # <= 4 mat-vecs and a full machine: two rows per warp
+    ("benchmark", 1, 18, 32, 32, 3, 1, 1300, "euler"),
 ]
 
 
@@ -646,14 +646,12 @@ def test_warp_kernel_agrees_with_the_interpreter_and_the_oracle(family, io, no, 
     bm = snsde_b200.BrownianIncrements(dW.to(dev))
     a, va = _solve_with_variant(*args, True, monkeypatch, bm=bm)
     b, vb = _solve_with_variant(*args, False, monkeypatch, bm=bm)
-    expect_warp = family != "tutorial" or L + 5 <= 6          # tutorial: linear_X, emb (2 mat-vecs), L + 1 of f_net, linear_out
-    assert vb == "interpreter" and va == ("warp" if expect_warp else "interpreter"), (va, vb)
-    close(a, b, rtol=1e-6)                      # same arithmetic, same summation order
-    print("bit-identical to the interpreter kernel:", bool(torch.equal(a, b)))
+    assert vb == "interpreter" and va == "warp", (va, vb)
+    close(a, b, rtol=5e-6)                      # same arithmetic; four partial sums per output instead of one
     # Philox mode: the two forms draw the same stream
     pa, _ = _solve_with_variant(*args, True, monkeypatch, seed=21)
     pb, _ = _solve_with_variant(*args, False, monkeypatch, seed=21)
-    close(pa, pb, rtol=1e-6)
+    close(pa, pb, rtol=5e-6)
     if B <= 64:
         m.to("cpu"); m.set_X(coeffs, times)
         want = solver.sdeint(m, y0, ts, dt, solver.BrownianTable(dW), method=method)
@@ -661,7 +659,7 @@ def test_warp_kernel_agrees_with_the_interpreter_and_the_oracle(family, io, no, 
 
 
 def test_warp_kernel_fused_final_index_and_row_offset(dev, monkeypatch):
-    """Per-row capture and batch sharding on the warp-resident form: shards reproduce the full batch bit for bit."""
+    """Per-row capture and batch sharding on the warp-shuffle form: shards reproduce the full batch bit for bit."""
     B, H, C, L, K = 70, 32, 4, 1, 10
     m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=5)
     mg = m.to(dev)
