@@ -65,6 +65,7 @@ struct snsde_plan {
   snsde_emit* d_emits = nullptr; int emits_cap = 0; std::vector<snsde_emit> h_emits;
   snsde_point* d_points = nullptr; int points_cap = 0; std::vector<snsde_point> h_points;
   float* d_vtab = nullptr; size_t vtab_cap = 0;     // [S][npg][H] row-independent diffusion coefficient (FMA kernels)
+  bool vtab_valid = false; int vtab_S = 0, vtab_npg = 0;   // cached while the weights and the evaluation times are unchanged
   cublasHandle_t cublas = nullptr;                  // weight-gradient GEMMs of the backward pass (created lazily)
   int64_t launches = 0;
   // sticky flags raised by the kernels: one word of mapped page-locked host memory (the rare device store travels over
@@ -422,7 +423,8 @@ __global__ void philox_fill_kernel(unsigned long long seed, unsigned long long r
 
 // ---- table upload (steps / emits / points are host data; uploaded only when they change) ------------
 template <typename T>
-static int upload_table(T*& d_ptr, int& cap, std::vector<T>& host_copy, const T* src, int n, cudaStream_t stream) {
+static int upload_table(T*& d_ptr, int& cap, std::vector<T>& host_copy, const T* src, int n, cudaStream_t stream,
+                        bool* changed = nullptr) {
   if (n > cap) {
     cudaFree(d_ptr); d_ptr = nullptr; host_copy.clear(); cap = 0;
     CUDA_TRY(cudaMalloc(&d_ptr, sizeof(T) * (size_t)std::max(n, 64)));
@@ -430,6 +432,7 @@ static int upload_table(T*& d_ptr, int& cap, std::vector<T>& host_copy, const T*
   }
   if ((int)host_copy.size() != n || (n && memcmp(host_copy.data(), src, sizeof(T) * n) != 0)) {
     host_copy.assign(src, src + n);
+    if (changed) *changed = true;
     // pageable source: the runtime stages it before returning
     if (n) CUDA_TRY(cudaMemcpyAsync(d_ptr, src, sizeof(T) * n, cudaMemcpyHostToDevice, stream));
   }
@@ -438,11 +441,13 @@ static int upload_table(T*& d_ptr, int& cap, std::vector<T>& host_copy, const T*
 
 static int upload_tables(snsde_plan* p, const snsde_step* steps, int S, const snsde_emit* emits, int E,
                          const snsde_point* points, cudaStream_t stream) {
-  int rc = upload_table(p->d_steps, p->steps_cap, p->h_steps, steps, S, stream);
+  bool times_changed = false;
+  int rc = upload_table(p->d_steps, p->steps_cap, p->h_steps, steps, S, stream, &times_changed);
   if (rc != SNSDE_OK) return rc;
-  rc = upload_table(p->d_emits, p->emits_cap, p->h_emits, emits, E, stream);
+  if (emits || E == 0) rc = upload_table(p->d_emits, p->emits_cap, p->h_emits, emits, E, stream);
   if (rc != SNSDE_OK) return rc;
-  if (points) rc = upload_table(p->d_points, p->points_cap, p->h_points, points, S * kSrkPoints, stream);
+  if (points) rc = upload_table(p->d_points, p->points_cap, p->h_points, points, S * kSrkPoints, stream, &times_changed);
+  if (times_changed) p->vtab_valid = false;              // the row-independent coefficient table is per evaluation time
   return rc;
 }
 
@@ -693,6 +698,7 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
     else if (rc != SNSDE_OK) return fail(rc, "tensor-core weight packing failed: %s", tcg_unsupported_reason());
   }
   p->has_weights = true;
+  p->vtab_valid = false;                              // the coefficient table is a function of the weights
   return SNSDE_OK;
   SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
@@ -767,11 +773,15 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
   fp.groups = 1; fp.nw = 1; fp.smem_w_floats = 0;
   if (pg.tail.coef_src == CO_VBUF && S > 0) {
     const int npg = srk ? kSrkGPoints : 1;
-    rc = ensure_vtab(p, (size_t)S * npg * pg.H);
-    if (rc != SNSDE_OK) return rc;
-    cudaError_t e = vec_tables_launch(pg, p->d_wimg, p->d_steps, fp.points, S, npg, p->d_vtab, stream);
-    if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "coefficient table kernel launch: %s", cudaGetErrorString(e));
-    p->launches += 1;
+    if (!p->vtab_valid || p->vtab_S != S || p->vtab_npg != npg) {
+      p->vtab_valid = false;
+      rc = ensure_vtab(p, (size_t)S * npg * pg.H);
+      if (rc != SNSDE_OK) return rc;
+      cudaError_t e = vec_tables_launch(pg, p->d_wimg, p->d_steps, fp.points, S, npg, p->d_vtab, stream);
+      if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "coefficient table kernel launch: %s", cudaGetErrorString(e));
+      p->launches += 1;
+      p->vtab_valid = true; p->vtab_S = S; p->vtab_npg = npg;
+    }
     fp.vtab = p->d_vtab;
   }
   if (p->warp_ok) {                        // hidden <= 32: one warp owns its rows end to end

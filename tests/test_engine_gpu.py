@@ -677,3 +677,39 @@ def test_warp_kernel_fused_final_index_and_row_offset(dev, monkeypatch):
     want = stream[fi.to(dev), torch.arange(B, device=dev)]
     assert torch.equal(full, want)
     assert torch.equal(torch.cat(parts), full)
+
+
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_cached_coefficient_table_follows_weights_and_step_times(dev, precision, monkeypatch):
+    """The row-independent diffusion coefficient (noise_t) is tabulated once per (weights, evaluation times) on the fp32
+    kernels: a solve after an in-place weight update, or on another time grid, must not read the old table."""
+    for warp in (True, False):
+        if warp:
+            monkeypatch.delenv("SNSDE_NO_WARP", raising=False)
+        else:
+            monkeypatch.setenv("SNSDE_NO_WARP", "1")
+        B, H, C, L, K = 9, 32, 4, 1, 8
+        m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=31)
+        mg = m.to(dev)
+        mg.set_X(coeffs.to(dev), times.to(dev))
+        dW = (torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(4))).to(dev)
+        bm = lambda: snsde_b200.BrownianIncrements(dW)                       # noqa: E731
+        with torch.no_grad():
+            z1 = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, bm=bm(), precision=precision)
+            z1b = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, bm=bm(), precision=precision)   # table reused
+            assert torch.equal(z1, z1b)
+            mg.noise_t[2].bias.add_(0.7)                                      # in-place update (an optimizer step)
+            z2 = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, bm=bm(), precision=precision)
+            snsde_b200.engine._PLANS.pop(mg, None)                            # fresh plan, fresh table
+            z2f = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, bm=bm(), precision=precision)
+            assert not torch.equal(z1, z2) and torch.equal(z2, z2f)
+            ts = times[:5]
+            z3 = snsde_b200.sdeint(mg, y0.to(dev), ts.to(dev), dt=1.0, bm=snsde_b200.BrownianIncrements(dW[:4]), precision=precision)
+            assert torch.equal(z3, z2f[:5])
+            half = times.to(dev) * 0.5                                        # other evaluation times, same step count
+            mg.set_X(coeffs.to(dev), half)
+            z4 = snsde_b200.sdeint(mg, y0.to(dev), half, dt=0.5, bm=bm(), precision=precision)
+            snsde_b200.engine._PLANS.pop(mg, None)
+            z4f = snsde_b200.sdeint(mg, y0.to(dev), half, dt=0.5, bm=bm(), precision=precision)
+            assert torch.equal(z4, z4f)
+        snsde_b200.engine._PLANS.pop(mg, None)
