@@ -133,8 +133,9 @@ int snsde_plan_set_weights(snsde_plan* plan, const float* blob, int64_t n_floats
 int snsde_plan_kernel_kind(const snsde_plan* plan);
 
 /* For plans whose kernel kind is 0, after snsde_plan_set_weights: 0 = the shared-memory interpreter kernel (any shape /
- * method), 1 = the warp-shuffle kernel (hidden, hidden_hidden and control width <= 32, euler / milstein: one warp owns
- * its rows end to end, activations and state in registers, layer inputs exchanged by warp shuffles, no barrier in the time loop).  Negative on error. */
+ * method), 1 = the warp-owned kernel (hidden, hidden_hidden and control width <= 32, euler / milstein: one warp owns
+ * its rows end to end with a helper warp preparing the state-independent inputs; used for launches of up to 4096 rows, larger
+ * batches run on the interpreter kernel, whose 8-row groups amortise the weight reads).  Negative on error. */
 int snsde_plan_fma_variant(const snsde_plan* plan);
 
 /* The solve.  Replaces torchsde.sdeint as called at neuralsde.py:78-82.

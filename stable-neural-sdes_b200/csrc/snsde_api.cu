@@ -784,7 +784,7 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
     }
     fp.vtab = p->d_vtab;
   }
-  if (p->warp_ok) {                        // hidden <= 32: one warp owns its rows end to end
+  if (p->warp_ok && B <= kWarpMaxRows) {   // hidden <= 32 and rows scarce: a pair of warps owns each row end to end
     fp.wimg = p->d_wimg_warp; fp.wimg_floats = p->wimg_warp_floats;
     cudaError_t e = warp_launch(fp, p->wprog, E, p->num_sms, p->smem_optin, stream);
     if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "warp kernel launch: %s", cudaGetErrorString(e));

@@ -442,9 +442,12 @@ static cudaError_t warp_launch_r(const FmaParams& p, WarpProg wp, int n_emits, i
 }
 
 // `p.wimg` / `p.wimg_floats` must describe the WARP image (warp_build), not the interpreter's.
+// One row per pair: measured on the tutorial function (H = 32, 1xB200, SDE-steps/s, this kernel vs the interpreter
+// kernel) 64 rows 3.2e7 / 1.0e7, 512 rows 2.0e8 / 6.0e7, 2048 rows 4.0e8 / 2.4e8, 8192 rows 3.4e8 / 5.8e8, 32768 rows
+// 3.5e8 / 1.0e9 - a latency kernel: it wins while rows are scarce, and the interpreter's 8-row groups (each weight
+// read feeds 8 FMAs, 15 groups share one staged image) win once the machine is full.  The caller switches at
+// kWarpMaxRows; a two-rows-per-pair variant was measured slower than both (165 registers) and is not instantiated.
 cudaError_t warp_launch(const FmaParams& p, const WarpProg& wp, int n_emits, int num_sms, int smem_optin, cudaStream_t stream) {
-  // two rows per pair (each weight load feeds two rows) once there are enough rows to fill the machine with such pairs
-  if (p.B >= 2 * 8 * num_sms) return warp_launch_r<2>(p, wp, n_emits, num_sms, smem_optin, stream);
   return warp_launch_r<1>(p, wp, n_emits, num_sms, smem_optin, stream);
 }
 

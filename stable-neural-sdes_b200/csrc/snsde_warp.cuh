@@ -9,6 +9,7 @@
 namespace snsde {
 
 constexpr int kWarpMaxMv = 16;             // mat-vecs per step
+constexpr int kWarpMaxRows = 4096;         // rows per launch up to which the warp-owned kernel beats the interpreter (snsde_warp.cu)
 constexpr int kWarpDstDrift = kNumRowBufs; // pseudo-destination of the final drift op
 constexpr int kWarpMvInts = 12;            // a descriptor is read from shared memory with three 16-byte loads
 enum : int { kMvFirst = 1, kMvLast = 2, kMvSinCos = 4 };

@@ -625,7 +625,7 @@ WARP_CASES = [  # family, io, no, H, HH, C, L, B, method
     ("benchmark", 4, 17, 32, 32, 5, 1, 19, "euler"), ("benchmark", 6, 17, 32, 32, 7, 1, 1500, "milstein"),
     ("benchmark", 2, 16, 16, 16, 4, 2, 33, "euler"), ("benchmark", 3, 18, 32, 32, 3, 1, 40, "euler"),
     ("benchmark", 1, 19, 24, 30, 3, 2, 9, "euler"), ("benchmark", 0, 5, 8, 8, 32, 1, 5, "milstein"),
-    ("benchmark", 5, 9, 32, 17, 3, 3, 1, "milstein"), ("benchmark", 4, 13, 31, 31, 6, 1, 2400, "euler"),     # a full machine: two rows per warp
+    ("benchmark", 5, 9, 32, 17, 3, 3, 1, "milstein"), ("benchmark", 4, 13, 31, 31, 6, 1, 2400, "euler"),     # several pairs per CTA
     ("benchmark", 1, 14, 32, 32, 3, 1, 12, "euler"), ("benchmark", 3, 3, 5, 9, 2, 4, 3, "euler"),
     ("benchmark", 1, 18, 32, 32, 3, 1, 1300, "euler"),
 ]
@@ -713,3 +713,22 @@ def test_cached_coefficient_table_follows_weights_and_step_times(dev, precision,
             z4f = snsde_b200.sdeint(mg, y0.to(dev), half, dt=0.5, bm=bm(), precision=precision)
             assert torch.equal(z4, z4f)
         snsde_b200.engine._PLANS.pop(mg, None)
+
+
+def test_large_launches_of_small_models_run_on_the_interpreter_and_agree_with_the_warp_kernel(dev):
+    """hidden <= 32 is eligible for the warp-owned kernel, which serves launches of up to 4096 rows; rows never interact,
+    so the first rows of a 5000-row launch (interpreter kernel) equal the same rows solved alone (warp-owned kernel)."""
+    B, H, C, L, K = 5000, 32, 3, 1, 7
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=77)
+    mg = m.to(dev)
+    with torch.no_grad():
+        mg.set_X(coeffs.to(dev), times.to(dev))
+        big = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, seed=5, precision="fp32")
+        assert next(iter(snsde_b200.plans_of(mg).values())).variant == "warp"          # eligibility is a plan property
+        mg.set_X(coeffs[:96].to(dev), times.to(dev))
+        small = snsde_b200.sdeint(mg, y0[:96].to(dev), times.to(dev), dt=1.0, seed=5, precision="fp32")
+    close(big[:, :96], small, rtol=5e-6)
+    m.to("cpu"); m.set_X(coeffs[:16], times)
+    plan = next(iter(snsde_b200.plans_of(mg).values()))
+    dW = snsde_b200.philox_increments(5, plan.step_plan(times, 1.0, times), 16, H, dev).cpu()
+    close(big[:, :16], solver.sdeint(m, y0[:16], times, 1.0, solver.BrownianTable(dW)))
