@@ -660,7 +660,7 @@ int snsde_plan_set_weights(snsde_plan* p, const float* blob, int64_t n_floats, i
     std::vector<float> wimg_warp;
     p->warp_ok = getenv("SNSDE_NO_WARP") == nullptr &&                                               // env: testing aid
                  warp_build(p->prog, p->desc.method, blob, ib.img.data(), p->wprog, wimg_warp) &&
-                 warp_smem_bytes((int)wimg_warp.size(), p->wprog.n_mv, 1, 1, 0, 0, false) <= (size_t)p->smem_optin;
+                 warp_smem_bytes((int)wimg_warp.size(), 1, 1, 0, 0, false, p->desc.method == SNSDE_METHOD_SRK) <= (size_t)p->smem_optin;
     if (p->warp_ok) {
       if ((int)wimg_warp.size() > p->wimg_warp_cap) {
         cudaFree(p->d_wimg_warp);
@@ -786,7 +786,7 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
   }
   if (p->warp_ok && B <= kWarpMaxRows) {   // hidden <= 32 and rows scarce: a pair of warps owns each row end to end
     fp.wimg = p->d_wimg_warp; fp.wimg_floats = p->wimg_warp_floats;
-    cudaError_t e = warp_launch(fp, p->wprog, E, p->num_sms, p->smem_optin, stream);
+    cudaError_t e = warp_launch(fp, p->wprog, p->desc.method, E, p->num_sms, p->smem_optin, stream);
     if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "warp kernel launch: %s", cudaGetErrorString(e));
     p->launches += 1;
     return SNSDE_OK;

@@ -12,7 +12,7 @@ constexpr int kWarpMaxMv = 16;             // mat-vecs per step
 constexpr int kWarpMaxRows = 4096;         // rows per launch up to which the warp-owned kernel beats the interpreter (snsde_warp.cu)
 constexpr int kWarpDstDrift = kNumRowBufs; // pseudo-destination of the final drift op
 constexpr int kWarpMvInts = 12;            // a descriptor is read from shared memory with three 16-byte loads
-enum : int { kMvFirst = 1, kMvLast = 2, kMvSinCos = 4 };
+enum : int { kMvFirst = 1, kMvLast = 2, kMvSinCos = 4, kMvDiff = 8 };
 
 // One mat-vec of at most 32 x 32:  acc (+)= sum_k act_src[k] * W[lane][k], K padded to 8 * n8 with zero weights.
 struct WarpMv {
@@ -22,7 +22,8 @@ struct WarpMv {
   int stride;       // floats between weight rows: 8 * n8 + 4 (conflict-free 16-byte loads, lane = row)
   int w_off;        // offset of the [N][stride] rows in the warp image
   int flags;        // kMvFirst: starts an output (acc = bias + time term); kMvLast: completes it (activation, write to
-                    // dst); kMvSinCos: the output has time-feature weights
+                    // dst); kMvSinCos: the output has time-feature weights; kMvDiff: part of the diffusion (the SRK stages evaluate drift and
+                    // diffusion at different states)
   int dst;          // activation row written, or kWarpDstDrift
   int act;
   int b_off, tw_off; // 32-float bias row; sin row followed by the cos row (time features)
@@ -39,10 +40,10 @@ struct WarpProg {
 };
 
 // Flattens the per-row ops of `pg` into mat-vecs and builds their weight image from the nn.Linear blob; false when the
-// model / method is outside the kernel's envelope (hidden or control width above 32, more than kWarpMaxMv mat-vecs, SRK,
-// Milstein through a noise network, LatentSDE).  `fma_img`: the interpreter's host image (per-feature coefficient).
+// model / method is outside the kernel's envelope (hidden or control width above 32, more than kWarpMaxMv mat-vecs,
+// Milstein through a noise network).  `fma_img`: the interpreter's host image (per-feature coefficient).
 bool warp_build(const Program& pg, int method, const float* blob, const float* fma_img, WarpProg& wp, std::vector<float>& img);
-size_t warp_smem_bytes(int img_floats, int n_mv, int pairs, int R, int S, int n_emits, bool tables);
-cudaError_t warp_launch(const FmaParams& p, const WarpProg& wp, int n_emits, int num_sms, int smem_optin, cudaStream_t stream);
+size_t warp_smem_bytes(int img_floats, int pairs, int R, int S, int n_emits, bool tables, bool srk);
+cudaError_t warp_launch(const FmaParams& p, const WarpProg& wp, int method, int n_emits, int num_sms, int smem_optin, cudaStream_t stream);
 
 }  // namespace snsde

@@ -628,6 +628,9 @@ WARP_CASES = [  # family, io, no, H, HH, C, L, B, method
     ("benchmark", 5, 9, 32, 17, 3, 3, 1, "milstein"), ("benchmark", 4, 13, 31, 31, 6, 1, 2400, "euler"),     # several pairs per CTA
     ("benchmark", 1, 14, 32, 32, 3, 1, 12, "euler"), ("benchmark", 3, 3, 5, 9, 2, 4, 3, "euler"),
     ("benchmark", 1, 18, 32, 32, 3, 1, 1300, "euler"),
+    # SRK: six passes per step through the same mat-vec code (drift / diffusion at the stage states)
+    ("benchmark", 4, 17, 32, 32, 5, 1, 19, "srk"), ("benchmark", 3, 18, 32, 32, 3, 1, 40, "srk"), ("benchmark", 1, 19, 24, 30, 3, 2, 9, "srk"),
+    ("benchmark", 6, 6, 16, 16, 4, 2, 300, "srk"), ("tutorial", 0, 0, 32, 32, 2, 1, 64, "srk"), ("benchmark", 5, 0, 8, 12, 3, 1, 5, "srk"),
 ]
 
 
@@ -640,10 +643,11 @@ def test_warp_kernel_agrees_with_the_interpreter_and_the_oracle(family, io, no, 
     dt = 0.5
     ts = torch.cat([times[:1], times[3:4], (times[5:6] + times[6:7]) / 2, times[-1:]])
     dW = torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(3)) * dt ** 0.5
+    dU = dt * (dW / 2 + torch.randn(K - 1, B, H, generator=torch.Generator().manual_seed(4)) * (dt / 12) ** 0.5)
     mg = m.to(dev)
     mg.set_X(coeffs.to(dev), times.to(dev))
     args = (mg, coeffs, times.to(dev), y0.to(dev), ts.to(dev), dt, method, dev)
-    bm = snsde_b200.BrownianIncrements(dW.to(dev))
+    bm = snsde_b200.BrownianIncrements(dW.to(dev), dU.to(dev))
     a, va = _solve_with_variant(*args, True, monkeypatch, bm=bm)
     b, vb = _solve_with_variant(*args, False, monkeypatch, bm=bm)
     assert vb == "interpreter" and va == "warp", (va, vb)
@@ -654,7 +658,7 @@ def test_warp_kernel_agrees_with_the_interpreter_and_the_oracle(family, io, no, 
     close(pa, pb, rtol=5e-6)
     if B <= 64:
         m.to("cpu"); m.set_X(coeffs, times)
-        want = solver.sdeint(m, y0, ts, dt, solver.BrownianTable(dW), method=method)
+        want = solver.sdeint(m, y0, ts, dt, solver.BrownianTable(dW, dU=dU), method=method)
         close(a, want)
 
 

@@ -186,21 +186,21 @@ def test_patched_forward_reproduces_the_reference_goldens(cases, dev):
             pred, lat, logqp = model(c["coeffs"].to(dev), c["times"].to(dev),
                                      bm=snsde_b200.BrownianIncrements(c["dW"].to(dev), c["dU"].to(dev)), **kw)
         plan = next(iter(snsde_b200.plans_of(model).values()))
-        assert plan.kernel == "fma_fp32" and plan.desc["family"] == _lib.FAMILY_LATENT_SDE
+        assert plan.kernel == "fma_fp32" and plan.variant == "warp" and plan.desc["family"] == _lib.FAMILY_LATENT_SDE
         close(lat, c["latent"], 1e-4, f"latent {c['method']}")
         close(pred, c["pred"], 1e-4, f"pred {c['method']}")
         close(logqp, c["logqp"], 1e-4, f"logqp {c['method']}")
 
 
 LATENT_SHAPES = [  # C, H, HH, L, B, K, method       one warp / several warps per row group, ragged batch, deep MLP
-    (2, 5, 6, 1, 7, 6, "euler"), (3, 33, 40, 2, 9, 7, "euler"), (4, 65, 64, 1, 12, 6, "srk"), (2, 32, 32, 3, 64, 9, "srk"),
+    (2, 5, 6, 1, 7, 6, "euler"), (2, 5, 6, 1, 7, 6, "srk"), (3, 32, 32, 2, 33, 7, "milstein"), (3, 33, 40, 2, 9, 7, "euler"), (4, 65, 64, 1, 12, 6, "srk"), (2, 32, 32, 3, 64, 9, "srk"),
     (3, 17, 130, 2, 5, 6, "milstein"), (2, 129, 96, 1, 300, 5, "euler"), (2, 8, 8, 1, 1030, 5, "srk"),
 ]
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("C,H,HH,L,B,K,method", LATENT_SHAPES)
-def test_augmented_solve_matches_the_oracle(C, H, HH, L, B, K, method, dev):
+def test_augmented_solve_matches_the_oracle(C, H, HH, L, B, K, method, dev, monkeypatch):
     torch.manual_seed(H * 7 + B)
     m = olatent.LatentSDE(C, H, HH, L, theta=0.9, mu=-0.2, sigma=0.45)
     times = torch.linspace(0, 1.5, K)
@@ -219,6 +219,18 @@ def test_augmented_solve_matches_the_oracle(C, H, HH, L, B, K, method, dev):
                                 bm=snsde_b200.BrownianIncrements(dW.to(dev), dU.to(dev)))
     close(got, want, 1e-4, "augmented states")
     close(got[..., -1], want[..., -1], 1e-4, "KL accumulator")
+    plan = next(iter(snsde_b200.plans_of(mg).values()))
+    assert plan.variant == ("warp" if max(H, HH) <= 32 else "interpreter")
+    if plan.variant == "warp":                              # the same solve on the interpreter kernel
+        monkeypatch.setenv("SNSDE_NO_WARP", "1")
+        snsde_b200.engine._PLANS.pop(mg, None)
+        with torch.no_grad():
+            ref = snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=dt, method=method, names=olatent.NAMES,
+                                    bm=snsde_b200.BrownianIncrements(dW.to(dev), dU.to(dev)))
+        assert next(iter(snsde_b200.plans_of(mg).values())).variant == "interpreter"
+        monkeypatch.delenv("SNSDE_NO_WARP")
+        snsde_b200.engine._PLANS.pop(mg, None)
+        close(got, ref, 5e-6, "warp-owned vs interpreter kernel")
     assert float(want[-1, :, -1].min()) > 0.0
     with pytest.raises(ValueError, match="augmented"):
         snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=dt)
