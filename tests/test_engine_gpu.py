@@ -736,3 +736,40 @@ def test_large_launches_of_small_models_run_on_the_interpreter_and_agree_with_th
     plan = next(iter(snsde_b200.plans_of(mg).values()))
     dW = snsde_b200.philox_increments(5, plan.step_plan(times, 1.0, times), 16, H, dev).cpu()
     close(big[:, :16], solver.sdeint(m, y0[:16], times, 1.0, solver.BrownianTable(dW)))
+
+
+def test_warp_kernel_randomised_shapes_against_the_interpreter(dev, monkeypatch):
+    """Seeded sweep over small models at the edges of the warp-owned kernel's envelope (width 1, 32 channels, 5 layers,
+    single rows, zero and one step, every method): both fp32 kernels must agree, and the plan must pick the warp form."""
+    rng = np.random.default_rng(123)
+    n_checked = 0
+    for trial in range(36):
+        io = int(rng.integers(0, 7))
+        no = int(rng.choice([0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19]))
+        method = ["euler", "milstein", "srk"][trial % 3]
+        if method == "milstein" and no in (14, 15, 18, 19):
+            method = "euler"                               # full vjp through noise_y: interpreter only (not this test)
+        H = int(rng.choice([1, 2, 3, 7, 16, 31, 32]))
+        HH = H if io in (0, 2, 4, 6) else int(rng.choice([1, 5, 32]))
+        C = int(rng.choice([1, 2, 9, 32]))
+        L = int(rng.choice([1, 2, 5]))
+        B = int(rng.choice([1, 2, 3, 65, 130]))
+        K = int(rng.choice([1, 2, 6]))
+        m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, max(K, 2), seed=1000 + trial, HH=HH, spacing=0.5)
+        ts = times[:K]
+        S = K - 1
+        g = torch.Generator().manual_seed(trial)
+        dW = torch.randn(S, B, H, generator=g) * 0.5 ** 0.5
+        dU = 0.5 * (dW / 2 + torch.randn(S, B, H, generator=g) * (0.5 / 12) ** 0.5)
+        mg = m.to(dev)
+        mg.set_X(coeffs.to(dev), times.to(dev))
+        args = (mg, coeffs, times.to(dev), y0.to(dev), ts.to(dev), 0.5, method, dev)
+        for kw in (dict(bm=snsde_b200.BrownianIncrements(dW.to(dev), dU.to(dev))), dict(seed=trial)):
+            a, va = _solve_with_variant(*args, True, monkeypatch, **kw)
+            b, vb = _solve_with_variant(*args, False, monkeypatch, **kw)
+            assert (va, vb) == ("warp", "interpreter"), (trial, io, no, method, H, HH, C, L, va, vb)
+            assert a.shape == (K, B, H) and torch.isfinite(a).all()
+            assert torch.equal(a[0].cpu(), y0)
+            close(a, b, rtol=5e-6)
+            n_checked += 1
+    assert n_checked == 72
