@@ -691,7 +691,7 @@ def main():
     configs = {}
     if args.workload == "c2" and not args.no_configs and not args.rows and not args.solver_steps:
         del pinned, raw_pinned
-        for name in ("c1", "c3", "c4", "c5"):
+        for name in os.environ.get("BENCH_CONFIGS", "c1,c3,c4,c5").split(","):       # env: debugging aid (subset / order)
             cw = dict(WORKLOADS[name])
             cwl = Workload(name, cw, args.precision, dev, rank, world)
             # long-horizon trajectories of these models are ill-conditioned in fp32 (tests/test_fullsize_gpu.py):
