@@ -189,7 +189,9 @@ int snsde_plan_status_nowait(snsde_plan* plan);
 /* ---- backward pass through the solve -------------------------------------------------------------
  * Replaces the autograd graph the reference builds through torchsde.sdeint when it trains
  * (benchmark_classification/common_sde.py:156-162: `pred_y = model(...); loss.backward()`;
- * benchmark_forecasting/common_sde.py:145-150).  Method euler.
+ * benchmark_forecasting/common_sde.py:145-150).  Methods euler and milstein (the latter for the elementwise diffusions:
+ * every noise option but 14, 15, 18, 19; its diagonal term 0.5 (g v) dg/dy is differentiated through both factors, as
+ * torchsde's create_graph vjp is).
  *
  * Protocol: run snsde_forward with a step plan that emits EVERY solver state (slot s+1 = state after step s;
  * out_dev = states [S+1, B, H]); form the requested outputs from those states (linear interpolation / per-row

@@ -62,22 +62,27 @@ def euler_step(sde, bm, t0, t1, y0):
 
 
 def milstein_step(sde, bm, t0, t1, y0):
+    """torchsde 0.2.5 ``Milstein.step`` (Ito, derivative-based) on ``ForwardSDE.g_prod_and_gdg_prod_diagonal``: the vjp is
+    taken with ``create_graph=torch.is_grad_enabled()`` and ``grad_outputs = g * v`` inside the graph, so under autograd
+    the gradient flows through both factors of ``0.5 * (g v) dg/dy`` (second derivative of g)."""
     dt = t1 - t0
     dW = bm(t0, t1)
     v = dW ** 2 - dt
     f = sde.f(t0, y0)
-    g_prod = sde.g(t0, y0) * dW
+    requires_grad = torch.is_grad_enabled()
     with torch.enable_grad():
-        yr = y0.detach().requires_grad_(True)
-        g = sde.g(t0, yr)
+        y = y0 if y0.requires_grad else y0.detach().requires_grad_(True)
+        g = sde.g(t0, y)
         # torchsde misc.vjp: an output outside the graph (a g built from buffers only, e.g. LatentSDE.g_aug) is made a
         # leaf first, so the vjp is "unused" -> zeros, not an error
         gdg = None
         if g.requires_grad:
-            (gdg,) = torch.autograd.grad(g, yr, grad_outputs=g.detach() * v, allow_unused=True)
+            (gdg,) = torch.autograd.grad(g, y, grad_outputs=g * v, create_graph=requires_grad, allow_unused=True)
     if gdg is None:
         gdg = torch.zeros_like(y0)
-    return y0 + f * dt + g_prod + 0.5 * gdg
+    if not requires_grad:
+        g, gdg = g.detach(), gdg.detach()
+    return y0 + f * dt + g * dW + 0.5 * gdg
 
 
 class SRID2:

@@ -859,8 +859,10 @@ int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_str
   SNSDE_API_BEGIN
   if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
   if (!p->has_weights) return fail(SNSDE_ERR_NO_WEIGHTS, "snsde_backward before snsde_plan_set_weights");
-  if (p->desc.method != SNSDE_METHOD_EULER)
-    return fail(SNSDE_ERR_UNSUPPORTED, "the backward pass is implemented for method 'euler' (the reference's training default, neuralsde.py:75)");
+  if (p->desc.method == SNSDE_METHOD_SRK)
+    return fail(SNSDE_ERR_UNSUPPORTED, "the backward pass is implemented for methods 'euler' (the reference's training default, neuralsde.py:75) and 'milstein', not 'srk'");
+  if (p->desc.method == SNSDE_METHOD_MILSTEIN && p->prog.tail.vjp_kind != 0)
+    return fail(SNSDE_ERR_UNSUPPORTED, "backward of 'milstein' through a state-dependent noise network (noise options 14, 15, 18, 19) needs second derivatives of the network: not implemented");
   if (!states_dev || !grad_states_dev || !grad_y0_dev || !grad_blob_dev) return fail(SNSDE_ERR_BAD_ARG, "states/grad_states/grad_y0/grad_blob is NULL");
   if (B < 1 || S < 0 || (S && !steps_host)) return fail(SNSDE_ERR_BAD_ARG, "bad sizes B=%d S=%d", B, S);
   const Program& pg = p->prog;

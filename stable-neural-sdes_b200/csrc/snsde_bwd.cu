@@ -1,4 +1,5 @@
-// Reverse sweep of the Euler-Maruyama solve: dL/dy0 and the per-op cotangents behind the weight gradients.
+// Reverse sweep of the Euler-Maruyama solve (and of Milstein with an elementwise diffusion): dL/dy0 and the per-op
+// cotangents behind the weight gradients.
 //
 // What it replaces: the autograd graph the reference builds through torchsde.sdeint's Python step loop
 // (/root/reference/benchmark_classification/common_sde.py:156-162 `loss.backward()` through
@@ -217,6 +218,11 @@ __global__ void __launch_bounds__(NTMAX) snsde_bwd_kernel(const BwdParams p) {
         if (t.geometric) ay += a_pre * d * (1.f - th * th);
         float ay_g, a_coef, a_sth;
         diffusion_backward(t, coef, y[r], st.t0, g, a_g, ay_g, a_coef, a_sth);
+        if (t.milstein) {                                    // y_{s+1} += 0.5 (g v) dg/dy, v = dW^2 - h  (diagonal closed form)
+          float my, mc, ms;
+          milstein_backward(t, coef, y[r], st.t0, g, __fmul_rn(w[r], w[r]) - st.h, lam[r], my, mc, ms);
+          ay_g += my; a_coef += mc; a_sth += ms;
+        }
         a_y[r] = ay + ay_g;
         acc_theta += a_sth;
         sCot[final_i * slot + r * ld + tid] = a_pre * th;           // cotangent of the drift pre-activation

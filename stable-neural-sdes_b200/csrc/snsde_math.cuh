@@ -92,6 +92,48 @@ __device__ __forceinline__ void diffusion_backward(const TailOp& t, float coef, 
   a_coef = a_raw * dc;
 }
 
+// Cotangents of the diagonal Milstein term  T = 0.5 v g dg/dy,  v = dW^2 - h  (torchsde Milstein.step with
+// ForwardSDE.gdg_prod_diagonal: vjp(g, y, grad_outputs = g v, create_graph = True) - under autograd the gradient flows
+// through BOTH factors, i.e. through the second derivative of g).  For the elementwise diffusions of neuralsde.py:233-307
+// g = tanh(s n(raw(coef, y))) [bounded] or g = raw [unbounded]; with r1 = d raw/dy, r2 = d2 raw/dy2, rc = d raw/d coef,
+// r1c = d r1/d coef and q = 1 - g^2:
+//   g'  = q s r1          g''  = -2 g g' s r1 + q s r2
+//   g_c = q s rc          g'_c = -2 g g_c s r1 + q s r1c
+//   g_s = q raw           g'_s = -2 g g_s s r1 + q r1            (s = sigmoid(theta))
+//   dT/dy = 0.5 v (g'^2 + g g''),  dT/dcoef = 0.5 v (g_c g' + g g'_c),  dT/ds = 0.5 v (g_s g' + g g'_s).
+// nan_to_num passes no gradient where raw is not finite; a g that does not depend on y has T = 0.
+__device__ __forceinline__ void milstein_backward(const TailOp& t, float coef, float y, float tt, float g, float v, float a_T,
+                                                  float& a_y, float& a_coef, float& a_sth) {
+  a_y = 0.f; a_coef = 0.f; a_sth = 0.f;
+  float raw, r1, r2 = 0.f, rc = 0.f, r1c = 0.f;
+  switch (t.special) {
+    case SP_SQRT: raw = sqrtf(y); r1 = 0.5f / raw; r2 = -0.25f / (raw * y); break;
+    case SP_CUBE: raw = y * y * y; r1 = 3.f * y * y; r2 = 6.f * y; break;
+    case SP_SIGMOID: raw = 1.f / (1.f + expf(-y)); r1 = raw * (1.f - raw); r2 = r1 * (1.f - 2.f * raw); break;
+    case SP_RELU: raw = y < 0.f ? 0.f : y; r1 = y > 0.f ? 1.f : 0.f; break;
+    case SP_NONE:
+      if (t.mult == MU_Y) { raw = coef * y; r1 = coef; rc = y; r1c = 1.f; }
+      else if (t.mult == MU_TY) { raw = tt * y; r1 = tt; }
+      else return;                                           // state-independent g: no Milstein term
+      break;
+    default: return;                                         // SP_ZERO
+  }
+  const float hv = 0.5f * v * a_T;
+  if (t.bounded) {
+    if (!is_finite_f(raw)) return;
+    const float s = t.s_theta, q = 1.f - g * g;
+    const float g1 = q * s * r1, g2 = -2.f * g * g1 * s * r1 + q * s * r2;
+    const float gc = q * s * rc, g1c = -2.f * g * gc * s * r1 + q * s * r1c;
+    const float gs = q * raw, g1s = -2.f * g * gs * s * r1 + q * r1;
+    a_y = hv * (g1 * g1 + g * g2);
+    a_coef = hv * (gc * g1 + g * g1c);
+    a_sth = hv * (gs * g1 + g * g1s);
+  } else {                                                    // g = raw
+    a_y = hv * (r1 * r1 + raw * r2);
+    a_coef = hv * (rc * r1 + raw * r1c);
+  }
+}
+
 // d act(v) / dv given the pre-activation v (LipSwish) or the activated output (ReLU: out > 0).
 __device__ __forceinline__ float act_grad(float pre, float post, int act) {
   if (act == ACT_RELU) return post > 0.f ? 1.f : 0.f;

@@ -364,9 +364,11 @@ class _SolveStates(torch.autograd.Function):
 
 
 def _states_with_grad(sde, plan, sp, y0, dW, seed, row_offset):
-    if plan.method != "euler":
+    if plan.method == "srk" or (plan.method == "milstein" and plan.desc["family"] == _lib.FAMILY_BENCHMARK
+                                and plan.desc["noise_option"] in (14, 15, 18, 19)):
         raise RuntimeError(f"snsde: the backward pass is implemented for method='euler' (the reference's training "
-                           f"default, neuralsde.py:75), not {plan.method!r}; call under torch.no_grad() for inference")
+                           f"default, neuralsde.py:75) and for 'milstein' with an elementwise diffusion, not for "
+                           f"{plan.method!r} on this model; call under torch.no_grad() for inference")
     keys = packing.grad_keys(plan.desc)
     named = dict(sde.named_parameters())
     missing = [k for k in keys if k not in named]
@@ -444,8 +446,8 @@ def sdeint(sde, y0, ts, dt=1e-3, method=None, options=None, bm=None, seed=None, 
     parameters and never calls Python ``f``/``g``.  ``method``: ``'euler'`` (default), ``'milstein'``,
     ``'srk'``.  ``options`` is accepted and ignored, as torchsde's fixed-step solvers ignore ``options['dt']``
     (neuralsde.py:39-46).  ``bm=None`` draws increments in-kernel (Philox, ``seed``);
-    ``bm=BrownianIncrements(dW[, dU])`` replays a table.  Under autograd (``method='euler'``) the result
-    carries a backward through the reverse-sweep kernel.  The tensor-core kernels flag operands beyond the
+    ``bm=BrownianIncrements(dW[, dU])`` replays a table.  Under autograd (``method='euler'``, or ``'milstein'`` with an
+    elementwise diffusion) the result carries a backward through the reverse-sweep kernel.  The tensor-core kernels flag operands beyond the
     fp16 range: the flag is polled (and raised) on the next call, or at once with ``check_range=True``
     (one stream synchronisation; the solve is then re-run on the fp32 kernel).
     """

@@ -85,6 +85,64 @@ def test_backward_matches_autograd_through_the_oracle(io, no, H, C, L, B, K, dev
         grad_close(p.grad, want, name)
 
 
+MILSTEIN_BWD_CASES = [
+    # io, no, H, C, L, B, K     state-dependent elementwise diffusions: the Milstein term carries second derivatives of g
+    (6, 17, 32, 5, 1, 9, 7), (6, 17, 64, 6, 2, 8, 6), (4, 13, 32, 4, 1, 8, 6), (5, 6, 32, 3, 1, 8, 5), (6, 3, 16, 3, 1, 8, 5),
+    (1, 8, 16, 3, 1, 8, 5), (5, 9, 16, 3, 1, 8, 5), (3, 10, 16, 3, 1, 8, 5), (1, 11, 16, 3, 1, 8, 5), (1, 7, 16, 3, 1, 8, 5),
+    # state-independent diffusions: the Milstein term vanishes, the sweep equals Euler's
+    (2, 16, 32, 4, 1, 8, 6), (4, 17, 128, 10, 1, 8, 5), (1, 0, 16, 3, 1, 8, 5), (0, 4, 16, 4, 1, 8, 5),
+]
+
+
+@pytest.mark.parametrize("io,no,H,C,L,B,K", MILSTEIN_BWD_CASES)
+def test_milstein_backward_matches_autograd_through_the_oracle(io, no, H, C, L, B, K, dev):
+    """Method 'milstein' under autograd: torchsde differentiates 0.5 * vjp(g; g (dW^2 - h)) through both factors
+    (create_graph); the engine's closed form carries the second derivative of every elementwise diffusion."""
+    m, times, coeffs, y0 = make_problem(io, no, B, H, C, L, K, seed=300 + io * 20 + no, spacing=0.5)
+    if no == 7:
+        y0 = y0.abs() + 1.5                    # sqrt(y): keep the short trajectory in the domain
+    dt = 0.5
+    S = K - 1
+    g = torch.Generator().manual_seed(11)
+    dW = torch.randn(S, B, H, generator=g) * dt ** 0.5
+    if no == 7:
+        dW = dW * 0.3
+    ts = torch.cat([times[:1], times[2:3], (times[2:3] + times[3:4]) / 2, times[-1:]])
+    w = torch.randn(len(ts), B, H, generator=g)
+    mo = copy.deepcopy(m).double()
+    mo.set_X(coeffs.double(), times.double())
+    y0o = y0.double().requires_grad_(True)
+    zo = solver.sdeint_with_grad(mo, y0o, ts.double(), dt, solver.BrownianTable(dW.double()), method="milstein")
+    (zo * w.double()).sum().backward()
+    mg = copy.deepcopy(m).to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    y0g = y0.to(dev).requires_grad_(True)
+    zg = snsde_b200.sdeint(mg, y0g, ts.to(dev), dt=dt, method="milstein", bm=snsde_b200.BrownianIncrements(dW.to(dev)),
+                           precision="fp32")
+    close(zg, zo.float())
+    (zg * w.to(dev)).sum().backward()
+    grad_close(y0g.grad, y0o.grad, "y0")
+    named_o = dict(mo.named_parameters())
+    for name, p in mg.named_parameters():
+        want = named_o[name].grad
+        if want is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        grad_close(p.grad, want, name)
+
+
+def test_milstein_backward_refuses_noise_networks_and_srk_has_no_backward(dev):
+    m, times, coeffs, y0 = make_problem(3, 18, 4, 16, 3, 1, 5, seed=1)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    for method in ("milstein", "srk"):
+        with pytest.raises(RuntimeError, match="backward"):
+            snsde_b200.sdeint(mg, y0.to(dev).requires_grad_(True), times.to(dev), dt=1.0, method=method, seed=1)
+    with torch.no_grad():                      # inference is unaffected
+        snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, method="milstein", seed=1)
+
+
 def test_backward_through_fused_final_index_and_philox_replay(dev):
     """Training path of the classification wrapper: per-row final_index capture + in-kernel Philox increments
     (the backward regenerates the same stream) vs the oracle fed the materialised increments."""
