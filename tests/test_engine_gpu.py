@@ -773,3 +773,20 @@ def test_warp_kernel_randomised_shapes_against_the_interpreter(dev, monkeypatch)
             close(a, b, rtol=5e-6)
             n_checked += 1
     assert n_checked == 72
+
+
+@pytest.mark.parametrize("method,K", [("euler", 2700), ("srk", 950)])
+def test_warp_kernel_long_trajectories_read_their_tables_from_global_memory(method, K, dev, monkeypatch):
+    """Step / emit / point tables beyond the shared-memory budget (96 KB) stay in global memory: same results."""
+    B, H, C, L = 3, 8, 2, 1
+    m, times, coeffs, y0 = make_problem(4, 17, B, H, C, L, K, seed=9, spacing=0.01)
+    dt = 0.01
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    ts = times[[0, 7, K // 2, K - 1]]
+    args = (mg, coeffs, times.to(dev), y0.to(dev), ts.to(dev), dt, method, dev)
+    a, va = _solve_with_variant(*args, True, monkeypatch, seed=3)
+    b, vb = _solve_with_variant(*args, False, monkeypatch, seed=3)
+    assert (va, vb) == ("warp", "interpreter")
+    assert torch.isfinite(a).all()
+    close(a, b, rtol=2e-5)                     # thousands of steps of fp32 re-association
