@@ -1,13 +1,14 @@
 // Warp-owned fp32 kernel for hidden sizes <= 32 (the north star's "warp-shuffle / FMA path for hidden < 64").
-// A ROW GROUP = R batch rows owned end to end by a PAIR of warps: a main warp that runs the dependent chain of a solver
+// A ROW GROUP = R batch rows (R = 1 is what ships) owned end to end by a PAIR of warps: a main warp that runs the dependent chain of a solver
 // step (the layers, the SDE update, the outputs) and a helper warp that prepares, one batch of steps ahead, everything
 // that does not depend on the state: X(t) of every row, the Brownian increments, the row-independent diffusion
 // coefficient.  Lane j = feature j; the SDE state lives in the main warp's registers.  The pair meets at one named
 // barrier per batch of 4 steps; inside a step the main warp synchronises with nobody (__syncwarp only).
 //
-// Replaces, like snsde_fma.cu, the Python step loop of torchsde.sdeint (Euler.step / Milstein.step) with the
-// per-step Diffusion_model.f/g evaluation (/root/reference/benchmark_classification/models_sde/neuralsde.py:295-307),
-// torchcde.CubicSpline.evaluate (:296) and the tutorial NeuralLSDEFunc (notebook cell 7) - for the shapes where the
+// Replaces, like snsde_fma.cu, the Python step loop of torchsde.sdeint (Euler.step / Milstein.step /
+// SRK.diagonal_or_scalar_step) with the per-step Diffusion_model.f/g evaluation
+// (/root/reference/benchmark_classification/models_sde/neuralsde.py:295-307), torchcde.CubicSpline.evaluate (:296), the
+// tutorial NeuralLSDEFunc (notebook cell 7) and LatentSDE.f_aug/g_aug (torch-ists/.../latent_sde.py:74-90) - for the shapes where the
 // interpreter kernel is pure latency: with one warp per SM sub-partition every instruction issues behind the previous
 // one (measured: ~5 cycles per instruction whatever the mix), so the time per step is the number of instructions on the
 // main warp's path.  The interpreter walks ~1700 per step through a 55 KB loop body (profiles/r2_c1_fma_kernel.txt:
@@ -29,6 +30,8 @@
 //      loaded: ptxas otherwise pairs every load with its first use): 2.17 us/step, 720 instructions per step on the
 //      main warp.  Packed FFMA2 (half the FMA instructions) measured no faster: what is left is the dependent
 //      latency chain load -> FMA chain -> reduction -> activation -> store of six layers, not issue slots.
+//      Then: hand-over batches of 4 steps (the first batch is start-up latency), cp.async staging of the image, the
+//      coefficient table cached across solves: 101-107 us per c1 solve (315 us on the interpreter kernel).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <string.h>

@@ -8,10 +8,10 @@
 
 namespace snsde {
 
-constexpr int kWarpMaxMv = 16;             // mat-vecs per step
+constexpr int kWarpMaxMv = 16;             // mat-vecs per step (the descriptors travel as a kernel parameter: every field is a
+                                           // constant-bank operand of the unrolled mat-vec slot that uses it)
 constexpr int kWarpMaxRows = 4096;         // rows per launch up to which the warp-owned kernel beats the interpreter (snsde_warp.cu)
 constexpr int kWarpDstDrift = kNumRowBufs; // pseudo-destination of the final drift op
-constexpr int kWarpMvInts = 12;            // a descriptor is read from shared memory with three 16-byte loads
 enum : int { kMvFirst = 1, kMvLast = 2, kMvSinCos = 4, kMvDiff = 8 };
 
 // One mat-vec of at most 32 x 32:  acc (+)= sum_k act_src[k] * W[lane][k], K padded to 8 * n8 with zero weights.
@@ -27,9 +27,7 @@ struct WarpMv {
   int dst;          // activation row written, or kWarpDstDrift
   int act;
   int b_off, tw_off; // 32-float bias row; sin row followed by the cos row (time features)
-  int pad0, pad1;
 };
-static_assert(sizeof(WarpMv) == kWarpMvInts * 4, "descriptor layout");
 
 struct WarpProg {
   int n_mv;
