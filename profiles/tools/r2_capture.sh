@@ -10,7 +10,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 $NCU -k regex:snsde_tc_kernel -s 4 -c 1 -o $O/r2_c2_tc python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs > /dev/null 2>&1
 $NCU -k regex:snsde_tcg_kernel -s 4 -c 1 -o $O/r2_c4_tcg python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 $NCU -k regex:snsde_tcg_kernel -s 4 -c 1 -o $O/r2_c5_tcg python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-$NCU -k regex:snsde_fma_kernel -s 4 -c 1 -o $O/r2_c1_fma python bench.py --workload c1 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+SNSDE_NO_WARP=1 $NCU -k regex:snsde_fma_kernel -s 4 -c 1 -o $O/r2_c1_fma python bench.py --workload c1 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+$NCU -k regex:snsde_warp_kernel -s 4 -c 1 -o $O/r2_c1_warp python bench.py --workload c1 --steps 2 --warmup 3 --no-cpu-baseline --no-configs > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/r2_launches_c1.csv python bench.py --workload c1 --no-configs --no-cpu-baseline --steps 5 --warmup 3 > /dev/null 2>&1
 $NCU -k regex:snsde_bwd_kernel -s 1 -c 1 -o $O/r2_c2_bwd python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 # clock64 trace of the resident kernel (trace build)
 SNSDE_TRACE_BUILD=1 SNSDE_TC_TRACE=$O/r2_trace_c2.txt python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > /dev/null 2>&1

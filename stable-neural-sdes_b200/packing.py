@@ -85,4 +85,6 @@ def pack(sde, desc):
 
 
 def weights_version(sde):
-    return tuple((p.data_ptr(), p._version) for p in sde.parameters())
+    """Changes whenever a tensor of the weight blob is updated in place or replaced (buffers included: the LatentSDE
+    prior's theta / mu / sigma are buffers)."""
+    return tuple((p.data_ptr(), p._version) for p in list(sde.parameters()) + list(sde.buffers()))
