@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SNSDE_ABI_VERSION 3
+#define SNSDE_ABI_VERSION 4
 
 typedef enum {
   SNSDE_OK = 0,
@@ -189,9 +189,10 @@ int snsde_plan_status_nowait(snsde_plan* plan);
 /* ---- backward pass through the solve -------------------------------------------------------------
  * Replaces the autograd graph the reference builds through torchsde.sdeint when it trains
  * (benchmark_classification/common_sde.py:156-162: `pred_y = model(...); loss.backward()`;
- * benchmark_forecasting/common_sde.py:145-150).  Methods euler and milstein (the latter for the elementwise diffusions:
- * every noise option but 14, 15, 18, 19; its diagonal term 0.5 (g v) dg/dy is differentiated through both factors, as
- * torchsde's create_graph vjp is).
+ * benchmark_forecasting/common_sde.py:145-150).  Methods euler, milstein (for the elementwise diffusions: every noise
+ * option but 14, 15, 18, 19; its diagonal term 0.5 (g v) dg/dy is differentiated through both factors, as torchsde's
+ * create_graph vjp is) and srk (points_host as in snsde_forward; dU_dev beside dW_dev in table mode) - the default
+ * method of the torch-ists wrappers (nsde_model.py:63-74, latent_sde.py:107-109).
  *
  * Protocol: run snsde_forward with a step plan that emits EVERY solver state (slot s+1 = state after step s;
  * out_dev = states [S+1, B, H]); form the requested outputs from those states (linear interpolation / per-row
@@ -209,9 +210,9 @@ int snsde_plan_status_nowait(snsde_plan* plan);
 int64_t snsde_backward_workspace_bytes(const snsde_plan* plan, int32_t B, int32_t S);
 int snsde_backward(snsde_plan* plan,
                    const float* coeffs_dev, int64_t coeff_row_stride, int32_t n_knots, int32_t B,
-                   const snsde_step* steps_host, int32_t S,
+                   const snsde_step* steps_host, int32_t S, const snsde_point* points_host,
                    const float* states_dev, const float* grad_states_dev,
-                   const float* dW_dev, uint64_t seed, uint64_t row_offset,
+                   const float* dW_dev, const float* dU_dev, uint64_t seed, uint64_t row_offset,
                    float* grad_y0_dev, float* grad_blob_dev,
                    void* workspace_dev, int64_t workspace_bytes, void* stream);
 

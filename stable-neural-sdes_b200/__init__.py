@@ -4,7 +4,7 @@ Public surface (mirrors the reference's operator interface for this path):
     sdeint(sde, y0, ts, dt, method=..., bm=..., seed=...)   -> [len(ts), B, H]
     solve_final(sde, times, final_index, z0, ...)            -> [B, H]   (fused gather)
     patch(model)                                             -> swaps the engine into any of the reference's three NeuralSDE wrappers
-    (under autograd, 'euler' and elementwise-diffusion 'milstein': backward through the reverse-sweep kernel; methods euler / milstein / srk;
+    (under autograd, 'euler', 'srk' and elementwise-diffusion 'milstein': backward through the reverse-sweep kernels; methods euler / milstein / srk;
      a LatentSDE is patched / solved as its augmented system)
     BrownianIncrements(dW), philox_increments(...), Plan, build_step_plan, dist helpers
 """

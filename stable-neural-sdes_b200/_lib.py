@@ -7,7 +7,7 @@ import os
 LIB_PATH = HERE / ("libsnsde_trace.so" if os.environ.get("SNSDE_TRACE_BUILD") else "libsnsde.so")
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_WEIGHTS, ERR_INTERNAL = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 3
+ABI_VERSION = 4
 FAMILY_BENCHMARK, FAMILY_TUTORIAL_LSDE, FAMILY_LATENT_SDE = 0, 1, 2
 METHOD = {"euler": 0, "milstein": 1, "srk": 2}
 PRECISION = {"fp32": 0, "tc": 1, "auto": 2}
@@ -81,7 +81,7 @@ def load():
     lib.snsde_philox_fill.argtypes = [u64, u64, i32, i32, i32, vp, vp, vp, ctypes.c_int, vp]
     lib.snsde_backward_workspace_bytes.restype = i64
     lib.snsde_backward_workspace_bytes.argtypes = [vp, i32, i32]
-    lib.snsde_backward.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, vp, vp, u64, u64, vp, vp, vp, i64, vp]
+    lib.snsde_backward.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, vp, vp, vp, vp, u64, u64, vp, vp, vp, i64, vp]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.snsde_abi_version() != ABI_VERSION:

@@ -805,34 +805,43 @@ int snsde_forward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stri
 
 // ---- backward -----------------------------------------------------------------------------------
 struct BwdLayout {
-  size_t aux = 0, xbuf = 0, gvtab = 0, vtab = 0, total = 0;     // float offsets
+  size_t aux = 0, aux_g = 0, xbuf = 0, gvtab = 0, vtab = 0, pstate_f = 0, pstate_g = 0, total = 0;     // float offsets
   size_t dbuf[kMaxOps], pbuf[kMaxOps];
   int n_rops = 0; int rop[kMaxOps];
-  bool has_lipswish = false;
+  bool has_lipswish = false, has_g_ops = false;
 };
-static BwdLayout bwd_layout(const Program& pg, int B, int S) {
+// srk: every per-row buffer carries one block of S*B rows per evaluation site of the op's part (drift: 3, diffusion: 4)
+static BwdLayout bwd_layout(const Program& pg, int B, int S, bool srk) {
   BwdLayout L;
   const size_t SB = (size_t)S * B;
+  const size_t nf = srk ? 3 : 1, ng = srk ? 4 : 1, nv = srk ? kSrkGPoints : 1;
   auto take = [&](size_t n) { const size_t o = L.total; L.total += (n + 3) & ~(size_t)3; return o; };
-  L.aux = take(SB * 3);
-  L.xbuf = pg.uses_control ? take(SB * pg.C) : 0;
-  L.vtab = take((size_t)S * pg.H);
-  L.gvtab = take((size_t)S * pg.H);
+  L.aux = take(nf * SB * 3);
+  L.xbuf = pg.uses_control ? take(nf * SB * pg.C) : 0;
+  L.vtab = take((size_t)S * nv * pg.H);
+  L.gvtab = take((size_t)S * nv * pg.H);
   bool consumed[kMaxOps] = {false};
   for (int o = 0; o < pg.n_ops; ++o) {
     const DenseOp& op = pg.ops[o];
     if (op.vec) continue;
+    if (op.part == 1) L.has_g_ops = true;
     if (op.src_op >= 0) consumed[op.src_op] = true;
     if (op.src2 >= 0 && op.src2_op >= 0) consumed[op.src2_op] = true;
     if (op.act == ACT_LIPSWISH) L.has_lipswish = true;
+  }
+  if (srk) {
+    L.aux_g = take(ng * SB * 3);
+    L.pstate_f = take(nf * SB * pg.H);
+    if (L.has_g_ops) L.pstate_g = take(ng * SB * pg.H);
   }
   for (int o = 0; o < pg.n_ops; ++o) {
     const DenseOp& op = pg.ops[o];
     L.dbuf[o] = L.pbuf[o] = (size_t)-1;
     if (op.vec) continue;
+    const size_t ns = op.part == 1 ? ng : nf;
     L.rop[L.n_rops++] = o;
-    L.dbuf[o] = take(SB * op.N);
-    if (consumed[o]) L.pbuf[o] = take(SB * op.N);
+    L.dbuf[o] = take(ns * SB * op.N);
+    if (consumed[o]) L.pbuf[o] = take(ns * SB * op.N);
   }
   return L;
 }
@@ -841,7 +850,7 @@ int64_t snsde_backward_workspace_bytes(const snsde_plan* p, int32_t B, int32_t S
   SNSDE_API_BEGIN
   if (!p || !p->has_weights) return fail(SNSDE_ERR_NO_WEIGHTS, "plan has no weights");
   if (B < 1 || S < 0) return fail(SNSDE_ERR_BAD_ARG, "bad sizes B=%d S=%d", B, S);
-  return (int64_t)(bwd_layout(p->prog, B, S).total * sizeof(float));
+  return (int64_t)(bwd_layout(p->prog, B, S, p->desc.method == SNSDE_METHOD_SRK).total * sizeof(float));
   SNSDE_API_END(SNSDE_ERR_INTERNAL)
 }
 
@@ -852,15 +861,17 @@ int64_t snsde_backward_workspace_bytes(const snsde_plan* p, int32_t B, int32_t S
   } while (0)
 
 int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_stride, int32_t n_knots, int32_t B,
-                   const snsde_step* steps_host, int32_t S, const float* states_dev, const float* grad_states_dev,
-                   const float* dW_dev, uint64_t seed, uint64_t row_offset,
+                   const snsde_step* steps_host, int32_t S, const snsde_point* points_host,
+                   const float* states_dev, const float* grad_states_dev,
+                   const float* dW_dev, const float* dU_dev, uint64_t seed, uint64_t row_offset,
                    float* grad_y0_dev, float* grad_blob_dev, void* workspace_dev, int64_t workspace_bytes,
                    void* stream_v) {
   SNSDE_API_BEGIN
   if (!p) return fail(SNSDE_ERR_BAD_ARG, "plan is NULL");
   if (!p->has_weights) return fail(SNSDE_ERR_NO_WEIGHTS, "snsde_backward before snsde_plan_set_weights");
-  if (p->desc.method == SNSDE_METHOD_SRK)
-    return fail(SNSDE_ERR_UNSUPPORTED, "the backward pass is implemented for methods 'euler' (the reference's training default, neuralsde.py:75) and 'milstein', not 'srk'");
+  const bool srk = p->desc.method == SNSDE_METHOD_SRK;
+  if (srk && S && !points_host) return fail(SNSDE_ERR_BAD_ARG, "method srk needs the per-step evaluation points");
+  if (srk && dW_dev && !dU_dev) return fail(SNSDE_ERR_BAD_ARG, "method srk with explicit increments needs dU beside dW");
   if (p->desc.method == SNSDE_METHOD_MILSTEIN && p->prog.tail.vjp_kind != 0)
     return fail(SNSDE_ERR_UNSUPPORTED, "backward of 'milstein' through a state-dependent noise network (noise options 14, 15, 18, 19) needs second derivatives of the network: not implemented");
   if (!states_dev || !grad_states_dev || !grad_y0_dev || !grad_blob_dev) return fail(SNSDE_ERR_BAD_ARG, "states/grad_states/grad_y0/grad_blob is NULL");
@@ -870,7 +881,11 @@ int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_str
   if (rc != SNSDE_OK) return rc;
   rc = validate_steps(pg, n_knots, steps_host, S);
   if (rc != SNSDE_OK) return rc;
-  const BwdLayout L = bwd_layout(pg, B, S);
+  if (srk && pg.uses_control)
+    for (int i = 0; i < S * kSrkPoints; ++i)
+      if (points_host[i].interval < 0 || points_host[i].interval > n_knots - 2)
+        return fail(SNSDE_ERR_BAD_ARG, "point %d: spline interval %d outside [0,%d]", i, points_host[i].interval, n_knots - 2);
+  const BwdLayout L = bwd_layout(pg, B, S, srk);
   if (workspace_bytes < (int64_t)(L.total * sizeof(float)) || (L.total && !workspace_dev))
     return fail(SNSDE_ERR_BAD_ARG, "workspace has %lld bytes, snsde_backward_workspace_bytes says %lld", (long long)workspace_bytes, (long long)(L.total * sizeof(float)));
   if ((uintptr_t)workspace_dev & 15) return fail(SNSDE_ERR_BAD_ARG, "workspace must be 16-byte aligned");
@@ -885,9 +900,10 @@ int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_str
     CUDA_TRY(cudaMemcpyAsync(grad_y0_dev, grad_states_dev, sizeof(float) * (size_t)B * pg.H, cudaMemcpyDeviceToDevice, stream));
     return SNSDE_OK;
   }
-  rc = upload_tables(p, steps_host, S, nullptr, 0, nullptr, stream);
+  rc = upload_tables(p, steps_host, S, nullptr, 0, srk ? points_host : nullptr, stream);
   if (rc != SNSDE_OK) return rc;
   float* ws = (float*)workspace_dev;
+  const int nf = srk ? 3 : 1, ng = srk ? 4 : 1, nv = srk ? kSrkGPoints : 1;
 
   BwdParams bp;
   memset(&bp, 0, sizeof(bp));
@@ -895,7 +911,10 @@ int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_str
   bp.wimg = p->d_wimg; bp.wimg_floats = p->wimg_floats; bp.blob = p->d_blob;
   bp.coeffs = coeffs_dev; bp.coeff_row_stride = coeff_row_stride;
   bp.B = B; bp.S = S; bp.steps = p->d_steps;
-  bp.states = states_dev; bp.grad_states = grad_states_dev; bp.dW = dW_dev; bp.seed = seed; bp.row_offset = row_offset;
+  bp.states = states_dev; bp.grad_states = grad_states_dev; bp.dW = dW_dev; bp.dU = dU_dev; bp.seed = seed; bp.row_offset = row_offset;
+  bp.points = srk ? p->d_points : nullptr;
+  bp.pstate_f = srk ? ws + L.pstate_f : nullptr;
+  bp.pstate_g = (srk && L.has_g_ops) ? ws + L.pstate_g : nullptr;
   bp.grad_y0 = grad_y0_dev; bp.grad_blob = grad_blob_dev;
   bp.xbuf = pg.uses_control ? ws + L.xbuf : nullptr;
   bp.n_rops = L.n_rops; bp.has_lipswish = L.has_lipswish;
@@ -906,24 +925,27 @@ int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_str
   }
   const bool vbuf = pg.tail.coef_src == CO_VBUF;
   if (vbuf) {
-    cudaError_t e = vec_tables_launch(pg, p->d_wimg, p->d_steps, nullptr, S, 1, ws + L.vtab, stream);
+    cudaError_t e = vec_tables_launch(pg, p->d_wimg, p->d_steps, bp.points, S, nv, ws + L.vtab, stream);
     if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "coefficient table kernel launch: %s", cudaGetErrorString(e));
-    CUDA_TRY(cudaMemsetAsync(ws + L.gvtab, 0, sizeof(float) * (size_t)S * pg.H, stream));
+    CUDA_TRY(cudaMemsetAsync(ws + L.gvtab, 0, sizeof(float) * (size_t)S * nv * pg.H, stream));
     bp.vtab = ws + L.vtab; bp.gvtab = ws + L.gvtab;
     p->launches += 1;
   }
   GroupConfig gc;
-  if (!pick_group_config(p, B, [&](int R) { return bwd_group_smem_floats(pg, L.n_rops, R, L.has_lipswish); }, false, gc))   // 8 rows per group measured slower (13.5 vs 10.8 ms at c2)
+  auto group_floats = [&](int R) {
+    return srk ? bwd_srk_group_smem_floats(pg, L.n_rops, R, L.has_lipswish) : bwd_group_smem_floats(pg, L.n_rops, R, L.has_lipswish);
+  };
+  if (!pick_group_config(p, B, group_floats, false, gc))   // 8 rows per group measured slower (13.5 vs 10.8 ms at c2)
     return fail(SNSDE_ERR_UNSUPPORTED, "the backward pass keeps every activation of a step in shared memory: hidden size too large (%zu bytes per row group)",
-                bwd_group_smem_floats(pg, L.n_rops, 1, L.has_lipswish) * sizeof(float));
+                group_floats(1) * sizeof(float));
   bp.groups = gc.groups; bp.nw = gc.nw; bp.smem_w_floats = gc.smem_w_floats;
-  cudaError_t e = bwd_fill_aux(p->d_steps, S, B, ws + L.aux, stream);
+  cudaError_t e = srk ? bwd_srk_fill_aux(p->d_points, S, B, ws + L.aux, ws + L.aux_g, stream) : bwd_fill_aux(p->d_steps, S, B, ws + L.aux, stream);
   if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "aux kernel launch: %s", cudaGetErrorString(e));
-  e = bwd_launch(bp, gc.R, gc.smem, stream);
+  e = srk ? bwd_srk_launch(bp, gc.R, gc.smem, stream) : bwd_launch(bp, gc.R, gc.smem, stream);
   if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "reverse-sweep kernel launch (nw=%d groups=%d smem=%zu): %s", gc.nw, gc.groups, gc.smem, cudaGetErrorString(e));
   p->launches += 2;
   if (vbuf) {
-    e = vec_bwd_launch(pg, p->d_wimg, p->d_blob, p->d_steps, S, ws + L.gvtab, grad_blob_dev, stream);
+    e = vec_bwd_launch(pg, p->d_wimg, p->d_blob, p->d_steps, bp.points, S, nv, ws + L.gvtab, grad_blob_dev, stream);
     if (e != cudaSuccess) return fail(SNSDE_ERR_CUDA, "coefficient-network backward launch: %s", cudaGetErrorString(e));
     p->launches += 1;
   }
@@ -934,27 +956,30 @@ int snsde_backward(snsde_plan* p, const float* coeffs_dev, int64_t coeff_row_str
   CUBLAS_TRY(cublasSetMathMode(p->cublas, CUBLAS_PEDANTIC_MATH));                  // fp32 accumulate, no TF32
   const int SB = S * B;
   const float one = 1.f;
-  // C'[K x N] (ldc = ldw: the [N][ldw] blob rows) += P'[K x SB] (lda) * D'[N x SB]^T (ldb = N)
-  auto gemm = [&](const float* P, int lda, int K, const float* D, int N, float* C, int ldc) -> cublasStatus_t {
-    return cublasSgemm(p->cublas, CUBLAS_OP_N, CUBLAS_OP_T, K, N, SB, &one, P, lda, D, N, &one, C, ldc);
+  // C'[K x N] (ldc = ldw: the [N][ldw] blob rows) += P'[K x M] (lda) * D'[N x M]^T (ldb = N); M = rows of all the op's sites
+  auto gemm = [&](int M, const float* P, int lda, int K, const float* D, int N, float* C, int ldc) -> cublasStatus_t {
+    return cublasSgemm(p->cublas, CUBLAS_OP_N, CUBLAS_OP_T, K, N, M, &one, P, lda, D, N, &one, C, ldc);
   };
   for (int i = 0; i < L.n_rops; ++i) {
     const int o = L.rop[i];
     const DenseOp& op = pg.ops[o];
     const float* D = bp.dbuf[o];
     float* gW = grad_blob_dev + op.g_w;
+    const bool gpart = op.part == 1;
+    const int M = (gpart ? ng : nf) * SB;
+    const float* aux = ws + ((srk && gpart) ? L.aux_g : L.aux);
     for (int part = 0; part < 2; ++part) {
       const int src = part == 0 ? op.src : op.src2, src_op = part == 0 ? op.src_op : op.src2_op;
       const int K = part == 0 ? op.K : op.K2, col = part == 0 ? op.g_col : op.g_col2;
       if (src < 0) continue;
       const float* P; int lda;
-      if (src_op == SRC_STATE) { P = states_dev; lda = pg.H; }
+      if (src_op == SRC_STATE) { P = srk ? (gpart ? bp.pstate_g : bp.pstate_f) : states_dev; lda = pg.H; }
       else if (src_op == SRC_CONTROL) { P = bp.xbuf; lda = pg.C; }
       else { P = bp.pbuf[src_op]; lda = pg.ops[src_op].N; }
-      CUBLAS_TRY(gemm(P, lda, K, D, op.N, gW + col, op.g_ldw));
+      CUBLAS_TRY(gemm(M, P, lda, K, D, op.N, gW + col, op.g_ldw));
     }
-    if (op.tmode == TM_SINCOS) CUBLAS_TRY(gemm(ws + L.aux, 3, 2, D, op.N, gW, op.g_ldw));
-    if (op.g_b >= 0) CUBLAS_TRY(gemm(ws + L.aux + 2, 3, 1, D, op.N, grad_blob_dev + op.g_b, 1));
+    if (op.tmode == TM_SINCOS) CUBLAS_TRY(gemm(M, aux, 3, 2, D, op.N, gW, op.g_ldw));
+    if (op.g_b >= 0) CUBLAS_TRY(gemm(M, aux + 2, 3, 1, D, op.N, grad_blob_dev + op.g_b, 1));
   }
   return SNSDE_OK;
   SNSDE_API_END(SNSDE_ERR_INTERNAL)

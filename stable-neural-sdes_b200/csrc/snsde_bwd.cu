@@ -304,14 +304,19 @@ __global__ void __launch_bounds__(NTMAX) snsde_bwd_kernel(const BwdParams p) {
 __global__ void __launch_bounds__(1024) vec_bwd_kernel(const Program pg, const float* __restrict__ wimg,
                                                        const float* __restrict__ blob,
                                                        const snsde_step* __restrict__ steps,
+                                                       const snsde_point* __restrict__ points, int npg,
                                                        const float* __restrict__ gvtab, float* __restrict__ grad_blob) {
   extern __shared__ __align__(16) float vsm[];          // post[kMaxOps][ld] pre[kMaxOps][ld] cot[kMaxOps][ld] dlt[ld]
-  const int s = blockIdx.x, j = threadIdx.x, ld = pg.ld;
+  const int s = blockIdx.x / npg, q = blockIdx.x - s * npg, j = threadIdx.x, ld = pg.ld;
   float* const post = vsm;
   float* const pre = vsm + kMaxOps * ld;
   float* const cot = vsm + 2 * kMaxOps * ld;
   float* const dlt = vsm + 3 * kMaxOps * ld;
-  const snsde_step st = steps[s];
+  snsde_step st = steps[s];
+  if (points != nullptr) {                                 // SRK: coefficient rows at t0, t0+h/4, t0+h
+    const snsde_point pt = points[s * kSrkPoints + (q == 0 ? 0 : (q == 1 ? 1 : 3))];
+    st.t0 = pt.t; st.sin_t0 = pt.sin_t; st.cos_t0 = pt.cos_t;
+  }
   int last = -1;
   for (int o = 0; o < pg.n_ops; ++o) {
     const DenseOp& op = pg.ops[o];
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(1024) vec_bwd_kernel(const Program pg, const f
     __syncthreads();
   }
   if (last < 0) return;
-  if (j < pg.ops[last].N) cot[last * ld + j] = gvtab[(size_t)s * pg.H + j];
+  if (j < pg.ops[last].N) cot[last * ld + j] = gvtab[(size_t)blockIdx.x * pg.H + j];
   for (int o = pg.n_ops - 1; o >= 0; --o) {
     const DenseOp& op = pg.ops[o];
     if (!op.vec) continue;
@@ -408,14 +413,14 @@ cudaError_t bwd_fill_aux(const snsde_step* steps, int S, int B, float* aux, cuda
   return cudaGetLastError();
 }
 
-cudaError_t vec_bwd_launch(const Program& pg, const float* wimg, const float* blob, const snsde_step* steps, int S,
-                           const float* gvtab, float* grad_blob, cudaStream_t stream) {
+cudaError_t vec_bwd_launch(const Program& pg, const float* wimg, const float* blob, const snsde_step* steps,
+                           const snsde_point* points, int S, int npg, const float* gvtab, float* grad_blob, cudaStream_t stream) {
   if (S == 0) return cudaSuccess;
   const int nt = std::max(32, (std::max(pg.H, pg.HH) + 31) & ~31);
   const size_t smem = sizeof(float) * (size_t)(3 * kMaxOps + 1) * pg.ld;
   cudaError_t e = cudaFuncSetAttribute(vec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  vec_bwd_kernel<<<S, nt, smem, stream>>>(pg, wimg, blob, steps, gvtab, grad_blob);
+  vec_bwd_kernel<<<S * npg, nt, smem, stream>>>(pg, wimg, blob, steps, points, npg, gvtab, grad_blob);
   return cudaGetLastError();
 }
 

@@ -34,6 +34,12 @@ struct BwdParams {
   int rop[kMaxOps];           // their program indices, in program order
   int groups, nw;
   int has_lipswish;           // keep pre-activations too (tutorial family)
+  // ---- method 'srk' (snsde_bwd_srk.cu): D / P / xbuf carry one block of S*B rows per evaluation site of the op's part
+  // (drift sites f0, f1, f2; diffusion sites g0, g1, g2, g3); vtab / gvtab are [S][kSrkGPoints][H]
+  const snsde_point* points;  // [S][kSrkPoints]
+  const float* dU;            // explicit space-time Levy integrals [S][B][H] (with dW) or null
+  float* pstate_f;            // [3*S*B][H] states the drift sites were evaluated at (GEMM operand of ops that read the state)
+  float* pstate_g;            // [4*S*B][H] states of the diffusion sites, or null (no per-row diffusion network)
 };
 
 size_t bwd_group_smem_floats(const Program& pg, int n_rops, int R, int has_lipswish);
@@ -41,7 +47,12 @@ cudaError_t bwd_launch(const BwdParams& p, int R, size_t smem, cudaStream_t stre
 // aux[i] = (sin t_s, cos t_s, 1) for i = s*B + b: the "activations" behind the time-feature columns and the biases
 cudaError_t bwd_fill_aux(const snsde_step* steps, int S, int B, float* aux, cudaStream_t stream);
 // backward of the row-independent coefficient networks (vec ops): one CTA per step, atomics into grad_blob
-cudaError_t vec_bwd_launch(const Program& pg, const float* wimg, const float* blob, const snsde_step* steps, int S,
-                           const float* gvtab, float* grad_blob, cudaStream_t stream);
+// (points != null: method 'srk', npg = kSrkGPoints coefficient rows per step at t0, t0+h/4, t0+h)
+cudaError_t vec_bwd_launch(const Program& pg, const float* wimg, const float* blob, const snsde_step* steps,
+                           const snsde_point* points, int S, int npg, const float* gvtab, float* grad_blob, cudaStream_t stream);
+// method 'srk'
+size_t bwd_srk_group_smem_floats(const Program& pg, int n_rops, int R, int has_lipswish);
+cudaError_t bwd_srk_launch(const BwdParams& p, int R, size_t smem, cudaStream_t stream);
+cudaError_t bwd_srk_fill_aux(const snsde_point* points, int S, int B, float* aux_f, float* aux_g, cudaStream_t stream);
 
 }  // namespace snsde

@@ -15,8 +15,8 @@ the reference's three wrappers at the ``_solve_sde_path`` seam:
   (which calls ``torchsde.sdeint_adjoint`` on the augmented system inline) is replaced.
 
 Training: under autograd the solve saves every solver state and the backward pass runs the
-reverse-sweep kernel behind ``snsde_backward`` (the reference back-propagates through
-torchsde's step loop, benchmark_classification/common_sde.py:156-162).
+reverse-sweep kernels behind ``snsde_backward`` (Euler, SRK, Milstein with an elementwise diffusion; the
+reference back-propagates through torchsde's step loop, benchmark_classification/common_sde.py:156-162).
 
 PyTorch is plumbing here (device memory, streams, the autograd hook); all arithmetic of the path
 runs in the CUDA kernels behind include/snsde.h.  There is no CPU/eager fallback.
@@ -228,7 +228,7 @@ class Plan:
             _ptr(out), ctypes.c_void_p(stream)))
         return out
 
-    def backward(self, states, grad_states, plan, coeffs=None, dW=None, seed=0, row_offset=0):
+    def backward(self, states, grad_states, plan, coeffs=None, dW=None, dU=None, seed=0, row_offset=0):
         """Reverse sweep (``snsde_backward``): ``states``/``grad_states`` are ``[S+1, B, H]``.  Returns
         ``(grad_y0 [B, H], grad_blob [n_weights])``."""
         dev, H = self.device, self.hidden
@@ -243,14 +243,25 @@ class Plan:
             raise ValueError("snsde: grad_states must have the shape of states")
         if dW is not None:
             dW = dW.detach().to(device=dev, dtype=torch.float32).contiguous()
+        points = None
+        if self.method == "srk":
+            if plan.points is None:
+                raise ValueError("snsde: method 'srk' needs a step plan built with method='srk'")
+            points = ctypes.c_void_p(plan.points.ctypes.data)
+            if dW is not None:
+                if dU is None:
+                    raise ValueError("snsde: method 'srk' with explicit increments needs dU beside dW")
+                dU = dU.detach().to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            dU = None
         nbytes = _lib.check(self.lib.snsde_backward_workspace_bytes(self._h, B, S))
         ws = torch.empty((nbytes + 3) // 4, device=dev, dtype=torch.float32)
         gy0 = torch.empty((B, H), device=dev, dtype=torch.float32)
         gblob = torch.empty(self.n_weights, device=dev, dtype=torch.float32)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.snsde_backward(
-            self._h, _ptr(coeffs), stride, plan.n_knots, B, ctypes.c_void_p(plan.steps.ctypes.data), S,
-            _ptr(states), _ptr(grad_states), _ptr(dW), ctypes.c_uint64(seed & (2 ** 64 - 1)),
+            self._h, _ptr(coeffs), stride, plan.n_knots, B, ctypes.c_void_p(plan.steps.ctypes.data), S, points,
+            _ptr(states), _ptr(grad_states), _ptr(dW), _ptr(dU if dW is not None else None), ctypes.c_uint64(seed & (2 ** 64 - 1)),
             ctypes.c_uint64(row_offset), _ptr(gy0), _ptr(gblob), _ptr(ws), ws.numel() * 4, ctypes.c_void_p(stream)))
         return gy0, gblob
 
@@ -342,9 +353,9 @@ class _SolveStates(torch.autograd.Function):
     outputs are formed from the states by differentiable indexing (lerp / per-row capture) outside."""
 
     @staticmethod
-    def forward(ctx, plan, sp, coeffs, dW, seed, row_offset, keys, y0, *params):
-        states = plan.forward(y0, sp.dense(), coeffs=coeffs, dW=dW, seed=seed, row_offset=row_offset)
-        ctx.plan, ctx.sp, ctx.coeffs, ctx.dW, ctx.seed, ctx.row_offset = plan, sp, coeffs, dW, seed, row_offset
+    def forward(ctx, plan, sp, coeffs, dW, dU, seed, row_offset, keys, y0, *params):
+        states = plan.forward(y0, sp.dense(), coeffs=coeffs, dW=dW, dU=dU, seed=seed, row_offset=row_offset)
+        ctx.plan, ctx.sp, ctx.coeffs, ctx.dW, ctx.dU, ctx.seed, ctx.row_offset = plan, sp, coeffs, dW, dU, seed, row_offset
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.dtypes = [p.dtype for p in params]
         ctx.save_for_backward(states)
@@ -353,29 +364,28 @@ class _SolveStates(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_states):
         (states,) = ctx.saved_tensors
-        gy0, gblob = ctx.plan.backward(states, grad_states, ctx.sp, coeffs=ctx.coeffs, dW=ctx.dW, seed=ctx.seed,
+        gy0, gblob = ctx.plan.backward(states, grad_states, ctx.sp, coeffs=ctx.coeffs, dW=ctx.dW, dU=ctx.dU, seed=ctx.seed,
                                        row_offset=ctx.row_offset)
         grads, off = [], 0
         for shape, dtype in zip(ctx.shapes, ctx.dtypes):
             n = int(np.prod(shape)) if shape else 1
             grads.append(gblob[off:off + n].view(shape).to(dtype))
             off += n
-        return (None, None, None, None, None, None, None, gy0, *grads)
+        return (None, None, None, None, None, None, None, None, gy0, *grads)
 
 
-def _states_with_grad(sde, plan, sp, y0, dW, seed, row_offset):
-    if plan.method == "srk" or (plan.method == "milstein" and plan.desc["family"] == _lib.FAMILY_BENCHMARK
-                                and plan.desc["noise_option"] in (14, 15, 18, 19)):
-        raise RuntimeError(f"snsde: the backward pass is implemented for method='euler' (the reference's training "
-                           f"default, neuralsde.py:75) and for 'milstein' with an elementwise diffusion, not for "
-                           f"{plan.method!r} on this model; call under torch.no_grad() for inference")
+def _states_with_grad(sde, plan, sp, y0, dW, dU, seed, row_offset):
+    if plan.method == "milstein" and plan.desc["family"] == _lib.FAMILY_BENCHMARK and plan.desc["noise_option"] in (14, 15, 18, 19):
+        raise RuntimeError("snsde: the backward pass is implemented for methods 'euler', 'srk' and for 'milstein' with an "
+                           "elementwise diffusion - not for 'milstein' through a state-dependent noise network (second "
+                           "derivatives of the network); call under torch.no_grad() for inference")
     keys = packing.grad_keys(plan.desc)
     named = dict(sde.named_parameters())
     missing = [k for k in keys if k not in named]
     if missing:
         raise ValueError(f"snsde: parameters {missing} not found on the SDE module")
     params = [named[k] for k in keys]
-    return _SolveStates.apply(plan, sp, getattr(sde, "coeffs", None), dW, seed, row_offset, keys, y0, *params)
+    return _SolveStates.apply(plan, sp, getattr(sde, "coeffs", None), dW, dU, seed, row_offset, keys, y0, *params)
 
 
 def _select_outputs(states, sp):
@@ -421,7 +431,7 @@ def _solve(sde, plan, sp, y0, row_slot, bm, seed, row_offset, out, check_range):
     seed = seed or 0
     coeffs = getattr(sde, "coeffs", None)
     if _wants_grad(sde, y0):
-        states = _states_with_grad(sde, plan, sp, y0, dW, seed, row_offset)
+        states = _states_with_grad(sde, plan, sp, y0, dW, dU, seed, row_offset)
         res = _select_outputs(states, sp) if row_slot is None else _select_rows(states, sp, row_slot)
         if out is not None:
             raise ValueError("snsde: out= is not supported under autograd")
@@ -446,8 +456,8 @@ def sdeint(sde, y0, ts, dt=1e-3, method=None, options=None, bm=None, seed=None, 
     parameters and never calls Python ``f``/``g``.  ``method``: ``'euler'`` (default), ``'milstein'``,
     ``'srk'``.  ``options`` is accepted and ignored, as torchsde's fixed-step solvers ignore ``options['dt']``
     (neuralsde.py:39-46).  ``bm=None`` draws increments in-kernel (Philox, ``seed``);
-    ``bm=BrownianIncrements(dW[, dU])`` replays a table.  Under autograd (``method='euler'``, or ``'milstein'`` with an
-    elementwise diffusion) the result carries a backward through the reverse-sweep kernel.  The tensor-core kernels flag operands beyond the
+    ``bm=BrownianIncrements(dW[, dU])`` replays a table.  Under autograd (``'euler'``, ``'srk'``, or ``'milstein'`` with an
+    elementwise diffusion) the result carries a backward through the reverse-sweep kernels.  The tensor-core kernels flag operands beyond the
     fp16 range: the flag is polled (and raised) on the next call, or at once with ``check_range=True``
     (one stream synchronisation; the solve is then re-run on the fp32 kernel).
     """
@@ -682,7 +692,7 @@ def _forward_latent(self, coeffs, times, **kwargs):
     """``LatentSDE.forward`` (torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:92-147): the augmented system
     (posterior drift + KL path accumulator) is one engine solve; returns ``(embedding(latent), latent, logqp)``.
     Default method ``'srk'`` (:107-109); ``adjoint_method`` / ``options`` are accepted and ignored (fixed-step solve;
-    gradients come from the engine's own reverse sweep, method ``'euler'``)."""
+    gradients come from the engine's own reverse sweep of the discrete solve, not from a backward SDE)."""
     coeffs = _cat_coeffs(coeffs)
     eng = {k: kwargs.pop(k) for k in _ENGINE_KW if k in kwargs}
     method = kwargs.pop("method", None) or "srk"

@@ -330,5 +330,22 @@ def test_training_step_through_the_patched_latent_forward(dev):
         scale = max(float(want.abs().max()), 1e-6)
         err = float((p.grad.cpu().double() - want).abs().max())
         assert err <= 1e-4 * scale, f"{name}: {err:.3e} vs scale {scale:.3g}"
-    with pytest.raises(RuntimeError, match="euler"):               # default 'srk' has no backward: refuse, never drop gradients
-        mg(coeffs.to(dev), times.to(dev))
+    # the reference's default method ('srk', latent_sde.py:107-109) trains too: reverse sweep of the SRK solve
+    # (increments scaled per step: the linspace grid ends in a sliver step of ~1e-7, where an O(sqrt(dt)) increment would make
+    # the SRK weights I_kkk / h cancel catastrophically in fp32 - in torchsde as much as here)
+    h = torch.tensor([b - a for a, b in solver.step_times(times, solver.solver_dt(times))]).view(-1, 1, 1)
+    dW = torch.randn(S, B, H) * h.sqrt()
+    dU = h * (dW / 2 + torch.randn(S, B, H) * (h / 12).sqrt())
+    mo2 = copy.deepcopy(m).double()
+    pred, _, logqp = mo2(coeffs.double(), times.double(), bm=solver.BrownianTable(dW.double(), dU=dU.double()), with_grad=True)
+    ((pred - target.double()).pow(2).mean() + 0.1 * logqp).backward()
+    mg.zero_grad(set_to_none=True)
+    predg, _, logqpg = mg(coeffs.to(dev), times.to(dev), bm=snsde_b200.BrownianIncrements(dW.to(dev), dU.to(dev)))
+    close(predg, pred.float(), 1e-4, "pred (srk)")
+    ((predg - target.to(dev)).pow(2).mean() + 0.1 * logqpg).backward()
+    named_o = dict(mo2.named_parameters())
+    for name, p in mg.named_parameters():
+        want = named_o[name].grad
+        scale = max(float(want.abs().max()), 1e-6)
+        err = float((p.grad.cpu().double() - want).abs().max())
+        assert err <= 1e-4 * scale, f"srk {name}: {err:.3e} vs scale {scale:.3g}"

@@ -135,15 +135,88 @@ def test_milstein_backward_matches_autograd_through_the_oracle(io, no, H, C, L, 
         grad_close(p.grad, want, name, rtol=5e-4 if want.numel() == 1 else 1e-4)
 
 
-def test_milstein_backward_refuses_noise_networks_and_srk_has_no_backward(dev):
+def test_milstein_backward_refuses_noise_networks(dev):
     m, times, coeffs, y0 = make_problem(3, 18, 4, 16, 3, 1, 5, seed=1)
     mg = m.to(dev)
     mg.set_X(coeffs.to(dev), times.to(dev))
-    for method in ("milstein", "srk"):
-        with pytest.raises(RuntimeError, match="backward"):
-            snsde_b200.sdeint(mg, y0.to(dev).requires_grad_(True), times.to(dev), dt=1.0, method=method, seed=1)
+    with pytest.raises(RuntimeError, match="backward"):          # never drops gradients silently
+        snsde_b200.sdeint(mg, y0.to(dev).requires_grad_(True), times.to(dev), dt=1.0, method="milstein", seed=1)
     with torch.no_grad():                      # inference is unaffected
         snsde_b200.sdeint(mg, y0.to(dev), times.to(dev), dt=1.0, method="milstein", seed=1)
+
+
+SRK_BWD_CASES = [
+    # family, io, no, H, C, L, B, K     the torch-ists default method under autograd: three drift and four diffusion sites per step
+    ("benchmark", 4, 17, 32, 5, 1, 9, 7), ("benchmark", 6, 17, 32, 5, 2, 8, 6), ("benchmark", 2, 16, 32, 4, 1, 8, 6),
+    ("benchmark", 3, 18, 32, 3, 1, 7, 6), ("benchmark", 1, 19, 32, 3, 2, 7, 6), ("benchmark", 1, 14, 16, 3, 1, 8, 5),
+    ("benchmark", 4, 15, 16, 4, 1, 8, 5), ("benchmark", 0, 5, 16, 4, 2, 8, 5), ("benchmark", 5, 6, 32, 3, 1, 8, 5),
+    ("benchmark", 6, 3, 16, 3, 1, 8, 5), ("benchmark", 1, 9, 16, 3, 1, 8, 5), ("benchmark", 1, 0, 16, 3, 1, 8, 5),
+    ("benchmark", 4, 17, 128, 10, 1, 8, 5), ("benchmark", 3, 18, 64, 3, 1, 6, 5), ("tutorial", 0, 0, 32, 2, 1, 8, 6),
+]
+
+
+@pytest.mark.parametrize("family,io,no,H,C,L,B,K", SRK_BWD_CASES)
+def test_srk_backward_matches_autograd_through_the_oracle(family, io, no, H, C, L, B, K, dev):
+    """Method 'srk' under autograd on the torch-ists grid (linspace knots, sliver last step): dL/dz0 and dL/d(every
+    parameter) against fp64 autograd through the oracle's srk_step on identical (dW, U)."""
+    m, _, _, y0 = make_problem(io, no, B, H, C, L, K, seed=400 + io * 20 + no, family=family)
+    times = torch.linspace(0, 1, K)
+    x = (torch.randn(B, K, C, generator=torch.Generator().manual_seed(1)) * 0.2).cumsum(1)
+    coeffs = spline.hermite_cubic_coefficients_with_backward_differences(x, times)
+    dt = solver.solver_dt(times)
+    steps = solver.step_times(times, dt)
+    S = len(steps)
+    g = torch.Generator().manual_seed(13)
+    h = torch.tensor([b - a for a, b in steps]).view(S, 1, 1)
+    dW = torch.randn(S, B, H, generator=g) * h.sqrt()
+    dU = h * (0.5 * dW + torch.randn(S, B, H, generator=g) * (h / 12).sqrt())
+    ts = torch.cat([times[:1], times[2:3], (times[2:3] + times[3:4]) / 2, times[-1:]])
+    w = torch.randn(len(ts), B, H, generator=g)
+    mo = copy.deepcopy(m).double()
+    mo.set_X(coeffs.double(), times.double())
+    y0o = y0.double().requires_grad_(True)
+    zo = solver.sdeint_with_grad(mo, y0o, ts.double(), dt, solver.BrownianTable(dW.double(), dU=dU.double()), method="srk")
+    (zo * w.double()).sum().backward()
+    mg = copy.deepcopy(m).to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    y0g = y0.to(dev).requires_grad_(True)
+    zg = snsde_b200.sdeint(mg, y0g, ts.to(dev), dt=dt, method="srk", bm=snsde_b200.BrownianIncrements(dW.to(dev), dU.to(dev)),
+                           precision="fp32")
+    assert zg.requires_grad
+    close(zg, zo.float())
+    (zg * w.to(dev)).sum().backward()
+    grad_close(y0g.grad, y0o.grad, "y0")
+    named_o = dict(mo.named_parameters())
+    for name, p in mg.named_parameters():
+        want = named_o[name].grad
+        if want is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        grad_close(p.grad, want, name, rtol=5e-4 if want.numel() == 1 else 1e-4)
+
+
+def test_srk_backward_philox_replay_equals_the_table(dev):
+    """In-kernel increments: the reverse sweep regenerates dW and the Levy integrals from the two Philox streams."""
+    m, times, coeffs, y0 = make_problem(4, 17, 10, 32, 4, 1, 9, seed=21, spacing=0.25)
+    mg = m.to(dev)
+    mg.set_X(coeffs.to(dev), times.to(dev))
+    grads = []
+    for mode in ("philox", "table"):
+        mg.zero_grad(set_to_none=True)
+        y0g = y0.to(dev).requires_grad_(True)
+        if mode == "philox":
+            z = snsde_b200.sdeint(mg, y0g, times.to(dev), dt=0.25, method="srk", seed=5, precision="fp32")
+        else:
+            plan = snsde_b200.plans_of(mg)[("srk", "fp32", str(dev))]
+            dW, dU = snsde_b200.philox_increments(5, plan.step_plan(times, 0.25, times), 10, 32, dev, with_U=True)
+            z = snsde_b200.sdeint(mg, y0g, times.to(dev), dt=0.25, method="srk", bm=snsde_b200.BrownianIncrements(dW, dU),
+                                  precision="fp32")
+        z[-1].pow(2).sum().backward()
+        grads.append((y0g.grad.clone(), mg.linear_out.weight.grad.clone(), mg.noise_t[0].weight.grad.clone()))
+    assert torch.equal(grads[0][0], grads[1][0])                      # same increments, same arithmetic
+    for a, b in zip(*grads):                                           # (atomics order the coefficient-network sums)
+        grad_close(a, b, "philox replay vs table", rtol=1e-5)
 
 
 def test_backward_through_fused_final_index_and_philox_replay(dev):
