@@ -288,3 +288,56 @@ def test_committed_conditioning_evidence_is_consistent():
     assert ev["c3"]["max_rel"] > 1e-3 and ev["c3"]["median_rel"] < 1e-6          # ill-conditioned in rare elements only
     assert all(v["max_rel_first_24_steps"] < 1e-5 for v in ev.values())
     assert ev["c2"]["max_rel"] < 1e-4
+
+
+def test_srk_reverse_sweep_site_order_and_coefficients():
+    """The reverse of one SRID2 step as csrc/snsde_bwd_srk.cu performs it - stage states recomputed, the six evaluation
+    sites visited in the order g3, g2, f2, g1, f1, (f0, g0), J^T products scattered with the transposed tableau
+    coefficients - against autograd through the oracle's srk_step (fp64, a state-dependent drift and diffusion)."""
+    torch.manual_seed(5)
+    B, H = 3, 4
+    A, Bm = torch.randn(H, H, dtype=torch.float64) * 0.5, torch.randn(H, H, dtype=torch.float64) * 0.3
+
+    class Sde:
+        sde_type, noise_type = "ito", "diagonal"
+        def f(self, t, y): return torch.tanh(y @ A.T + torch.sin(t))
+        def g(self, t, y): return torch.tanh(0.7 * (y @ Bm.T) * torch.cos(t))
+    sde = Sde()
+    t0, t1 = torch.tensor(0.3, dtype=torch.float64), torch.tensor(0.55, dtype=torch.float64)
+    h = t1 - t0
+    sq = h.sqrt()
+    W = torch.randn(B, H, dtype=torch.float64) * sq
+    U = h * (W / 2 + torch.randn(B, H, dtype=torch.float64) * (h / 12).sqrt())
+    y0 = torch.randn(B, H, dtype=torch.float64, requires_grad=True)
+    lam = torch.randn(B, H, dtype=torch.float64)
+    y1 = solver.srk_step(sde, solver.BrownianTable(W[None], dU=U[None]), t0, t1, y0)
+    (want,) = torch.autograd.grad(y1, y0, grad_outputs=lam)
+
+    def vjp(fn, t, z, cot):                      # J(z)^T cot of one evaluation site
+        z = z.detach().requires_grad_(True)
+        (out,) = torch.autograd.grad(fn(t, z), z, grad_outputs=cot)
+        return out
+    with torch.no_grad():
+        y = y0.detach()
+        tq, th = t0 + 0.25 * h, t0 + 0.5 * h
+        f0, g0 = sde.f(t0, y), sde.g(t0, y)
+        H01 = y + f0 * h
+        H11 = y + 0.25 * f0 * h - 0.5 * g0 * sq
+        f1, g1 = sde.f(t1, H01), sde.g(tq, H11)
+        H02 = y + 0.25 * f0 * h + g0 * U / h + 0.25 * f1 * h + 0.5 * g1 * U / h
+        H12 = y + f0 * h + g0 * sq
+        f2, g2 = sde.f(th, H02), sde.g(t1, H12)
+        H13 = y + 2 * g0 * sq - g1 * sq + 0.25 * f2 * h + 0.5 * g2 * sq
+        Ikk, Ikkk = (W ** 2 - h) / 2, (W ** 3 - 3 * h * W) / 6
+        c0, c1, c2 = Ikk / sq, U / h, Ikkk / h
+        gw = [-W + c0 + 2 * c1 - 2 * c2, 4 / 3 * W - 4 / 3 * c0 - 4 / 3 * c1 + 5 / 3 * c2, 2 / 3 * W + c0 / 3 - 2 / 3 * c1 - 2 / 3 * c2, c2]
+    yb = lam.clone()
+    fb = [lam * h / 6, lam * h / 6, lam * 2 * h / 3]
+    gb = [lam * gw[0], lam * gw[1], lam * gw[2], lam * gw[3]]
+    z = vjp(sde.g, tq, H13, gb[3]); yb += z; gb[0] = gb[0] + 2 * sq * z; gb[1] = gb[1] - sq * z; fb[2] = fb[2] + 0.25 * h * z; gb[2] = gb[2] + 0.5 * sq * z
+    z = vjp(sde.g, t1, H12, gb[2]); yb += z; fb[0] = fb[0] + h * z; gb[0] = gb[0] + sq * z
+    z = vjp(sde.f, th, H02, fb[2]); yb += z; fb[0] = fb[0] + 0.25 * h * z; gb[0] = gb[0] + U / h * z; fb[1] = fb[1] + 0.25 * h * z; gb[1] = gb[1] + 0.5 * U / h * z
+    z = vjp(sde.g, tq, H11, gb[1]); yb += z; fb[0] = fb[0] + 0.25 * h * z; gb[0] = gb[0] - 0.5 * sq * z
+    z = vjp(sde.f, t1, H01, fb[1]); yb += z; fb[0] = fb[0] + h * z
+    yb += vjp(sde.f, t0, y, fb[0]) + vjp(sde.g, t0, y, gb[0])
+    assert torch.allclose(yb, want, rtol=1e-10, atol=1e-12)
