@@ -341,3 +341,42 @@ def test_srk_reverse_sweep_site_order_and_coefficients():
     z = vjp(sde.f, t1, H01, fb[1]); yb += z; fb[0] = fb[0] + h * z
     yb += vjp(sde.f, t0, y, fb[0]) + vjp(sde.g, t0, y, gb[0])
     assert torch.allclose(yb, want, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["MU_Y", "MU_TY", "SQRT", "CUBE", "SIGMOID", "RELU"])
+@pytest.mark.parametrize("bounded", [True, False])
+def test_milstein_term_closed_form_cotangents(kind, bounded):
+    """The closed forms of csrc/snsde_math.cuh `milstein_backward` (cotangents of T = 0.5 v g dg/dy w.r.t. y, the
+    coefficient and sigmoid(theta), through BOTH factors as torchsde's create_graph vjp differentiates them) against
+    double autograd, for every state-dependent elementwise diffusion of neuralsde.py:233-307."""
+    torch.manual_seed(0)
+    y = (torch.rand(6, dtype=torch.float64) + 0.3).requires_grad_(True)
+    coef = torch.randn(6, dtype=torch.float64).requires_grad_(True)
+    s = torch.tensor(0.7, dtype=torch.float64, requires_grad=True)
+    tt, v = 1.3, torch.randn(6, dtype=torch.float64)
+    raw = {"MU_Y": lambda: coef * y, "MU_TY": lambda: tt * y, "SQRT": lambda: y.sqrt(), "CUBE": lambda: y ** 3,
+           "SIGMOID": lambda: torch.sigmoid(y), "RELU": lambda: torch.relu(y)}[kind]()
+    g = torch.tanh(s * torch.nan_to_num(raw)) if bounded else raw
+    (gdg,) = torch.autograd.grad(g, y, grad_outputs=g * v, create_graph=True)
+    ay, ac, as_ = torch.autograd.grad((0.5 * gdg).sum(), (y, coef, s), allow_unused=True)
+    # ---- the device function, transcribed ----
+    yd, cd, sd = y.detach(), coef.detach(), s.detach()
+    r2 = rc = r1c = torch.zeros_like(yd)
+    if kind == "MU_Y": rw, r1, rc, r1c = cd * yd, cd, yd, torch.ones_like(yd)
+    elif kind == "MU_TY": rw, r1 = tt * yd, torch.full_like(yd, tt)
+    elif kind == "SQRT": rw = yd.sqrt(); r1 = 0.5 / rw; r2 = -0.25 / (rw * yd)
+    elif kind == "CUBE": rw, r1, r2 = yd ** 3, 3 * yd * yd, 6 * yd
+    elif kind == "SIGMOID": rw = 1 / (1 + torch.exp(-yd)); r1 = rw * (1 - rw); r2 = r1 * (1 - 2 * rw)
+    else: rw, r1 = torch.relu(yd), (yd > 0).double()
+    hv = 0.5 * v
+    if bounded:
+        gd = torch.tanh(sd * rw); q = 1 - gd * gd
+        g1 = q * sd * r1; g2 = -2 * gd * g1 * sd * r1 + q * sd * r2
+        gc = q * sd * rc; g1c = -2 * gd * gc * sd * r1 + q * sd * r1c
+        gs = q * rw; g1s = -2 * gd * gs * sd * r1 + q * r1
+        my, mc, ms = hv * (g1 * g1 + gd * g2), hv * (gc * g1 + gd * g1c), (hv * (gs * g1 + gd * g1s)).sum()
+    else:
+        my, mc, ms = hv * (r1 * r1 + rw * r2), hv * (rc * r1 + rw * r1c), torch.tensor(0.0, dtype=torch.float64)
+    assert torch.allclose(ay, my, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(ac if ac is not None else torch.zeros_like(mc), mc, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(as_ if as_ is not None else torch.tensor(0.0, dtype=torch.float64), ms, rtol=1e-10, atol=1e-12)
