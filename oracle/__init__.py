@@ -11,8 +11,11 @@ reference hot path ``torchsde.sdeint(Diffusion_model, ...)``:
                             (reference benchmark_classification/models_sde/neuralsde.py:123-307)
                             and the tutorial ``NeuralLSDEFunc``.
 * ``oracle.solver``       - torchsde 0.2.5 fixed-step ``integrate`` + ``Euler.step`` +
-                            diagonal Ito ``Milstein.step`` + explicit-increment
-                            Brownian source.
+                            diagonal Ito ``Milstein.step`` (vjp with ``create_graph`` under
+                            autograd, as ``ForwardSDE.gdg_prod_diagonal`` takes it) +
+                            ``SRK.diagonal_or_scalar_step`` (SRID2) + ``names=`` remapping +
+                            explicit-increment Brownian source; ``sdeint_with_grad`` leaves
+                            autograd on (the oracle of the engine's backward passes).
 * ``oracle.latent``       - the LatentSDE augmented system ``f_aug``/``g_aug`` and its forward
                             (reference torch-ists/torch_ists/diff_module/NSDE/latent_sde.py:24-147).
 * ``oracle.philox``       - numpy replica of the Philox4x32-10 counter RNG bits.

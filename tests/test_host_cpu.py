@@ -332,3 +332,21 @@ def test_bench_algorithmic_costs_match_the_survey_contract():
     assert abs(bench.alg_bytes_per_sde_step(bench.WORKLOADS["c2"], 1) - (560 + 4 * 128 * 2 / 200)) < 1e-9
     assert bench.alg_bytes_per_sde_step(bench.WORKLOADS["c4"], 2) < 16          # input option 3 never reads X(t)
     assert abs(bench.alg_bytes_per_sde_step(bench.WORKLOADS["c5"], 10) - (224 + 4 * 256 * 11 / 500)) < 1e-9
+
+
+def test_control_at_equals_the_spline_read_and_carries_gradients():
+    """engine._control_at (the torch-op spline read the training path of the patched LatentSDE.forward uses,
+    latent_sde.py:100-101) equals CubicSpline.evaluate at knots, inside intervals and when clamped outside the grid."""
+    from snsde_b200 import engine
+    from oracle import spline
+    torch.manual_seed(2)
+    B, K, C = 3, 6, 4
+    times = torch.cat([torch.zeros(1), torch.rand(K - 1) + 0.2]).cumsum(0)
+    x = torch.randn(B, K, C)
+    coeffs = spline.hermite_cubic_coefficients_with_backward_differences(x, times).requires_grad_(True)
+    X = spline.CubicSpline(coeffs.detach(), times)
+    for t in (times[0], times[2], (times[2] + times[3]) / 2, times[-1], times[0] - 0.3, times[-1] + 0.4):
+        got = engine._control_at(coeffs, times, t)
+        assert torch.allclose(got, X.evaluate(t), rtol=1e-6, atol=1e-6)
+    engine._control_at(coeffs, times, times[0]).sum().backward()
+    assert coeffs.grad is not None and float(coeffs.grad[:, 0, :C].abs().sum()) == B * C       # X(t0) = a of interval 0
