@@ -152,6 +152,8 @@ SRK_BWD_CASES = [
     ("benchmark", 4, 15, 16, 4, 1, 8, 5), ("benchmark", 0, 5, 16, 4, 2, 8, 5), ("benchmark", 5, 6, 32, 3, 1, 8, 5),
     ("benchmark", 6, 3, 16, 3, 1, 8, 5), ("benchmark", 1, 9, 16, 3, 1, 8, 5), ("benchmark", 1, 0, 16, 3, 1, 8, 5),
     ("benchmark", 4, 17, 128, 10, 1, 8, 5), ("benchmark", 3, 18, 64, 3, 1, 6, 5), ("tutorial", 0, 0, 32, 2, 1, 8, 6),
+    # enough rows for 4-row groups (the launch shape of real batches), ragged last group
+    ("benchmark", 4, 17, 32, 4, 1, 322, 5), ("benchmark", 3, 18, 32, 3, 1, 301, 5), ("benchmark", 6, 17, 128, 6, 1, 90, 4),
 ]
 
 
