@@ -263,27 +263,35 @@ def test_philox_replay_is_bit_identical_and_the_kl_channel_sees_no_noise(dev):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("C,H,HH,L,B,K", [(3, 9, 12, 2, 7, 6), (2, 33, 40, 1, 10, 5), (2, 70, 64, 3, 6, 5)])
-def test_backward_matches_autograd_through_the_oracle(C, H, HH, L, B, K, dev):
-    """Euler: dL/d(aug_y0) and dL/d(every drift parameter) with L mixing latent states and the KL accumulator."""
+@pytest.mark.parametrize("C,H,HH,L,B,K,method", [
+    (3, 9, 12, 2, 7, 6, "euler"), (2, 33, 40, 1, 10, 5, "euler"), (2, 70, 64, 3, 6, 5, "euler"),
+    (3, 9, 12, 2, 7, 6, "srk"), (2, 33, 40, 1, 10, 5, "srk"),
+    # enough rows for 4-row groups in the reverse sweeps (one and two warps per group), ragged last group
+    (2, 9, 12, 1, 330, 5, "euler"), (2, 9, 12, 1, 330, 5, "srk"), (3, 33, 40, 1, 161, 4, "srk")])
+def test_backward_matches_autograd_through_the_oracle(C, H, HH, L, B, K, method, dev):
+    """dL/d(aug_y0) and dL/d(every drift parameter) with L mixing latent states and the KL accumulator."""
     torch.manual_seed(40 + H)
     m = olatent.LatentSDE(C, H, HH, L, theta=1.1, mu=0.15, sigma=0.5)
     times = torch.linspace(0, 1, K)
     dt = solver.solver_dt(times)
-    S = len(solver.step_times(times, dt))
-    dW = torch.randn(S, B, H) * dt ** 0.5
+    steps = solver.step_times(times, dt)
+    S = len(steps)
+    h = torch.tensor([b - a for a, b in steps]).view(S, 1, 1)
+    dW = torch.randn(S, B, H) * h.sqrt()
+    dU = h * (dW / 2 + torch.randn(S, B, H) * (h / 12).sqrt())
     y0 = torch.cat([torch.randn(B, H - 1) * 0.5, torch.zeros(B, 1)], 1)
     w = torch.randn(K, B, H)
     mo = copy.deepcopy(m).double()
     y0o = y0.double().requires_grad_(True)
-    zo = solver.sdeint_with_grad(mo, y0o, times.double(), dt, solver.BrownianTable(dW.double()), method="euler", names=olatent.NAMES)
+    zo = solver.sdeint_with_grad(mo, y0o, times.double(), dt, solver.BrownianTable(dW.double(), dU=dU.double()), method=method,
+                                 names=olatent.NAMES)
     ((zo * w.double()).sum() + 3.0 * zo[-1, :, -1].mean()).backward()
     mg = LatentSDEParams(C, H, HH, L)
     mg.load_state_dict(m.state_dict())
     mg = mg.to(dev)
     y0g = y0.to(dev).requires_grad_(True)
-    zg = snsde_b200.sdeint(mg, y0g, times.to(dev), dt=dt, method="euler", names=olatent.NAMES,
-                           bm=snsde_b200.BrownianIncrements(dW.to(dev)))
+    zg = snsde_b200.sdeint(mg, y0g, times.to(dev), dt=dt, method=method, names=olatent.NAMES,
+                           bm=snsde_b200.BrownianIncrements(dW.to(dev), dU.to(dev)))
     close(zg, zo.float(), 1e-4, "states under autograd")
     ((zg * w.to(dev)).sum() + 3.0 * zg[-1, :, -1].mean()).backward()
 
