@@ -82,7 +82,81 @@ def srk_points(steps, knots=None):
     return np.ascontiguousarray(pts)
 
 
+def _step_grid(ts, dt32):
+    """Step boundaries ``b[0..S]`` of torchsde's fixed-step loop in float32: ``b[k+1] = min(fl32(b[k] + dt), ts[-1])`` until
+    ``ts[-1]`` is reached.  ``np.add.accumulate`` on float32 adds sequentially, i.e. exactly like the loop."""
+    first, last = ts[0], ts[-1]
+    parts, curr, total = [], first, 0
+    while True:                                               # chunks of <= 2^20 steps (a restart from `curr` continues the same sums)
+        est = (float(last) - float(curr)) / float(dt32)
+        n = int(min(max(np.ceil(est) + 2, 2), 1 << 20))
+        arr = np.full(n + 1, dt32, dtype=np.float32)
+        arr[0] = curr
+        grid = np.add.accumulate(arr, dtype=np.float32)
+        hit = np.nonzero(grid >= last)[0]
+        end = int(hit[0]) if hit.size else n
+        if end and not np.all(grid[1:end + 1] > grid[:end]):
+            raise ValueError("dt is too small to advance float32 time")
+        parts.append(grid[:end] if hit.size else grid[:n])
+        total += end
+        if hit.size:
+            break
+        if total > (1 << 26):
+            raise ValueError("more than 2^26 solver steps between ts[0] and ts[-1]")
+        curr = grid[n]
+    b = np.concatenate(parts + [np.asarray([last], dtype=np.float32)])
+    return b
+
+
 def build_step_plan(ts, dt, knots=None, method="euler"):
+    """Float32 replay of torchsde's ``BaseSDESolver.integrate`` bookkeeping (``next_t = min(curr_t + dt, ts[-1])``,
+    ``while curr_t < out_t``, linear interpolation of the two states bracketing an output time), vectorised: the grid is a
+    sequential float32 accumulation, an output time belongs to the first step that reaches it."""
+    ts = np.ascontiguousarray(ts, dtype=np.float32).reshape(-1)
+    if ts.size < 1:
+        raise ValueError("ts must hold at least one time")
+    if ts.size > 1 and not np.all(ts[1:] > ts[:-1]):
+        raise ValueError("Evaluation times `ts` must be strictly increasing.")
+    if not dt > 0:
+        raise ValueError("dt must be positive")
+    dt32 = np.float32(dt)
+    n_out = int(ts.size)
+    em = np.zeros(n_out, dtype=EMIT_DTYPE)
+    em["slot"] = np.arange(n_out, dtype=np.int32)
+    em["w_curr"][0] = 1.0
+    if n_out == 1:
+        steps = np.zeros(0, dtype=STEP_DTYPE)
+    else:
+        b = _step_grid(ts, dt32)
+        S = b.size - 1
+        t0, t1 = b[:-1], b[1:]
+        out_t = ts[1:]
+        k = np.searchsorted(t1, out_t, side="left")              # the step whose end first reaches the output time
+        prev, curr = t0[k], t1[k]
+        span = (curr - prev).astype(np.float32)
+        em["w_prev"][1:] = (curr - out_t).astype(np.float32) / span
+        em["w_curr"][1:] = (out_t - prev).astype(np.float32) / span
+        steps = np.zeros(S, dtype=STEP_DTYPE)
+        steps["t0"] = t0
+        steps["h"] = t1 - t0
+        steps["sqrt_h"] = np.sqrt(steps["h"])
+        steps["sin_t0"] = np.sin(t0)
+        steps["cos_t0"] = np.cos(t0)
+        idx_steps = np.arange(S)
+        steps["emit_begin"] = 1 + np.searchsorted(k, idx_steps, side="left")     # emits are ordered by their step
+        steps["emit_end"] = 1 + np.searchsorted(k, idx_steps, side="right")
+        if knots is not None:
+            knots = np.ascontiguousarray(knots, dtype=np.float32).reshape(-1)
+            idx = np.clip(np.searchsorted(knots, t0, side="left") - 1, 0, knots.size - 2)
+            steps["interval"] = idx
+            steps["frac"] = t0 - knots[idx]
+    points = srk_points(steps, knots) if method == "srk" else None
+    return StepPlan(steps, em, 1, n_out, 0 if knots is None else int(np.size(knots)), points)
+
+
+def build_step_plan_loop(ts, dt, knots=None, method="euler"):
+    """The same plan built step by step, statement for statement like the solver loop (kept as the checker of the
+    vectorised builder, tests/test_host_cpu.py)."""
     ts = np.ascontiguousarray(ts, dtype=np.float32).reshape(-1)
     if ts.size < 1:
         raise ValueError("ts must hold at least one time")

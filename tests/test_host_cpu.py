@@ -350,3 +350,36 @@ def test_control_at_equals_the_spline_read_and_carries_gradients():
         assert torch.allclose(got, X.evaluate(t), rtol=1e-6, atol=1e-6)
     engine._control_at(coeffs, times, times[0]).sum().backward()
     assert coeffs.grad is not None and float(coeffs.grad[:, 0, :C].abs().sum()) == B * C       # X(t0) = a of interval 0
+
+
+def test_vectorised_step_plan_is_bit_identical_to_the_loop():
+    """stepplan.build_step_plan (sequential float32 accumulation + searchsorted) against the statement-for-statement
+    loop, over integer / linspace (sliver last step) / irregular grids, dt below and above the knot spacing, output
+    times on and between knots, both methods."""
+    from snsde_b200 import stepplan as sp
+    rng = np.random.default_rng(0)
+    n = 0
+    for trial in range(600):
+        kind = trial % 5
+        K = int(rng.integers(2, 60))
+        if kind == 0: knots = np.arange(K, dtype=np.float32)
+        elif kind == 1: knots = np.linspace(0, 1, K).astype(np.float32)
+        elif kind == 2: knots = np.cumsum(np.concatenate([[rng.normal()], rng.random(K - 1) + 0.05])).astype(np.float32)
+        elif kind == 3: knots = (np.arange(K) * 0.25 + 3).astype(np.float32)
+        else: knots = np.linspace(-2, 5, K).astype(np.float32)
+        dmin = float((knots[1:] - knots[:-1]).min())
+        dt = [max(dmin, 1e-3), dmin * 0.37, dmin * 2.3, 1e-3 if dmin < 0.2 else 0.05][trial % 4]
+        ts = knots[np.sort(rng.choice(K, size=int(rng.integers(1, K + 1)), replace=False))]
+        if trial % 7 == 0 and len(ts) > 2:
+            ts = np.unique(np.concatenate([ts, (ts[:-1] + ts[1:]) / 2])).astype(np.float32)
+        for method in ("euler", "srk"):
+            a, b = sp.build_step_plan(ts, dt, knots, method=method), sp.build_step_plan_loop(ts, dt, knots, method=method)
+            assert (a.n_out, a.n_init_emits, a.n_knots) == (b.n_out, b.n_init_emits, b.n_knots)
+            assert a.steps.tobytes() == b.steps.tobytes() and a.emits.tobytes() == b.emits.tobytes()
+            assert (a.points is None) == (b.points is None) and (a.points is None or a.points.tobytes() == b.points.tobytes())
+            n += 1
+    assert n == 1200
+    for bad in (lambda: sp.build_step_plan(np.float32([16777216, 16777300]), 0.5),       # fl32(2^24 + 0.5) == 2^24: no advance
+                lambda: sp.build_step_plan(np.float32([0, 1]), 0.0)):
+        with pytest.raises(ValueError):
+            bad()
